@@ -1,0 +1,188 @@
+"""Mint the committed golden fixtures under tests/golden/ from the PATCHED REFERENCE ITSELF.
+
+Run in the build container only (needs /root/reference):   python -m oracle.make_golden
+
+The reference has no tests or golden vectors of its own, so these files are the
+parity pin: inputs and outputs of /root/reference/EM-EVRP (patches P1+P2, oracle/ref_shim.py)
+executed on CPU with torch fp32.  Files:
+
+  weights_seed0.npz        state_dict of AttentionModel built after torch.manual_seed(0)
+                           (trainer.py:261-272 kwargs), plus a BatchNorm perturbation recipe flag
+  greedy_n{20,50,100}.npz  instances (VehicleRoutingDataset seed 12345) + greedy eval-mode rollout:
+                           pi, ll, R and the per-step trace (mask fed to the step, log_p, dynamic
+                           after the step)
+  greedy_bn_n20.npz        same with non-trivial BatchNorm running stats / affine (perturb_bn)
+  sample_n20.npz           sampled rollout (actions recorded) + teacher-forced REINFORCE gradients of
+                           all 50 parameters, eval-mode BN and train-mode BN
+  dm_n20.npz               DM objective: reward := distance (DM-EVRP/problems/EVRP.py:231,280)
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_shim  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def perturb_bn(sd, seed=7):
+    """Deterministic (numpy) non-trivial BatchNorm statistics/affine; works on any state_dict with
+    the reference's keys.  Returns a new dict of torch tensors."""
+    rs = np.random.RandomState(seed)
+    out = {}
+    for k, v in sd.items():
+        v = v.clone()
+        if "normalizer.running_mean" in k:
+            v = torch.from_numpy((rs.randn(*v.shape) * 0.2).astype(np.float32))
+        elif "normalizer.running_var" in k:
+            v = torch.from_numpy((rs.rand(*v.shape) * 1.5 + 0.5).astype(np.float32))
+        elif "normalizer.weight" in k:
+            v = torch.from_numpy((rs.rand(*v.shape) + 0.5).astype(np.float32))
+        elif "normalizer.bias" in k:
+            v = torch.from_numpy((rs.randn(*v.shape) * 0.1).astype(np.float32))
+        out[k] = v
+    return out
+
+
+class Tracer:
+    """Records per-step tensors by wrapping the model's injected callbacks (plain attributes,
+    nets/DRLModel.py:67-68) and _get_log_p."""
+
+    def __init__(self, m):
+        self.m = m
+        self.masks, self.logps, self.dyns, self.dist = [], [], [], []
+        self._ud, self._glp = m.update_dynamic, m._get_log_p
+        m.update_dynamic = self.ud
+        m._get_log_p = self.glp
+
+    def ud(self, dynamic, distances, slope, now, chosen):
+        ar = torch.arange(distances.size(0))
+        self.dist.append(distances[ar, now, chosen].clone())
+        nd, r = self._ud(dynamic, distances, slope, now, chosen)
+        self.dyns.append(nd.clone())
+        return nd, r
+
+    def glp(self, fixed, now_idx, mask, route_feature, embeddings):
+        self.masks.append(mask.clone())
+        lp = self._glp(fixed, now_idx, mask, route_feature, embeddings)
+        self.logps.append(lp[:, 0, :].detach().clone())
+        return lp
+
+    def close(self):
+        self.m.update_dynamic, self.m._get_log_p = self._ud, self._glp
+
+    def arrays(self):
+        return dict(t_mask=torch.stack(self.masks, 1).numpy().astype(np.uint8),
+                    t_log_p=torch.stack(self.logps, 1).numpy(),
+                    t_dynamic=torch.stack(self.dyns, 1).numpy(),
+                    t_dist=torch.stack(self.dist, 1).numpy())
+
+
+def batch_of(ds, B):
+    return next(iter(DataLoader(ds, B, False)))
+
+
+def inputs_dict(ds, bat, B):
+    static, dynamic, D, G = bat
+    return dict(static=static.numpy().astype(np.float32), dynamic=dynamic.numpy().astype(np.float32),
+                elevation=ds.Elevation[:B].numpy().astype(np.float32),
+                distances=D.numpy(), slope=G.numpy())
+
+
+def greedy_fixture(name, N, B, seed=12345, bn=False):
+    ds, args = ref_shim.make_dataset(B, N, seed)
+    m = ref_shim.make_model(ds, args, 0)
+    if bn:
+        m.load_state_dict(perturb_bn(m.state_dict()))
+    m.eval(); m.set_decode_type("greedy")
+    bat = batch_of(ds, B)
+    tr = Tracer(m)
+    with torch.no_grad():
+        pi, ll, R = m(bat)
+    tr.close()
+    d = inputs_dict(ds, bat, B)
+    d.update(pi=pi.numpy(), ll=ll.numpy(), R=R.numpy(), bn_perturbed=np.array(bn), **tr.arrays())
+    np.savez_compressed(os.path.join(OUT, name), **d)
+    print(name, "T=", pi.shape[1], "mean cost", float(R.sum(1).mean()))
+
+
+def teacher_forced_grads(m, bat, pi, adv):
+    """REINFORCE gradient with the reference's own forward, actions forced to ``pi``
+    (trainer.py:115-124 with _select_node patched)."""
+    it = iter(pi.t())
+    orig = m._select_node
+    m._select_node = lambda probs, mask: next(it)
+    m.zero_grad()
+    pi2, ll, R = m(bat)
+    m._select_node = orig
+    assert torch.equal(pi2, pi)
+    loss = (adv * ll.sum(1)).mean()
+    loss.backward()
+    return ll.detach(), R, float(loss), {k: p.grad.detach().clone() for k, p in m.named_parameters()}
+
+
+def sample_fixture(name, N, B, seed=12346):
+    ds, args = ref_shim.make_dataset(B, N, seed)
+    m = ref_shim.make_model(ds, args, 0)
+    m.load_state_dict(perturb_bn(m.state_dict()))
+    bat = batch_of(ds, B)
+    m.eval(); m.set_decode_type("sample")
+    torch.manual_seed(99)
+    with torch.no_grad():
+        pi, ll0, R = m(bat)
+    cost = R.sum(1)
+    adv = (cost - cost.mean()).detach()
+    d = inputs_dict(ds, bat, B)
+    d.update(pi=pi.numpy(), R=R.numpy(), adv=adv.numpy())
+    # eval-mode BN gradients
+    ll, R2, loss, g = teacher_forced_grads(m, bat, pi, adv)
+    assert torch.equal(R2, R)
+    d.update(ll_eval=ll.numpy(), loss_eval=np.array(loss))
+    d.update({"g_eval/" + k: v.numpy() for k, v in g.items()})
+    # train-mode BN gradients (batch statistics; running stats get updated as a side effect)
+    m.train()
+    ll, R3, loss, g = teacher_forced_grads(m, bat, pi, adv)
+    d.update(ll_train=ll.numpy(), loss_train=np.array(loss))
+    d.update({"g_train/" + k: v.numpy() for k, v in g.items()})
+    d.update({"bn_after/" + k: v.numpy() for k, v in m.state_dict().items() if "running" in k or "tracked" in k})
+    np.savez_compressed(os.path.join(OUT, name), **d)
+    print(name, "T=", pi.shape[1], "loss eval/train", float(d["loss_eval"]), float(d["loss_train"]))
+
+
+def dm_fixture(name, N, B, seed=12345):
+    """DM objective = EM dynamics + reward := distance."""
+    ds, args = ref_shim.make_dataset(B, N, seed)
+    m = ref_shim.make_model(ds, args, 0)
+    m.eval(); m.set_decode_type("greedy")
+    bat = batch_of(ds, B)
+    tr = Tracer(m)
+    with torch.no_grad():
+        pi, ll, R = m(bat)
+    tr.close()
+    d = inputs_dict(ds, bat, B)
+    a = tr.arrays()
+    d.update(pi=pi.numpy(), ll=ll.numpy(), E=R.numpy(), R=a["t_dist"])
+    np.savez_compressed(os.path.join(OUT, name), **d)
+    print(name, "T=", pi.shape[1], "mean distance", float(a["t_dist"].sum(1).mean()))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ds, args = ref_shim.make_dataset(2, 20, 1)
+    m = ref_shim.make_model(ds, args, 0)
+    np.savez_compressed(os.path.join(OUT, "weights_seed0.npz"),
+                        **{k: v.numpy() for k, v in m.state_dict().items()})
+    greedy_fixture("greedy_n20.npz", 20, 32)
+    greedy_fixture("greedy_bn_n20.npz", 20, 16, bn=True)
+    greedy_fixture("greedy_n50.npz", 50, 8)
+    greedy_fixture("greedy_n100.npz", 100, 6)
+    sample_fixture("sample_n20.npz", 20, 16)
+    dm_fixture("dm_n20.npz", 20, 8)
+
+
+if __name__ == "__main__":
+    main()

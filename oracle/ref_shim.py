@@ -1,0 +1,108 @@
+"""Import shim for the UNMODIFIED-but-patched reference (test infrastructure, container only).
+
+The reference tree (/root/reference/EM-EVRP) does not run as shipped (defects
+D1..D7).  This module makes a scratch copy under ``oracle/_ref/EM-EVRP`` (git-ignored; never
+committed — reference sources are not copied into history), applies the two one-line patches
+the survey documents, stubs the two missing third-party imports and puts the copy on sys.path:
+
+  P1  problems/EVRP.py:71   drop the duplicated ``depot_charging`` column so that the node
+                            layout is [depot, F stations, N customers] as every consumer assumes
+  P2  nets/DRLModel.py:224  ``.cuda()`` -> ``.to(device)`` so the DRL model runs on CPU
+  D3  utils/reinforce_baselines.py:6 imports ``nets.point_network`` -> alias to nets.PointNetwork
+  D7  stub ``matplotlib.pyplot`` and ``xlwt`` (not installed here)
+
+It is used ONLY by ``oracle/make_golden.py`` (to mint the committed fixtures) and by the
+``not gpu`` test that pins the numpy oracle against the live reference when /root/reference is
+present.  Nothing on the GPU box may import this file: /root/reference does not exist there.
+"""
+import os
+import shutil
+import sys
+import types
+
+REFERENCE_ROOT = "/root/reference/EM-EVRP"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SCRATCH = os.path.join(_HERE, "_ref", "EM-EVRP")
+
+
+def available() -> bool:
+    return os.path.isdir(REFERENCE_ROOT)
+
+
+def _patch(path, old, new):
+    with open(path) as f:
+        src = f.read()
+    if old not in src:
+        raise RuntimeError(f"patch anchor not found in {path}: {old!r}")
+    with open(path, "w") as f:
+        f.write(src.replace(old, new, 1))
+
+
+def prepare(force: bool = False) -> str:
+    """Create the patched scratch copy (idempotent). Returns its path."""
+    if not available():
+        raise RuntimeError("reference tree not present (this only works in the build container)")
+    marker = os.path.join(SCRATCH, ".patched")
+    if os.path.exists(marker) and not force:
+        return SCRATCH
+    if os.path.isdir(SCRATCH):
+        shutil.rmtree(SCRATCH)
+    os.makedirs(os.path.dirname(SCRATCH), exist_ok=True)
+    shutil.copytree(REFERENCE_ROOT, SCRATCH,
+                    ignore=shutil.ignore_patterns("__pycache__", "ExperimentalData", "BaselineAlgorithms"))
+    for root, _, files in os.walk(SCRATCH):
+        os.chmod(root, 0o755)
+        for fn in files:
+            os.chmod(os.path.join(root, fn), 0o644)
+    _patch(os.path.join(SCRATCH, "problems", "EVRP.py"),
+           "torch.cat((depot, depot_charging,  stations, locations),2)",
+           "torch.cat((depot, stations, locations),2)")
+    _patch(os.path.join(SCRATCH, "nets", "DRLModel.py"),
+           "torch.zeros([batch_size,  embed_dim]).float().cuda()",
+           "torch.zeros([batch_size,  embed_dim]).float().to(device)")
+    with open(marker, "w") as f:
+        f.write("P1 P2 applied\n")
+    return SCRATCH
+
+
+def load():
+    """Returns (AttentionModel, VehicleRoutingDataset) classes of the patched reference."""
+    path = prepare()
+    for name in ("matplotlib", "matplotlib.pyplot", "xlwt"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    if "matplotlib" in sys.modules and not hasattr(sys.modules["matplotlib"], "pyplot"):
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    import importlib
+    pn = importlib.import_module("nets.PointNetwork")
+    sys.modules.setdefault("nets.point_network", pn)
+    from nets.DRLModel import AttentionModel
+    from problems.EVRP import VehicleRoutingDataset
+    return AttentionModel, VehicleRoutingDataset
+
+
+def make_args(num_nodes, charging_num=5, Start_SOC=80., t_limit=10.):
+    return types.SimpleNamespace(CVRP_lib_test=False, Start_SOC=Start_SOC, t_limit=t_limit,
+                                 num_nodes=num_nodes, charging_num=charging_num)
+
+
+def make_dataset(B, N, seed, F=5):
+    _, DS = load()
+    args = make_args(N, F)
+    # positional order: problems/EVRP.py:10-11
+    return DS(B, N, 10., 80., 50., 4, 4, F, seed, args), args
+
+
+def make_model(ds, args, weight_seed=0):
+    import torch
+    AM, _ = load()
+    torch.manual_seed(weight_seed)
+    m = AM(128, 128, args, n_encode_layers=3, normalization='batch', tanh_clipping=10.,
+           mask_inner=True, mask_logits=True,
+           update_dynamic=ds.update_dynamic, update_mask=ds.update_mask)
+    return m
