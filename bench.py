@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""bench.py — greedy rollout throughput of EM-EVRP-100 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--nodes N]
+
+A step = one pass of the hot path (init-embed + encoder + precompute kernels, then ONE persistent rollout
+kernel) over one batch of `--batch` synthetic EM-EVRP-100 instances per GPU (config 4 of BASELINE.json:
+batch 8192; with N GPUs every rank owns its own 8192 instances -> weak scaling, no data-path collective).
+
+value      instances/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+e2e        the same through the public API call `model((static, dynamic, distances, slope))` with static/dynamic
+           in pinned HOST memory (distances/slope live on the device exactly as the reference's dataset keeps
+           them, problems/EVRP.py:87-92) and pi / cost read back to the host, copies inside the timed region
+roofline   rollout kernel: algorithmic bytes ((1568*S+2048) B per instance-step x executed
+           instance-steps) / CUDA-event duration of the kernel launch, against MEASURED_PEAKS.json hbm_gbs
+cpu_baseline  the numpy oracle port of the same path on the host cores, bounded sample (rank 0, N=1)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "greedy rollout instances/sec (EVRP-100)"
+UNIT = "instances/s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def synth(B, N, seed):
+    from oracle import evrp_oracle as O          # generator only (instance distribution of problems/EVRP.py:43-92)
+    return O.generate_instances(B, N, seed=seed)
+
+
+def golden_weights():
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "weights_seed0.npz")))
+
+
+def cpu_port_rate(N, sample, threads=None):
+    """numpy oracle (kind 'port') greedy rollout on the host cores: instances/s on a bounded sample."""
+    from oracle import evrp_oracle as O
+    from threadpoolctl import threadpool_info
+    W = golden_weights()
+    s, d, e = O.generate_instances(sample, N, seed=4242)
+    D, G = O.pairwise_matrices(s, e)
+    O.rollout(W, s[:8], d[:8], D[:8], G[:8])      # warm-up
+    t = time.perf_counter()
+    o = O.rollout(W, s, d, D, G)
+    dt = time.perf_counter() - t
+    cores = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    return sample / dt, cores, dt, int(o["pi"].shape[1])
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        rows = [r for ts, r in self.rows if t0 <= ts <= t1 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(float(r[2]) for r in rows)}
+
+
+def run_reference(a):
+    """The reference's CPU implementation of the path, restated (oracle port), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = a.ref_sample
+    for _ in range(a.warmup if a.warmup < 1 else 1):
+        cpu_port_rate(a.nodes, 16)
+    rates, T, cores, t_all = [], 0, 1, 0.0
+    for _ in range(a.steps):
+        r, cores, dt, T = cpu_port_rate(a.nodes, sample)
+        rates.append(r); t_all += dt
+    v = float(np.mean(rates))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * t_all / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"EM-EVRP-{a.nodes} greedy rollout, random-init attention policy (BASELINE configs[3])",
+                       "per_step_instances": sample, "nodes": a.nodes, "stations": 5, "decode_steps": T},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} instances per step x {a.steps} steps (numpy oracle port of the "
+                                       f"reference path; the Python reference itself cannot travel to the GPU box)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--batch", type=int, default=8192, help="instances per GPU per step (BASELINE configs[3])")
+    ap.add_argument("--nodes", type=int, default=100)
+    ap.add_argument("--cpu-sample", type=int, default=1024)
+    ap.add_argument("--ref-sample", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+    import evrp_b200
+    evrp_b200.lib()                                   # fail loudly without the CUDA library
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    N, B, F = a.nodes, a.batch, 5
+    S = N + F + 1
+    args = types.SimpleNamespace(CVRP_lib_test=False, Start_SOC=80., t_limit=10., num_nodes=N, charging_num=F)
+    ds = evrp_b200.VehicleRoutingDataset(2, N, 10., 80., 50., 4, 4, F, 1, args)
+    model = evrp_b200.AttentionModel(128, 128, args, n_encode_layers=3, update_dynamic=ds.update_dynamic,
+                                     update_mask=ds.update_mask)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in golden_weights().items()})   # torch.manual_seed(0) init
+    model = model.to(dev).eval()
+    model.set_decode_type("greedy")
+    static, dynamic, elev = synth(B, N, seed=1000 + rank)
+    st_h = torch.from_numpy(static).pin_memory(); dy_h = torch.from_numpy(dynamic).pin_memory()
+    st, dy = st_h.to(dev), dy_h.to(dev)
+    D, G = evrp_b200.policy_math.pairwise_matrices(st, torch.from_numpy(elev).to(dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        with torch.no_grad():
+            emb, kvl, fixed = model.encode(st, dy)
+            return model.rollout(emb, kvl, fixed, dy, D, G)
+
+    def step_e2e():
+        with torch.no_grad():
+            pi, ll, R = model((st_h, dy_h, D, G))
+            return R.sum(1).cpu(), pi.cpu()
+
+    for _ in range(max(a.warmup, 3)):
+        o = step_resident()
+    # ---------------- device-resident timing ----------------
+    model.profile_events = []
+    enc_ev = []
+    sampler = ClockSampler(local)
+    barrier()
+    t0 = time.perf_counter()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    inst_steps = 0
+    for _ in range(a.steps):
+        o = step_resident()
+        inst_steps += int(o["steps"].sum())
+    e_end.record()
+    barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1)
+    ms_total = e_start.elapsed_time(e_end)
+    roll_ms = [s.elapsed_time(e) for s, e in model.profile_events]
+    model.profile_events = None
+    T = int(o["pi"].shape[1])
+    # ---------------- end-to-end through the public API, host buffers ----------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    te0 = time.perf_counter()
+    for _ in range(a.steps):
+        cost, pi_host = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - te0
+    h2d = st_h.numel() * 4 + dy_h.numel() * 4
+    d2h = cost.numel() * 4 + pi_host.numel() * 8
+    tm = torch.tensor([ms_total, e2e_s * 1e3, float(np.mean(roll_ms)), float(inst_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tm.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tm.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total, e2e_ms, roll_avg_ms = mx[0].item(), mx[1].item(), mx[2].item()
+        inst_steps_all = sm[3].item()
+    else:
+        ms_total, e2e_ms, roll_avg_ms, inst_steps_all = tm[0].item(), tm[1].item(), tm[2].item(), tm[3].item()
+    if rank == 0:
+        pk, pk_src = peaks()
+        a_step = 1568 * S + 2048                                   # SURVEY §8d algorithmic bytes per instance-step
+        alg_bytes_per_launch = a_step * (inst_steps / a.steps)     # this rank's launch
+        achieved = alg_bytes_per_launch / (roll_avg_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "rollout_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": world * B * a.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"EM-EVRP-{N} greedy rollout, random-init attention policy (BASELINE configs[3])",
+                           "per_gpu_batch": B, "global_batch": B * world, "nodes": N, "stations": F,
+                           "decode_steps": T, "mean_steps_per_instance": inst_steps / (a.steps * B),
+                           "l2": "inputs_exceed_l2 (distances+slope+kvl = %.0f MB per step)" % ((2 * S * S + 384 * S) * 4 * B / 1e6),
+                           "parallelism": f"dp{world} (instances sharded, no data-path collective)"},
+                "e2e": {"value": world * B * a.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h},
+                "gpu_launches": a.steps * (1 + 5 * 3 + 2 + 1),
+                "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "evrp::rollout_kernel", "achieved": achieved,
+                             "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s",
+                             "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
+                             "kernel_ms": roll_avg_ms, "kernel_share_of_step": roll_avg_ms / (ms_total / a.steps),
+                             "algorithmic_bytes_per_launch": alg_bytes_per_launch}}
+        if world == 1 and not a.no_cpu_baseline:
+            r, cores, dt, Tc = cpu_port_rate(N, a.cpu_sample)
+            line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{a.cpu_sample} EM-EVRP-{N} instances, greedy, numpy oracle port, {dt:.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,12 @@
+"""evrp_b200 — B200-native drop-in for the rollout hot path of
+mengchengTang/DRL-Energy-optimal-Routing-for-Electric-Vehicles.
+
+The package directory is named ``drl-energy-optimal-routing-for-electric-vehicles_b200`` (not importable as a
+Python identifier); the repo-root shim ``evrp_b200/`` loads it under the name ``evrp_b200``.
+"""
+from . import _lib
+from ._lib import EvrpLibraryError, lib
+from .model import AttentionModel
+from .problem import VehicleRoutingDataset, parse_cvrplib
+
+__all__ = ["AttentionModel", "VehicleRoutingDataset", "parse_cvrplib", "EvrpLibraryError", "lib"]

@@ -1,0 +1,98 @@
+// Shared device code: the EVRP environment step (a7 update_dynamic + a8 update_mask of SURVEY.md §8)
+// as scalar, separately-rounded fp32 arithmetic.  Every op is an explicit __f*_rn intrinsic so that nvcc
+// cannot contract a*b+c into an FMA: the recipe must reproduce the reference's op-by-op rounding bit for bit
+// (problems/EVRP.py:105-280).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/evrp_b200.h"
+
+#define EVRP_CUDA_OK(expr)                                 \
+  do {                                                     \
+    cudaError_t _e = (expr);                               \
+    if (_e != cudaSuccess) return -(int)_e;                \
+  } while (0)
+
+#define EVRP_LAUNCH_OK()                                   \
+  do {                                                     \
+    cudaError_t _e = cudaGetLastError();                   \
+    if (_e != cudaSuccess) return -(int)_e;                \
+  } while (0)
+
+namespace evrp {
+
+constexpr int D = EVRP_D;      // 128
+constexpr int H = EVRP_H;      // 8
+constexpr int DK = D / H;      // 16
+constexpr int FF = EVRP_FF;    // 512
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float div_scalar(float x, float d, float inv_d, int mode) {
+  return mode ? __fmul_rn(x, inv_d) : __fdiv_rn(x, d);
+}
+
+// soc consumption of one leg (problems/EVRP.py:246-252 and the four copies inside update_mask :155-211)
+__device__ __forceinline__ float leg_energy(const evrp_phys& p, float mass, float slope, float tc) {
+  const float mg = __fmul_rn(mass, p.g);
+  const float Pm = __fmul_rn(__fadd_rn(__fadd_rn(p.aero, __fmul_rn(mg, slope)), __fmul_rn(mg, p.Cr)), p.velocity);
+  float e = 0.f;
+  if (Pm > 0.f) e = div_scalar(__fmul_rn(__fmul_rn(p.kd, Pm), tc), 3600.f, p.inv_3600, p.div_mode);
+  else if (Pm < 0.f) e = div_scalar(__fmul_rn(__fmul_rn(p.kr, Pm), tc), 3600.f, p.inv_3600, p.div_mode);
+  return e;
+}
+
+__device__ __forceinline__ float vehicle_mass(const evrp_phys& p, float load) {
+  // self.mc + loads*self.max_load*self.w   (problems/EVRP.py:155,246)
+  return __fadd_rn(p.mc, __fmul_rn(__fmul_rn(load, p.max_load), p.w));
+}
+
+__device__ __forceinline__ float travel_time(const evrp_phys& p, float dist) {
+  return div_scalar(dist, p.velocity, p.inv_velocity, p.div_mode);
+}
+
+// Feasibility of node j after arriving at node c (rules 5-7 of problems/EVRP.py:150-218) given the
+// post-move scalars.  d0/g0 = D[c,j], G[c,j]; D0j/G0j = D[0,j], G[0,j]; d3/s3/d4 = rule-7 constants.
+// load_j / dem_j are the (row) load value at column j and the demand of j (loads - demands, :177).
+__device__ __forceinline__ bool reachable(const evrp_phys& p, int j, int F, float load0, float load_j, float dem_j,
+                                          float soc_j, float time_j, float d0, float g0, float D0j, float G0j,
+                                          float d3, float s3, float d4) {
+  const float tc0 = travel_time(p, d0);
+  const float soc0 = leg_energy(p, vehicle_mass(p, load0), g0, tc0);
+  if (soc_j < soc0 || time_j < tc0) return false;                                   // :216
+  const float mass2 = vehicle_mass(p, __fsub_rn(load_j, dem_j));                    // :177
+  const float soc2 = leg_energy(p, mass2, G0j, travel_time(p, D0j));                // :178-186
+  float soc3 = __fadd_rn(soc0, soc2);                                               // :188
+  if (j <= F) soc3 = 0.f;                                                           // :189
+  float tc3 = travel_time(p, __fadd_rn(d0, D0j));                                   // :190
+  if (j >= 1 && j <= F) tc3 = __fadd_rn(tc3, p.charging_time);                      // :191
+  else if (j > F) tc3 = __fadd_rn(tc3, p.serve_time);                               // :192
+  const float soc4 = leg_energy(p, mass2, s3, travel_time(p, d3));                  // :203-211
+  const float soc5 = __fadd_rn(soc0, soc4);                                         // :212
+  float tc5 = travel_time(p, __fadd_rn(__fadd_rn(d0, d3), d4));                     // :213
+  if (j > F) tc5 = __fadd_rn(tc5, p.charge_plus_serve);                             // :214
+  const bool via_depot_bad = (soc_j < soc3) || (time_j < tc3);
+  const bool via_station_bad = (soc_j < soc5) || (time_j < tc5);
+  return !(via_depot_bad && via_station_bad);                                       // :218
+}
+
+// Counter-based RNG for sampling: splitmix64 finaliser over (seed, row, step) -> uniform in [0,1).
+__device__ __forceinline__ float uniform01(uint64_t seed, uint64_t row, uint32_t step) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (row * 1024ull + step + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+}  // namespace evrp

@@ -1,0 +1,190 @@
+// Stand-alone EVRP environment step kernels behind the reference's problem API:
+//   VehicleRoutingDataset.update_dynamic  problems/EVRP.py:226-280
+//   VehicleRoutingDataset.update_mask     problems/EVRP.py:105-223
+// One warp per instance, lanes over the S nodes; pure fp32 element-wise work (HBM-bound: reads 2-7 rows of
+// D/G and the [4,S] state per instance).  The same device recipe (evrp_common.cuh) is fused into the
+// persistent rollout kernel; these kernels exist for foreign callers of the callback API and for the
+// bit-exact unit parity tests.
+#include <math.h>
+#include "evrp_common.cuh"
+
+namespace evrp {
+
+constexpr int STEP_WARPS = 8;
+
+__global__ void __launch_bounds__(STEP_WARPS * 32)
+update_dynamic_kernel(evrp_phys p, const float* __restrict__ dyn, const float* __restrict__ Dm,
+                      const float* __restrict__ Gm, const int64_t* __restrict__ now_idx,
+                      const int64_t* __restrict__ chosen_idx, int B, int S, int F,
+                      float* __restrict__ out, float* __restrict__ energy, float* __restrict__ distance) {
+  const int b = blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int c = (int)chosen_idx[b];
+  const int n = (int)now_idx[b];
+  const float* d = dyn + (size_t)b * 4 * S;
+  float* o = out + (size_t)b * 4 * S;
+  const float dist = Dm[((size_t)b * S + n) * S + c];
+  const float sl = Gm[((size_t)b * S + n) * S + c];
+  const float load0 = d[0];
+  const float tc = travel_time(p, dist);
+  const float e = leg_energy(p, vehicle_mass(p, load0), sl, tc);
+  const bool depot = (c == 0), station = (c > 0 && c <= F), customer = (c > F);
+  const float load_c = d[c], dem_c = d[S + c];
+  const float new_load = fmaxf(__fsub_rn(load_c, dem_c), 0.f);      // :265
+  const float new_dem = fmaxf(__fsub_rn(dem_c, load_c), 0.f);       // :266
+  for (int j = lane; j < S; j += 32) {
+    float L = d[j], dm = d[S + j], soc = d[2 * S + j], tim = d[3 * S + j];
+    tim = __fsub_rn(tim, tc);                                       // :254
+    if (depot) tim = p.t_limit;                                     // :255
+    if (station) tim = __fsub_rn(tim, p.charging_time);             // :256
+    if (customer) tim = __fsub_rn(tim, p.serve_time);               // :257
+    soc = __fsub_rn(soc, e);                                        // :258
+    if (c <= F) soc = p.start_soc;                                  // :259
+    if (customer) {                                                 // :264-272
+      L = new_load;
+      if (j == c) dm = new_dem;
+      if (j == 0) dm = __fadd_rn(-1.f, new_load);
+    }
+    if (depot) {                                                    // :274-276
+      L = 1.f;
+      if (j == 0) dm = 0.f;
+    }
+    o[j] = L; o[S + j] = dm; o[2 * S + j] = soc; o[3 * S + j] = tim;
+  }
+  if (lane == 0) {
+    energy[b] = e;
+    if (distance) distance[b] = dist;
+  }
+}
+
+__global__ void __launch_bounds__(STEP_WARPS * 32)
+update_mask_kernel(evrp_phys p, const float* __restrict__ dyn, const float* __restrict__ Dm,
+                   const float* __restrict__ Gm, const int64_t* __restrict__ chosen_idx, int B, int S, int F,
+                   float* __restrict__ mask, int32_t* __restrict__ any_demand) {
+  const int b = blockIdx.x * STEP_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int c = (int)chosen_idx[b];
+  const float* d = dyn + (size_t)b * 4 * S;
+  const float* Db = Dm + (size_t)b * S * S;
+  const float* Gb = Gm + (size_t)b * S * S;
+  const float load0 = d[0];
+  const bool depot = (c == 0), station = (c > 0 && c <= F), customer = (c > F);
+  // nearest station of the depot column (rule 7 scalar d4, :202)
+  int k0 = 0; float best0 = Db[(size_t)1 * S + 0];
+  for (int i = 1; i < F; ++i) { float v = Db[(size_t)(1 + i) * S + 0]; if (v < best0) { best0 = v; k0 = i; } }
+  const float d4 = Db[(size_t)(1 + k0) * S + 0];
+  // pass 1: global "anything left" flag (:127), rule-4 predicates (:143-145)
+  bool any_dem = false, cust_dem = false;
+  for (int j = lane; j < S; j += 32) {
+    const float dm = d[S + j];
+    any_dem |= (dm != 0.f);
+    cust_dem |= (j >= F && dm != 0.f);
+  }
+  any_dem = __any_sync(FULL, any_dem);
+  cust_dem = __any_sync(FULL, cust_dem);
+  if (any_dem && lane == 0) atomicOr(any_demand, 1);
+  const bool combined = (load0 == 0.f) || !cust_dem;
+  bool cust_ok = false;
+  float m0 = 0.f;
+  for (int j0 = 0; j0 < S; j0 += 32) {
+    const int j = j0 + lane;
+    bool m = false;
+    if (j < S) {
+      const float L = d[j], dm = d[S + j], soc = d[2 * S + j], tim = d[3 * S + j];
+      m = (dm != 0.f) && (dm < L);                                  // rule 1 :131
+      if (j == c) m = false;                                        // rule 2 :134
+      if (c <= F && j >= 1 && j <= F) m = false;                    // rule 3 :137
+      if (station && j == 0) m = true;                              //        :138
+      if (customer && j <= F) m = true;                             //        :139
+      if (depot && j == 0) m = false;                               //        :140
+      if (combined) m = (j == 0);                                   // rule 4 :146-148
+      int k = 0; float best = Db[(size_t)1 * S + j];                // rule 7 constants :196-201
+      for (int i = 1; i < F; ++i) { float v = Db[(size_t)(1 + i) * S + j]; if (v < best) { best = v; k = i; } }
+      const float d3 = (j == 0) ? 0.f : best;
+      const float s3 = Gb[(size_t)(1 + k) * S + j];
+      if (!reachable(p, j, F, load0, L, dm, soc, tim, Db[(size_t)c * S + j], Gb[(size_t)c * S + j],
+                     Db[j], Gb[j], d3, s3, d4)) m = false;          // rules 5-7
+      if (j > F && m) cust_ok = true;
+      if (j == 0) m0 = m ? 1.f : 0.f;
+      mask[(size_t)b * S + j] = m ? 1.f : 0.f;
+    }
+  }
+  cust_ok = __any_sync(FULL, cust_ok);
+  if (!cust_ok && lane == 0) mask[(size_t)b * S] = 1.f;             // rule 8 :220-221
+  (void)m0;
+}
+
+__global__ void finalize_mask_kernel(float* __restrict__ mask, size_t n, const int32_t* __restrict__ any_demand) {
+  if (*any_demand != 0) return;                                     // :127-128 all-zero mask ends the rollout
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    mask[i] = 0.f;
+}
+
+}  // namespace evrp
+
+extern "C" {
+
+void evrp_phys_default(evrp_phys* p, double velocity, double start_soc, double t_limit, double max_load) {
+  const double Cd = 0.7, A = 6.66, Ad = 1.2041;
+  const double v36 = velocity / 3.6;
+  p->aero = (float)(0.5 * Cd * A * Ad * (v36 * v36));
+  p->kd = (float)(1.18 * 1.11);
+  p->kr = (float)(0.85 * 0.93);
+  p->g = 9.81f; p->Cr = 0.01f; p->velocity = (float)velocity; p->mc = 4100.f; p->w = 1000.f;
+  p->max_load = (float)max_load; p->start_soc = (float)start_soc; p->t_limit = (float)t_limit;
+  p->charging_time = 1.f; p->serve_time = 0.33f; p->charge_plus_serve = (float)(1 + 0.33);
+  p->inv_velocity = (float)(1.0 / velocity); p->inv_3600 = (float)(1.0 / 3600.0);
+  p->div_mode = 0; p->objective = 0;
+}
+
+int evrp_abi_version(void) { return EVRP_ABI_VERSION; }
+
+int evrp_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  EVRP_CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  EVRP_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return 0;
+}
+
+int evrp_update_dynamic(const evrp_phys* phys, const float* dynamic, const float* distances, const float* slope,
+                        const int64_t* now_idx, const int64_t* chosen_idx, int B, int S, int F,
+                        float* new_dynamic, float* energy, float* distance, void* stream) {
+  if (!phys || !dynamic || !distances || !slope || !now_idx || !chosen_idx || !new_dynamic || !energy || B < 0 ||
+      S < 2 || F < 1 || F >= S)
+    return -EVRP_E_BADARG;
+  if (B == 0) return 0;
+  const int grid = (B + evrp::STEP_WARPS - 1) / evrp::STEP_WARPS;
+  evrp::update_dynamic_kernel<<<grid, evrp::STEP_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      *phys, dynamic, distances, slope, now_idx, chosen_idx, B, S, F, new_dynamic, energy, distance);
+  EVRP_LAUNCH_OK();
+  return 0;
+}
+
+int evrp_update_mask(const evrp_phys* phys, const float* dynamic, const float* distances, const float* slope,
+                     const int64_t* chosen_idx, int B, int S, int F, float* mask, int32_t* any_demand,
+                     void* stream) {
+  if (!phys || !dynamic || !distances || !slope || !chosen_idx || !mask || !any_demand || B < 0 || S < 2 || F < 1 ||
+      F >= S)
+    return -EVRP_E_BADARG;
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  EVRP_CUDA_OK(cudaMemsetAsync(any_demand, 0, sizeof(int32_t), st));
+  const int grid = (B + evrp::STEP_WARPS - 1) / evrp::STEP_WARPS;
+  evrp::update_mask_kernel<<<grid, evrp::STEP_WARPS * 32, 0, st>>>(*phys, dynamic, distances, slope, chosen_idx, B,
+                                                                  S, F, mask, any_demand);
+  EVRP_LAUNCH_OK();
+  const size_t n = (size_t)B * S;
+  int fgrid = (int)((n + 255) / 256);
+  if (fgrid > 1184) fgrid = 1184;
+  evrp::finalize_mask_kernel<<<fgrid, 256, 0, st>>>(mask, n, any_demand);
+  EVRP_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"

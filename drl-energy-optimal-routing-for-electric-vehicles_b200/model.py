@@ -1,0 +1,311 @@
+"""Drop-in ``AttentionModel`` (the reference's nets/DRLModel.py:41-313) whose forward runs on the
+hand-written sm_100a kernels of libevrp_b200.so.
+
+Same constructor signature, same 50 parameter tensors / state_dict keys (+ BatchNorm buffers), same
+``forward(input) -> (pi, ll, R)``, ``sample_many``, ``set_decode_type`` — so trainer.py / reinforce_baselines.py
+of the reference can use it unchanged.  Parameters are created in the reference's order with the same
+initialisers, so ``torch.manual_seed(s)`` followed by construction gives the reference's weights bit for bit
+(tests/test_boundary.py).
+
+What runs where
+  * greedy / sampled rollout (eval or no-grad): init-embed + encoder + precompute kernels
+    (csrc/evrp_encoder.cu) and ONE persistent rollout kernel (csrc/evrp_decode.cu).
+  * training forward (grad enabled): the same rollout kernel samples the actions and records per-step
+    (mask bits, vehicle scalars); log-likelihoods are then recomputed teacher-forced, batched over all T steps
+    at once, by ``policy_math`` so that autograd reaches all 50 parameters (round-1 state of SURVEY §8 a10;
+    the fused backward kernel is the next step).
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import _lib
+from . import policy_math
+
+
+# --------------------------------------------------------------------------------------------------
+# parameter containers that reproduce the reference's module tree (=> identical state_dict keys)
+#   embedder.layers.{l}.0.module.{W_query,W_key,W_val,W_out}      nets/GraphEncoder.py:41-45
+#   embedder.layers.{l}.1.normalizer.*                            nets/GraphEncoder.py:131
+#   embedder.layers.{l}.2.module.{0,2}.{weight,bias}              nets/GraphEncoder.py:172-176
+#   embedder.layers.{l}.3.normalizer.*
+# --------------------------------------------------------------------------------------------------
+class _Wrapped(nn.Module):
+    """holds a child under the attribute name ``module`` (the reference's SkipConnection)"""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+
+class _HeadProjections(nn.Module):
+    def __init__(self, n_heads, embed_dim):
+        super().__init__()
+        dk = embed_dim // n_heads
+        self.W_query = nn.Parameter(torch.empty(n_heads, embed_dim, dk))
+        self.W_key = nn.Parameter(torch.empty(n_heads, embed_dim, dk))
+        self.W_val = nn.Parameter(torch.empty(n_heads, embed_dim, dk))
+        self.W_out = nn.Parameter(torch.empty(n_heads, dk, embed_dim))
+        for p in self.parameters():                      # nets/GraphEncoder.py:49-53
+            bound = 1. / math.sqrt(p.size(-1))
+            p.data.uniform_(-bound, bound)
+
+
+class _Norm(nn.Module):
+    def __init__(self, embed_dim, normalization):
+        super().__init__()
+        if normalization != "batch":
+            raise NotImplementedError("evrp_b200 implements normalization='batch' (the reference default, run.py)")
+        self.normalizer = nn.BatchNorm1d(embed_dim, affine=True)
+
+
+class _EncoderParams(nn.Module):
+    def __init__(self, n_heads, embed_dim, n_layers, normalization, ff_hidden=512):
+        super().__init__()
+        self.layers = nn.Sequential(*(
+            nn.Sequential(
+                _Wrapped(_HeadProjections(n_heads, embed_dim)),
+                _Norm(embed_dim, normalization),
+                _Wrapped(nn.Sequential(nn.Linear(embed_dim, ff_hidden), nn.ReLU(), nn.Linear(ff_hidden, embed_dim))),
+                _Norm(embed_dim, normalization),
+            ) for _ in range(n_layers)))
+
+    def forward(self, *a, **k):
+        raise RuntimeError("the encoder runs inside libevrp_b200.so; call AttentionModel.forward")
+
+
+class AttentionModel(nn.Module):
+    """nets/DRLModel.py:41 — B200-native drop-in."""
+
+    def __init__(self, embedding_dim, hidden_dim, args, n_encode_layers=2, tanh_clipping=10., mask_inner=True,
+                 mask_logits=True, normalization='batch', n_heads=8, update_dynamic=None, update_mask=None):
+        super().__init__()
+        if embedding_dim != 128 or n_heads != 8:
+            raise NotImplementedError("libevrp_b200 kernels are specialised for embedding_dim=128, n_heads=8 "
+                                      "(run.py defaults / nets/DRLModel.py:52)")
+        if not (mask_inner and mask_logits):
+            raise NotImplementedError("mask_inner/mask_logits=False are not used by the reference trainer")
+        self.embedding_dim, self.hidden_dim, self.n_encode_layers = embedding_dim, hidden_dim, n_encode_layers
+        self.decode_type, self.temp = None, 1.0
+        self.tanh_clipping = tanh_clipping
+        self.feed_forward_hidden = 512
+        self.mask_inner, self.mask_logits = mask_inner, mask_logits
+        self.update_dynamic, self.update_mask = update_dynamic, update_mask
+        self.n_heads = n_heads
+        self.start_soc, self.t_limit = args.Start_SOC, args.t_limit
+        self.custom_num, self.charging_num = args.num_nodes, args.charging_num
+        self.velocity = float(getattr(args, "velocity", 50.))
+        self.max_load = getattr(args, "max_load", 4)
+        self.objective = getattr(args, "obj", "EM")
+        self.objective = "DM" if str(self.objective).upper().startswith("D") else "EM"
+        # parameter creation order = nets/DRLModel.py:78-102 (keeps RNG-stream parity with the reference)
+        self.init_embed_depot_and_station = nn.Linear(2, embedding_dim)
+        self.init_embed_station = nn.Linear(2, embedding_dim)
+        self.init_embed = nn.Linear(3, embedding_dim)
+        self.embedder = _EncoderParams(n_heads, embedding_dim, n_encode_layers, normalization)
+        self.tour = nn.Linear(3, embedding_dim, bias=False)
+        self.FF_tour = nn.Sequential(nn.Linear(2 * embedding_dim, 512), nn.ReLU(), nn.Linear(512, embedding_dim))
+        self.project_node_embeddings = nn.Linear(embedding_dim, 3 * embedding_dim, bias=False)
+        self.project_fixed_context = nn.Linear(embedding_dim, embedding_dim, bias=False)
+        self.project_out = nn.Linear(embedding_dim, embedding_dim, bias=False)
+        self._pack_cache = None
+        self.max_steps = 1000                     # nets/DRLModel.py:255
+        self.sample_seed = 0
+        self._calls = 0
+        self.last_energy = None                   # [B,T] energy of the last rollout (DM trainer's 3rd output)
+        self.profile_events = None                # list -> (start, end) CUDA events around each rollout kernel launch
+
+    # ------------------------------------------------------------------------------------------
+    def set_decode_type(self, decode_type, temp=None):   # nets/DRLModel.py:104-107
+        self.decode_type = decode_type
+        if temp is not None:
+            self.temp = temp
+
+    # ------------------------------------------------------------------------------------------
+    def _device(self):
+        return self.project_out.weight.device
+
+    def _fused_path_ok(self):
+        """The fused kernel is legal only when the injected callbacks are ours (or absent)."""
+        for cb in (self.update_dynamic, self.update_mask):
+            if cb is None:
+                continue
+            owner = getattr(cb, "__self__", None)
+            if not getattr(owner, "_evrp_b200_native", False):
+                return False
+        return True
+
+    def _phys(self):
+        """vehicle constants: the injected dataset's (problems/EVRP.py:21-41) when the callbacks are ours"""
+        owner = getattr(self.update_dynamic, "__self__", None)
+        if owner is not None and getattr(owner, "_evrp_b200_native", False):
+            return _lib.make_phys(float(owner.velocity), float(owner.Start_SOC), float(owner.t_limit),
+                                  owner.max_load, owner.objective)
+        return _lib.make_phys(self.velocity, float(self.start_soc), float(self.t_limit), self.max_load, self.objective)
+
+    def packed_weights(self):
+        """Kernel-side weight layouts (k-major transposes, folded BatchNorm / project_out / tour), rebuilt only
+        when a parameter or buffer changed (tensor version counters)."""
+        sd = list(self.parameters()) + list(self.buffers())
+        key = (tuple(t._version for t in sd), tuple(t.data_ptr() for t in sd), self.training)
+        if self._pack_cache is None or self._pack_cache[0] != key:
+            with torch.no_grad():
+                self._pack_cache = (key, policy_math.pack_weights(self))
+        return self._pack_cache[1]
+
+    def _prepare_inputs(self, input):
+        dev = self._device()
+        if dev.type != "cuda":
+            raise _lib.EvrpLibraryError("evrp_b200.AttentionModel runs on CUDA only (no CPU fallback); call .cuda()")
+        if isinstance(input, dict):
+            input = input["data"]
+        if len(input) == 4:                              # nets/DRLModel.py:118-123
+            static, dynamic, distances, slope = input
+            distances = distances.to(dev, torch.float32).contiguous()
+            slope = slope.to(dev, torch.float32).contiguous()
+            static = static.to(dev, torch.float32).contiguous()
+        else:                                            # nets/DRLModel.py:124-133
+            static, dynamic, elevations = input
+            static = static.to(dev, torch.float32).contiguous()
+            distances, slope = policy_math.pairwise_matrices(static, elevations.to(dev, torch.float32))
+        dynamic = dynamic.to(dev, torch.float32).contiguous()
+        return static, dynamic, distances, slope
+
+    # ------------------------------------------------------------------------------------------
+    def encode(self, static, dynamic):
+        """kernels: init-embed + encoder layers + precompute.  -> emb [B,S,128], kvl [B,S,384], fixed [B,128]"""
+        L = _lib.lib()
+        B, _, S = static.shape
+        pk = self.packed_weights()
+        dev = static.device
+        emb = torch.empty(B, S, 128, device=dev)
+        kvl = torch.empty(B, S, 384, device=dev)
+        fixed = torch.empty(B, 128, device=dev)
+        nbytes = L.evrp_encoder_workspace_bytes(B, S)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        rc = L.evrp_encoder_forward(pk["enc_struct"], _lib.ptr(static), _lib.ptr(dynamic), B, S, self.charging_num,
+                                    _lib.ptr(emb), _lib.ptr(kvl), _lib.ptr(fixed), _lib.ptr(ws), nbytes,
+                                    _lib.stream_ptr())
+        _lib.check(rc, "evrp_encoder_forward")
+        return emb, kvl, fixed
+
+    def rollout(self, emb, kvl, fixed, dynamic, distances, slope, n_replicas=1, forced=None, uniforms=None,
+                save_trace=False, decode_type=None, max_steps=None):
+        """ONE persistent kernel for the whole decode.  Returns dict of [rows,T] tensors (+trace)."""
+        L = _lib.lib()
+        B, S = emb.shape[0], emb.shape[1]
+        rows = B * n_replicas
+        dev = emb.device
+        decode_type = decode_type or self.decode_type
+        if forced is None and decode_type not in ("greedy", "sample"):
+            raise AssertionError("Unknown decode type")           # nets/DRLModel.py:341
+        pk = self.packed_weights()
+        phys = self._phys()
+        if forced is not None:
+            forced = forced.to(dev, torch.int64).contiguous()
+            tcap = forced.shape[1]
+        else:
+            tcap = int(max_steps or min(self.max_steps, 8 * S))
+        while True:
+            cfg = _lib.RolloutCfg(_lib.DECODE_SAMPLE if decode_type == "sample" else _lib.DECODE_GREEDY,
+                                  float(self.temp), float(self.tanh_clipping), tcap,
+                                  (self.sample_seed * 0x9E3779B1 + self._calls) & 0xFFFFFFFFFFFFFFFF, n_replicas)
+            pi = torch.zeros(rows, tcap, dtype=torch.int64, device=dev)
+            ll = torch.zeros(rows, tcap, device=dev)
+            R = torch.zeros(rows, tcap, device=dev)
+            E = torch.zeros(rows, tcap, device=dev)
+            smask = torch.zeros(rows, tcap, 4, dtype=torch.int32, device=dev) if save_trace else None
+            sveh = torch.zeros(rows, tcap, 3, device=dev) if save_trace else None
+            steps = torch.zeros(rows, dtype=torch.int32, device=dev)
+            meta = torch.zeros(2, dtype=torch.int32, device=dev)          # [t_max, status]
+            ev = None
+            if self.profile_events is not None:                   # bench.py: CUDA events around the kernel launch only
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
+            rc = L.evrp_rollout(phys, pk["dec_struct"], cfg, _lib.ptr(emb), _lib.ptr(kvl), _lib.ptr(fixed),
+                                _lib.ptr(dynamic), _lib.ptr(distances), _lib.ptr(slope), B, S, self.charging_num,
+                                _lib.ptr(forced), _lib.ptr(uniforms), _lib.ptr(pi), _lib.ptr(ll), _lib.ptr(R),
+                                _lib.ptr(E), _lib.ptr(smask), _lib.ptr(sveh), _lib.ptr(steps),
+                                _lib.ptr(meta[0:1]), _lib.ptr(meta[1:2]), _lib.stream_ptr())
+            _lib.check(rc, "evrp_rollout")
+            if ev is not None:
+                ev[1].record()
+                self.profile_events.append(ev)
+            t_max, status = (int(v) for v in meta.tolist())       # the single host sync of the rollout
+            if status & _lib.ST_STEP_CAP and forced is None and tcap < self.max_steps:
+                tcap = min(self.max_steps, tcap * 2)              # rare: tour longer than the first guess
+                continue
+            break
+        self._calls += 1
+        # the reference's Python asserts, raised from the device status word
+        assert not status & _lib.ST_NAN_LOGIT, "Probs should not contain any nans"            # DRLModel.py:324
+        assert not status & _lib.ST_INFEASIBLE_PICK, "Decode: infeasible action selected"     # DRLModel.py:328
+        assert not status & _lib.ST_NONUNIFORM_DYNAMIC, \
+            "dynamic rows (load, SOC, time) must be one scalar broadcast over the nodes (problems/EVRP.py:79-83)"
+        assert not status & _lib.ST_NO_FEASIBLE, "every node masked for an unfinished instance"
+        T = tcap if forced is not None else max(t_max, 1)
+        out = dict(pi=pi[:, :T], ll=ll[:, :T], R=R[:, :T], E=E[:, :T], steps=steps, status=status, t_max=t_max)
+        if save_trace:
+            out.update(mask_bits=smask[:, :T], veh=sveh[:, :T])
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, input, forced_actions=None):
+        """nets/DRLModel.py:109-140 -> (pi [B,T] int64, ll [B,T], R [B,T]).
+        ``forced_actions`` [B,T] (optional, not in the reference) teacher-forces the picks (gradient-parity tests)."""
+        static, dynamic, distances, slope = self._prepare_inputs(input)
+        if not self._fused_path_ok():
+            raise NotImplementedError(
+                "foreign update_dynamic/update_mask callbacks: the fused rollout kernel embeds the EVRP recipe of "
+                "problems/EVRP.py; pass evrp_b200.VehicleRoutingDataset's bound methods (or None)")
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if not need_grad and not self.training:
+            emb, kvl, fixed = self.encode(static, dynamic)
+            o = self.rollout(emb, kvl, fixed, dynamic, distances, slope, forced=forced_actions)
+            self.last_energy = o["E"]
+            return o["pi"], o["ll"], o["R"]
+        # training / grad path: differentiable encoder (train-mode BatchNorm uses batch statistics and updates the
+        # running buffers, nets/GraphEncoder.py:144-145), kernel rollout, teacher-forced differentiable log-probs
+        emb, kvl, fixed = policy_math.encode_torch(self, static, dynamic)
+        with torch.no_grad():
+            o = self.rollout(emb.detach().contiguous(), kvl.detach().contiguous(), fixed.detach().contiguous(),
+                             dynamic, distances, slope, save_trace=True, forced=forced_actions)
+        ll = policy_math.teacher_forced_ll(self, emb, kvl, fixed, o["pi"], o["mask_bits"], o["veh"], o["steps"])
+        self.last_energy = o["E"]
+        return o["pi"], ll, o["R"]
+
+    def forward_forced(self, input, actions, save_trace=False):
+        """Teacher-forced evaluation (tests / gradient parity): the policy's log-probs along given actions."""
+        static, dynamic, distances, slope = self._prepare_inputs(input)
+        emb, kvl, fixed = self.encode(static, dynamic)
+        return self.rollout(emb, kvl, fixed, dynamic, distances, slope, forced=actions, save_trace=save_trace)
+
+    # ------------------------------------------------------------------------------------------
+    def sample_many(self, input, batch_rep=1, iter_rep=1):
+        """nets/DRLModel.py:283-313 -> (mincosts [B], minpis [B,Tmax]).  The encoder runs ONCE per instance and the
+        batch_rep replicas share its output (the reference re-encodes every replica)."""
+        L = _lib.lib()
+        static, dynamic, distances, slope = self._prepare_inputs(input)
+        B = static.shape[0]
+        with torch.no_grad():
+            emb, kvl, fixed = self.encode(static, dynamic)
+            costs, pis, energies = [], [], []
+            for _ in range(iter_rep):
+                o = self.rollout(emb, kvl, fixed, dynamic, distances, slope, n_replicas=batch_rep)
+                T = o["pi"].shape[1]
+                Rc, pic = o["R"].contiguous(), o["pi"].contiguous()
+                mc = torch.empty(B, device=emb.device)
+                am = torch.empty(B, dtype=torch.int32, device=emb.device)
+                mp = torch.empty(B, T, dtype=torch.int64, device=emb.device)
+                _lib.check(L.evrp_sample_min(_lib.ptr(Rc), _lib.ptr(pic), B, batch_rep, T, _lib.ptr(mc), _lib.ptr(am),
+                                             _lib.ptr(mp), _lib.stream_ptr()), "evrp_sample_min")
+                costs.append(mc); pis.append(mp)
+                energies.append(o["E"].sum(1).view(batch_rep, B).gather(0, am.long()[None])[0])
+            T = max(p.shape[1] for p in pis)
+            pis = torch.stack([torch.nn.functional.pad(p, (0, T - p.shape[1])) for p in pis], 1)   # [B,iter,T]
+            costs = torch.stack(costs, 1)
+            mincosts, arg = costs.min(1)
+            minpis = pis[torch.arange(B, device=pis.device), arg]
+            self.last_energy = torch.stack(energies, 1)[torch.arange(B, device=pis.device), arg]
+        return mincosts, minpis

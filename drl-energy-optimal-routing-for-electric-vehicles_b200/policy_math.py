@@ -1,0 +1,161 @@
+"""Host-side helpers of the drop-in model:
+
+  pack_weights        reference state_dict layout -> kernel layouts (k-major, folded BN / project_out / tour)
+  pairwise_matrices   the 3-tuple input branch of nets/DRLModel.py:124-133 (distance / clamped-slope build)
+  encode_torch        differentiable encoder + precompute (training forward; train-mode BatchNorm)
+  teacher_forced_ll   differentiable log-likelihood of a recorded rollout, all T steps batched at once
+
+The two differentiable functions are plain PyTorch on the GPU; they exist so that autograd reaches all 50
+parameters for the REINFORCE step (trainer.py:115-127) while the rollout itself runs in the CUDA kernel.
+They are NOT used by the greedy / sampled inference path.
+"""
+import math
+
+import torch
+import torch.nn.functional as Fn
+
+from . import _lib
+
+
+def _bn_fold(bn):
+    """eval-mode BatchNorm1d as y = x*scale + shift (nets/GraphEncoder.py:144-145), folded in fp64"""
+    w, b = bn.weight.double(), bn.bias.double()
+    rm, rv = bn.running_mean.double(), bn.running_var.double()
+    scale = w / torch.sqrt(rv + bn.eps)
+    shift = b - rm * scale
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+def folded_node_projection(model):
+    """[384,128]: rows 0..255 = glimpse K|V projection, rows 256..383 = project_out^T @ W_logitK so that
+    logits[j] = heads . lK[j]  (nets/DRLModel.py:436-444).  Differentiable."""
+    W = model.project_node_embeddings.weight
+    Wl = (model.project_out.weight.double().t() @ W[256:].double()).to(W.dtype)
+    return torch.cat([W[:256], Wl], 0)
+
+
+def folded_tour_weight(model):
+    """[512,3] = FF_tour.0.weight[:, :128] @ tour.weight (nets/DRLModel.py:233-235).  Differentiable."""
+    W1 = model.FF_tour[0].weight
+    return (W1[:, :128].double() @ model.tour.weight.double()).to(W1.dtype)
+
+
+def pack_weights(model):
+    keep = {}
+    ew = _lib.EncoderWeights()
+
+    def dev(name, t):
+        t = t.detach().float().contiguous()
+        keep[name] = t
+        return _lib.ptr(t) if t.is_cuda else None
+
+    ew.depot_w = dev("depot_w", model.init_embed_depot_and_station.weight)
+    ew.depot_b = dev("depot_b", model.init_embed_depot_and_station.bias)
+    ew.station_w = dev("station_w", model.init_embed_station.weight)
+    ew.station_b = dev("station_b", model.init_embed_station.bias)
+    ew.cust_w = dev("cust_w", model.init_embed.weight)
+    ew.cust_b = dev("cust_b", model.init_embed.bias)
+    layers = model.embedder.layers
+    ew.n_layers = len(layers)
+    for l, layer in enumerate(layers):
+        att, bn1, ff, bn2 = layer[0].module, layer[1].normalizer, layer[2].module, layer[3].normalizer
+        Hh, d, dk = att.W_query.shape
+        cols = [w.permute(1, 0, 2).reshape(d, Hh * dk) for w in (att.W_query, att.W_key, att.W_val)]
+        lw = ew.layers[l]
+        lw.Wqkv = dev(f"l{l}.Wqkv", torch.cat(cols, 1))
+        lw.Wo = dev(f"l{l}.Wo", att.W_out.reshape(Hh * dk, d))
+        s, sh = _bn_fold(bn1)
+        lw.bn1_scale, lw.bn1_shift = dev(f"l{l}.bn1s", s), dev(f"l{l}.bn1b", sh)
+        lw.ff1_w, lw.ff1_b = dev(f"l{l}.ff1w", ff[0].weight.t()), dev(f"l{l}.ff1b", ff[0].bias)
+        lw.ff2_w, lw.ff2_b = dev(f"l{l}.ff2w", ff[2].weight.t()), dev(f"l{l}.ff2b", ff[2].bias)
+        s, sh = _bn_fold(bn2)
+        lw.bn2_scale, lw.bn2_shift = dev(f"l{l}.bn2s", s), dev(f"l{l}.bn2b", sh)
+    ew.node_proj = dev("node_proj", folded_node_projection(model).t())
+    ew.fixed_ctx_w = dev("fixed_ctx_w", model.project_fixed_context.weight.t())
+    dw = _lib.DecoderWeights()
+    dw.w1_veh = dev("w1_veh", folded_tour_weight(model).t())
+    dw.w1_max = dev("w1_max", model.FF_tour[0].weight[:, 128:].t())
+    dw.b1 = dev("b1", model.FF_tour[0].bias)
+    dw.w2 = dev("w2", model.FF_tour[2].weight.t())
+    dw.b2 = dev("b2", model.FF_tour[2].bias)
+    keep["enc_struct"], keep["dec_struct"] = ew, dw
+    return keep
+
+
+def pairwise_matrices(static, elevations):
+    """nets/DRLModel.py:128-133 / problems/EVRP.py:87-92, vectorised (no Python loop over S)."""
+    diff = static[:, :, :, None] - static[:, :, None, :]
+    D = torch.sqrt((diff * diff).sum(1))
+    G = torch.clamp((elevations[:, :, None] - elevations[:, None, :]) / (D + 0.000001), min=-0.10, max=0.10)
+    return D.contiguous(), G.contiguous()
+
+
+def init_embed_torch(model, static, dynamic):
+    F = model.charging_num
+    xy = static.transpose(1, 2) / 100
+    dem = dynamic[:, 1, :, None]
+    return torch.cat((model.init_embed_depot_and_station(xy[:, 0:1]),
+                      model.init_embed_station(xy[:, 1:F + 1]),
+                      model.init_embed(torch.cat((xy[:, F + 1:], dem[:, F + 1:]), 2))), 1)
+
+
+def encode_torch(model, static, dynamic):
+    """Differentiable restatement of the encoder kernels' math (nets/GraphEncoder.py:55-118,142-179).
+    BatchNorm follows ``model.training`` (batch statistics + running-stat update in train mode)."""
+    h = init_embed_torch(model, static, dynamic)
+    B, S, d = h.shape
+    for layer in model.embedder.layers:
+        att, bn1, ff, bn2 = layer[0].module, layer[1].normalizer, layer[2].module, layer[3].normalizer
+        flat = h.reshape(B * S, d)
+        Q = torch.matmul(flat, att.W_query).view(-1, B, S, att.W_query.shape[-1])
+        K = torch.matmul(flat, att.W_key).view(-1, B, S, att.W_key.shape[-1])
+        V = torch.matmul(flat, att.W_val).view(-1, B, S, att.W_val.shape[-1])
+        attn = torch.softmax(torch.matmul(Q, K.transpose(2, 3)) / math.sqrt(Q.shape[-1]), -1)
+        heads = torch.matmul(attn, V)
+        out = torch.mm(heads.permute(1, 2, 0, 3).reshape(B * S, -1), att.W_out.reshape(-1, d)).view(B, S, d)
+        h = bn1((h + out).view(-1, d)).view(B, S, d)
+        h = bn2((h + ff(h)).view(-1, d)).view(B, S, d)
+    kvl = Fn.linear(h, folded_node_projection(model))
+    fixed = model.project_fixed_context(h.mean(1))
+    return h, kvl, fixed
+
+
+def bits_to_mask(bits, S):
+    """[...,4] int32 mask words -> [...,S] bool"""
+    j = torch.arange(S, device=bits.device)
+    words = bits.to(torch.int64) & 0xFFFFFFFF
+    return ((words[..., j >> 5] >> (j & 31)) & 1).bool()
+
+
+def teacher_forced_ll(model, emb, kvl, fixed, pi, mask_bits, veh, steps):
+    """log-likelihood ll[B,T] of the recorded actions, differentiable w.r.t. emb / kvl / fixed and the decoder
+    parameters.  Equivalent to running nets/DRLModel.py:259-276 step by step with the actions forced: given the
+    actions, every step's inputs (running max, vehicle scalars, mask) are known up front, so the T steps are
+    evaluated as one batch."""
+    B, T = pi.shape
+    S, d, Hh = emb.shape[1], emb.shape[2], model.n_heads
+    idx = pi[..., None].expand(B, T, d)
+    visited = emb.gather(1, idx)                                           # emb[pi_t]
+    run_max = torch.cummax(visited, 1)[0]
+    run_max = torch.cat([torch.zeros_like(run_max[:, :1]), run_max[:, :-1]], 1)    # zeros before first pick
+    W1 = model.FF_tour[0]
+    h1 = torch.relu(Fn.linear(veh, folded_tour_weight(model)) + Fn.linear(run_max, W1.weight[:, 128:]) + W1.bias)
+    ctx = model.FF_tour[2](h1)
+    now = torch.cat([torch.zeros_like(pi[:, :1]), pi[:, :-1]], 1)
+    q = (fixed[:, None] + ctx) + emb.gather(1, now[..., None].expand(B, T, d))
+    live = torch.arange(T, device=pi.device)[None] < steps[:, None]
+    mask = bits_to_mask(mask_bits, S)
+    mask = mask | (~live[..., None] & (torch.arange(S, device=pi.device) == 0))   # padded steps: depot only
+    gK = kvl[..., :d].view(B, S, Hh, -1)
+    gV = kvl[..., d:2 * d].view(B, S, Hh, -1)
+    lK = kvl[..., 2 * d:]
+    compat = torch.einsum("bthd,bshd->bhts", q.view(B, T, Hh, -1), gK) / math.sqrt(d // Hh)
+    compat = compat.masked_fill(~mask[:, None], -math.inf)
+    heads = torch.einsum("bhts,bshd->bthd", torch.softmax(compat, -1), gV).reshape(B, T, d)
+    logits = torch.einsum("btd,bsd->bts", heads, lK) / math.sqrt(d)
+    if model.tanh_clipping > 0:
+        logits = torch.tanh(logits) * model.tanh_clipping
+    logits = logits.masked_fill(~mask, -math.inf)
+    log_p = torch.log_softmax(logits / model.temp, -1)
+    ll = log_p.gather(2, pi[..., None])[..., 0]
+    return torch.where(live, ll, torch.zeros_like(ll))

@@ -1,0 +1,158 @@
+"""Drop-in ``VehicleRoutingDataset`` (the reference's problems/EVRP.py:9-280).
+
+Same constructor signature and attributes (``static``, ``dynamic``, ``Elevation``, ``distances``, ``slope``),
+same ``__getitem__`` tuple arity rule, and the two environment callbacks
+
+    update_dynamic(dynamic, distances, slope, now_idx, chosen_idx) -> (new_dynamic, reward[B,1])
+    update_mask(dynamic, distances, slope, chosen_idx)             -> mask[B,S]
+
+which call the bit-exact CUDA step kernels (csrc/evrp_step.cu) instead of ~1,400 ATen ops per step.
+When these bound methods are injected into ``evrp_b200.AttentionModel`` the model recognises them
+(``_evrp_b200_native``) and runs the whole rollout in its fused persistent kernel instead.
+
+Node layout is [depot, F stations, N customers] (the layout every consumer of the reference assumes; the
+reference's own generator has an off-by-one — SURVEY.md §2.1 D4 — which the documented one-line patch P1
+removes; this generator reproduces the patched reference's RNG stream on CPU bit for bit).
+"""
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from . import _lib
+from . import policy_math
+
+
+def parse_cvrplib(path):
+    """Minimal CVRPLIB reader (NODE_COORD_SECTION / DEMAND_SECTION / CAPACITY) for the generalisation test of
+    utils/functions.py:213-231.  Returns (coords [n,2] int, demands [n] int, capacity int)."""
+    coords, demands, capacity, section = [], [], None, None
+    with open(path) as f:
+        for raw in f:
+            line = raw.strip()
+            if not line:
+                continue
+            head = line.split(":")[0].strip().upper()
+            if head == "CAPACITY":
+                capacity = int(line.split(":")[1])
+            elif head in ("NODE_COORD_SECTION", "DEMAND_SECTION", "DEPOT_SECTION", "EOF"):
+                section = head
+            elif section == "NODE_COORD_SECTION":
+                _, x, y = line.split()[:3]
+                coords.append((int(float(x)), int(float(y))))
+            elif section == "DEMAND_SECTION":
+                demands.append(int(line.split()[1]))
+    if capacity is None or not coords or len(coords) != len(demands):
+        raise ValueError(f"{path}: not a CVRPLIB instance with coordinates, demands and capacity")
+    return coords, demands, capacity
+
+
+class VehicleRoutingDataset(Dataset):
+    _evrp_b200_native = True
+
+    def __init__(self, num_samples, input_size, t_limit, Start_SOC, velocity, max_load, max_demand, charging_num,
+                 seed, args, objective=None, device=None):
+        super().__init__()
+        if seed is None:
+            seed = np.random.randint(1234567890)
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        lib_test = bool(getattr(args, "CVRP_lib_test", False))
+        if lib_test:
+            num_samples = 1
+        self.num_samples, self.input_size = num_samples, input_size
+        self.max_load, self.max_demand = max_load, max_demand
+        self.Start_SOC, self.t_limit, self.velocity = Start_SOC, t_limit, velocity
+        self.charging_num = F = charging_num
+        self.objective = objective or ("DM" if str(getattr(args, "obj", "EM")).upper().startswith("D") else "EM")
+        self.device = torch.device(device) if device is not None else \
+            torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        n, N = num_samples, input_size
+        S = N + 1 + F
+        # RNG draw order of problems/EVRP.py:43-46,68,70,72,77 (CPU generator)
+        lo_x = torch.randint(0, 50, (n, 1, 20)); hi_x = torch.randint(51, 101, (n, 1, 20))
+        lo_y = torch.randint(0, 50, (n, 1, 20)); hi_y = torch.randint(51, 101, (n, 1, 20))
+        q = torch.arange(F) % 4                                       # quadrant of station i
+        sx = torch.where((q < 2)[None, :], lo_x[:, 0, :F], hi_x[:, 0, :F])
+        sy = torch.where((q % 2 == 0)[None, :], lo_y[:, 0, :F], hi_y[:, 0, :F])
+        stations = torch.stack([sx, sy], 1).float()                   # [n,2,F]
+        if lib_test:
+            coords, dem, cap = parse_cvrplib(args.CVRP_lib_path)
+            if len(coords) - 1 != N:
+                raise ValueError("CVRPlib instance size does not match input_size")
+            xy = torch.tensor(coords, dtype=torch.float32).t()[None]  # [1,2,n]
+            locations = torch.cat([xy[:, :, :1], stations, xy[:, :, 1:]], 2)
+            demands = torch.cat([torch.zeros(1, 1, 1 + F), (torch.tensor(dem[1:]) / float(cap))[None, None]], 2)
+        else:
+            depot = torch.randint(25, 75, (n, 2, 1))
+            customers = torch.randint(0, 101, (n, 2, N))
+            locations = torch.cat((depot.float(), stations, customers.float()), 2)
+            demands = torch.randint(1, max_demand + 1, (n, 1, S)) * 0.25
+            demands = demands / float(max_load)
+            demands[:, :, :1 + F] = 0
+        self.static = locations
+        self.Elevation = torch.randint(0, 101, (n, S)) / 1000
+        ones = torch.ones(n, 1, S)
+        self.dynamic = torch.cat((ones, demands.float(), ones * Start_SOC, ones * t_limit), 1).float()
+        self.distances = self.slope = None
+        if self._precomputed():                                       # problems/EVRP.py:85-92
+            chunks = [policy_math.pairwise_matrices(self.static[i:i + 8192].to(self.device),
+                                                    self.Elevation[i:i + 8192].to(self.device))
+                      for i in range(0, n, 8192)]
+            self.distances = torch.cat([c[0] for c in chunks], 0)
+            self.slope = torch.cat([c[1] for c in chunks], 0)
+            self.Elevation = self.Elevation.to(self.device)
+
+    def _precomputed(self):
+        return self.input_size <= 20 or self.num_samples <= 12800
+
+    def __len__(self):
+        return self.num_samples
+
+    def __getitem__(self, idx):                                       # problems/EVRP.py:97-102
+        if self._precomputed():
+            return (self.static[idx], self.dynamic[idx], self.distances[idx], self.slope[idx])
+        return (self.static[idx], self.dynamic[idx], self.Elevation[idx])
+
+    # ------------------------------------------------------------------------------------------
+    def _phys(self):
+        return _lib.make_phys(float(self.velocity), float(self.Start_SOC), float(self.t_limit), self.max_load,
+                              self.objective)
+
+    @staticmethod
+    def _cuda(t, dtype):
+        if not t.is_cuda:
+            raise _lib.EvrpLibraryError("evrp_b200 environment kernels need CUDA tensors (no CPU fallback)")
+        return t.to(dtype).contiguous()
+
+    def update_dynamic(self, dynamic, distances, slope, now_idx, chosen_idx):
+        """problems/EVRP.py:226-280.  EM: (new_dynamic, energy[B,1]); DM: (new_dynamic, distance[B,1], energy[B,1])
+        (DM-EVRP/problems/EVRP.py:280)."""
+        L = _lib.lib()
+        dyn = self._cuda(dynamic.detach(), torch.float32)
+        D, G = self._cuda(distances, torch.float32), self._cuda(slope, torch.float32)
+        now, ch = self._cuda(now_idx, torch.int64), self._cuda(chosen_idx, torch.int64)
+        B, _, S = dyn.shape
+        out = torch.empty_like(dyn)
+        e = torch.empty(B, 1, device=dyn.device)
+        dist = torch.empty(B, 1, device=dyn.device)
+        rc = L.evrp_update_dynamic(self._phys(), _lib.ptr(dyn), _lib.ptr(D), _lib.ptr(G), _lib.ptr(now), _lib.ptr(ch),
+                                   B, S, self.charging_num, _lib.ptr(out), _lib.ptr(e), _lib.ptr(dist),
+                                   _lib.stream_ptr())
+        _lib.check(rc, "evrp_update_dynamic")
+        if self.objective == "DM":
+            return out, dist, e
+        return out, e
+
+    def update_mask(self, dynamic, distances, slope, chosen_idx=None):
+        """problems/EVRP.py:105-223 -> mask [B,S] float 0/1 (all-zero once the whole batch is finished)."""
+        L = _lib.lib()
+        dyn = self._cuda(dynamic.detach(), torch.float32)
+        D, G = self._cuda(distances, torch.float32), self._cuda(slope, torch.float32)
+        ch = self._cuda(chosen_idx, torch.int64)
+        B, _, S = dyn.shape
+        mask = torch.empty(B, S, device=dyn.device)
+        flag = torch.empty(1, dtype=torch.int32, device=dyn.device)
+        rc = L.evrp_update_mask(self._phys(), _lib.ptr(dyn), _lib.ptr(D), _lib.ptr(G), _lib.ptr(ch), B, S,
+                                self.charging_num, _lib.ptr(mask), _lib.ptr(flag), _lib.stream_ptr())
+        _lib.check(rc, "evrp_update_mask")
+        return mask

@@ -1,0 +1,273 @@
+"""REINFORCE step, baselines and the data-parallel plumbing around the rollout kernels.
+
+Mirrors (same names, argument meaning, return values) the parts of the reference that sit directly on the hot
+path:
+    rollout                 utils/reinforce_baselines.py:51-69
+    ExponentialBaseline     utils/reinforce_baselines.py:149-173
+    RolloutBaseline         utils/reinforce_baselines.py:207-276
+    WarmupBaseline          utils/reinforce_baselines.py:95-140
+    BaselineDataset         utils/reinforce_baselines.py:279-295
+    clip_grad_norms         trainer.py:53-70
+    reinforce_step          trainer.py:111-127   (one optimisation step)
+
+Multi-GPU: one process per GPU, instances sharded by contiguous index range, weights
+replicated.  Rollouts need no collective.  Training adds exactly two NCCL collectives: one flat all-reduce of
+the 874,112 gradient floats per step and the scalar / paired-difference reductions of the baseline statistics.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch.utils.data import DataLoader, Dataset
+
+
+# ------------------------------------------------------------------------------------------------
+# sharding helpers
+# ------------------------------------------------------------------------------------------------
+def world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n, rank=None, world_size=None):
+    """contiguous instance range [lo, hi) owned by ``rank`` (remainder spread over the first ranks)"""
+    if rank is None:
+        rank, world_size = world()
+    base, rem = divmod(n, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_sum_(t):
+    r, w = world()
+    if w > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def global_mean(x):
+    """mean over the GLOBAL batch of a per-rank 1-D tensor (loss / baseline means are global, trainer.py:121)"""
+    s = torch.stack([x.sum().double(), torch.tensor(float(x.numel()), dtype=torch.float64, device=x.device)])
+    allreduce_sum_(s)
+    return (s[0] / s[1]).to(x.dtype)
+
+
+def allreduce_gradients(params, global_batch_scale=1.0):
+    """ONE flat bucket: sum the gradients of all ranks (NCCL all-reduce over NVLink), scale, scatter back."""
+    r, w = world()
+    grads = [p.grad for p in params if p.grad is not None]
+    if w == 1 or not grads:
+        if global_batch_scale != 1.0:
+            for g in grads:
+                g.mul_(global_batch_scale)
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    if global_batch_scale != 1.0:
+        flat.mul_(global_batch_scale)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+# ------------------------------------------------------------------------------------------------
+# rollout + baselines
+# ------------------------------------------------------------------------------------------------
+def rollout(actor, dataset, args):
+    """greedy eval-mode costs of a whole dataset -> CPU tensor [len(dataset)]"""
+    actor.set_decode_type("greedy")
+    actor.eval()
+    costs = []
+    for bat in DataLoader(dataset, batch_size=args.batch_size):
+        with torch.no_grad():
+            _, _, R = actor(bat)
+        costs.append(R.sum(1).cpu())
+    return torch.cat(costs, 0)
+
+
+class Baseline(object):
+    def wrap_dataset(self, dataset):
+        return dataset
+
+    def unwrap_batch(self, batch):
+        return batch, None
+
+    def eval(self, x, c):
+        raise NotImplementedError
+
+    def get_learnable_parameters(self):
+        return []
+
+    def epoch_callback(self, model, epoch):
+        pass
+
+    def state_dict(self):
+        return {}
+
+    def load_state_dict(self, state_dict):
+        pass
+
+
+class NoBaseline(Baseline):
+    def eval(self, x, c):
+        return 0, 0
+
+
+class ExponentialBaseline(Baseline):
+    """v <- beta v + (1-beta) mean(c), mean over the global batch"""
+
+    def __init__(self, beta):
+        self.beta, self.v = beta, None
+
+    def eval(self, x, c):
+        mean = global_mean(c.detach())
+        self.v = mean if self.v is None else self.beta * self.v + (1. - self.beta) * mean
+        self.v = self.v.detach()
+        return self.v, 0
+
+    def state_dict(self):
+        return {'v': self.v}
+
+    def load_state_dict(self, state_dict):
+        self.v = state_dict['v']
+
+
+class BaselineDataset(Dataset):
+    def __init__(self, dataset=None, baseline=None):
+        assert len(dataset) == len(baseline)
+        self.dataset, self.baseline = dataset, baseline
+
+    def __getitem__(self, item):
+        return {'data': self.dataset[item], 'baseline': self.baseline[item]}
+
+    def __len__(self):
+        return len(self.dataset)
+
+
+def paired_ttest_one_sided(candidate, baseline):
+    """scipy.stats.ttest_rel(candidate, baseline) from GLOBAL sufficient statistics (n, sum d, sum d^2) so that
+    each rank only contributes its shard of the validation set.  Returns (t, p_one_sided)."""
+    from scipy import stats
+    d = (np.asarray(candidate, np.float64) - np.asarray(baseline, np.float64))
+    s = torch.tensor([float(d.size), d.sum(), (d * d).sum()], dtype=torch.float64)
+    if world()[1] > 1:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        s = allreduce_sum_(s.to(dev)).cpu()
+    n, sd, sdd = s.tolist()
+    mean = sd / n
+    var = (sdd - n * mean * mean) / (n - 1)
+    t = mean / math.sqrt(var / n)
+    p = stats.t.sf(abs(t), n - 1) * 2
+    return t, p / 2
+
+
+class RolloutBaseline(Baseline):
+    def __init__(self, actor, valid_data, args, epoch=0):
+        self.dataset, self.args = valid_data, args
+        self._update_model(actor, epoch)
+
+    def _update_model(self, actor, epoch):
+        self.actor = actor                      # the reference aliases the live actor (no deepcopy), :217-218
+        self.bl_vals = rollout(self.actor, self.dataset, self.args).cpu().numpy()
+        self.mean = float(global_mean(torch.from_numpy(self.bl_vals)))
+        self.epoch = epoch
+
+    def wrap_dataset(self, dataset):
+        return BaselineDataset(dataset, rollout(self.actor, dataset, self.args).view(-1, 1))
+
+    def unwrap_batch(self, batch):
+        return batch['data'], batch['baseline'].view(-1)
+
+    def eval(self, x, c):
+        with torch.no_grad():
+            v, _, _ = self.actor(x)
+        return v, 0
+
+    def epoch_callback(self, model, epoch):
+        cand = rollout(model, self.dataset, self.args).cpu().numpy()
+        cand_mean = float(global_mean(torch.from_numpy(cand)))
+        if cand_mean - self.mean < 0:
+            t, p_val = paired_ttest_one_sided(cand, self.bl_vals)
+            assert t < 0, "T-statistic should be negative"
+            if p_val < self.args.bl_alpha:
+                self._update_model(model, epoch)
+
+    def state_dict(self):
+        return {'model': self.actor.state_dict(), 'epoch': self.epoch}
+
+    def load_state_dict(self, state_dict):
+        self.actor.load_state_dict(state_dict['model'])
+        self._update_model(self.actor, state_dict['epoch'])
+
+
+class WarmupBaseline(Baseline):
+    def __init__(self, baseline, n_epochs=1, warmup_exp_beta=0.8):
+        self.baseline = baseline
+        assert n_epochs > 0
+        self.warmup_baseline = ExponentialBaseline(warmup_exp_beta)
+        self.alpha, self.n_epochs = 0, n_epochs
+
+    def wrap_dataset(self, dataset):
+        return self.baseline.wrap_dataset(dataset) if self.alpha > 0 else self.warmup_baseline.wrap_dataset(dataset)
+
+    def unwrap_batch(self, batch):
+        return self.baseline.unwrap_batch(batch) if self.alpha > 0 else self.warmup_baseline.unwrap_batch(batch)
+
+    def eval(self, x, c):
+        if self.alpha == 1:
+            return self.baseline.eval(x, c)
+        if self.alpha == 0:
+            return self.warmup_baseline.eval(x, c)
+        v, l = self.baseline.eval(x, c)
+        vw, lw = self.warmup_baseline.eval(x, c)
+        return self.alpha * v + (1 - self.alpha) * vw, self.alpha * l + (1 - self.alpha * lw)   # :125 as written
+
+    def epoch_callback(self, model, epoch):
+        self.baseline.epoch_callback(model, epoch)
+        self.alpha = (epoch + 1) / float(self.n_epochs)
+
+    def state_dict(self):
+        return self.baseline.state_dict()
+
+    def load_state_dict(self, state_dict):
+        self.baseline.load_state_dict(state_dict)
+
+
+# ------------------------------------------------------------------------------------------------
+# one optimisation step
+# ------------------------------------------------------------------------------------------------
+def clip_grad_norms(param_groups, max_norm=math.inf):
+    """trainer.py:53-70"""
+    grad_norms = [torch.nn.utils.clip_grad_norm_(g['params'], max_norm if max_norm > 0 else math.inf, norm_type=2)
+                  for g in param_groups]
+    clipped = [min(g, max_norm) for g in grad_norms] if max_norm > 0 else grad_norms
+    return grad_norms, clipped
+
+
+def reinforce_step(actor, baseline, optimizer, batch, max_grad_norm=2.0, forced_actions=None):
+    """trainer.py:113-127 for one batch (this rank's shard of the global batch).
+    loss = mean over the GLOBAL batch of (reward - baseline).detach() * ll.sum(1)."""
+    r, w = world()
+    x, bl_val = baseline.unwrap_batch(batch)
+    pi, ll, R = actor(x) if forced_actions is None else actor(x, forced_actions=forced_actions)
+    reward = R.sum(1)
+    if bl_val is None:
+        bl_val, bl_loss = baseline.eval(x, reward)
+    else:
+        bl_val, bl_loss = bl_val.to(reward.device), 0
+    advantage = reward - bl_val
+    local = (advantage.detach() * ll.sum(1))
+    n_global = torch.tensor(float(local.numel()), device=local.device)
+    allreduce_sum_(n_global)
+    loss = local.sum() / n_global + bl_loss          # each rank holds its share of the global mean
+    optimizer.zero_grad()
+    loss.backward()
+    allreduce_gradients([p for g in optimizer.param_groups for p in g['params']])
+    grad_norms = clip_grad_norms(optimizer.param_groups, max_grad_norm)
+    optimizer.step()
+    loss_global = allreduce_sum_(loss.detach().clone())
+    return dict(loss=loss_global, reward=global_mean(reward.detach()), grad_norm=grad_norms[0][0], pi=pi, T=pi.shape[1])

@@ -1,0 +1,176 @@
+/* evrp_b200.h — C ABI of libevrp_b200.so (hand-written sm_100a CUDA behind plain pointers).
+ *
+ * Drop-in boundary for ONE hot path of mengchengTang/DRL-Energy-optimal-Routing-for-Electric-Vehicles:
+ * the batched autoregressive rollout of the Transformer pointer policy and the EVRP environment step.
+ * The reference is pure Python/PyTorch and has no FFI of its own; every entry point below cites the
+ * reference interface (file:line under /root/reference/EM-EVRP) that it replaces.  A maintainer binds
+ * these with ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in _host; tensors are dense, row-major,
+ *    fp32 unless stated; node layout is [depot, F stations, N customers], S = 1+F+N <= EVRP_MAX_S
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing and keeps
+ *    no state between calls; scratch comes from the caller (`*_workspace_bytes`)
+ *  - return value: 0 ok; <0 = -(cudaError_t) of a CUDA runtime failure or EVRP_E_* argument error.
+ *    Domain errors (the reference's Python asserts) are reported through a device-side int32 status word
+ *    the caller passes in and reads back together with the results (bit mask EVRP_ST_*).
+ *  - never throws, never falls back to the CPU.
+ */
+#ifndef EVRP_B200_H
+#define EVRP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVRP_ABI_VERSION 3
+#define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
+#define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
+#define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
+#define EVRP_FF 512             /* feed_forward_hidden (nets/DRLModel.py:64, nets/GraphEncoder.py:159) */
+#define EVRP_MAX_LAYERS 8
+
+/* argument errors (returned negated) */
+#define EVRP_E_BADARG 1000
+#define EVRP_E_TOO_MANY_NODES 1001
+#define EVRP_E_WORKSPACE 1002
+
+/* device status bits (OR-ed into *status by kernels) */
+#define EVRP_ST_NAN_LOGIT 1        /* nets/DRLModel.py:324,405  "Probs should not contain any nans"          */
+#define EVRP_ST_INFEASIBLE_PICK 2  /* nets/DRLModel.py:328      greedy/forced action is masked               */
+#define EVRP_ST_STEP_CAP 4         /* nets/DRLModel.py:255      an instance did not finish within max_steps  */
+#define EVRP_ST_NONUNIFORM_DYNAMIC 8 /* load/SOC/time rows of `dynamic` are not one scalar broadcast over S   */
+#define EVRP_ST_NO_FEASIBLE 16     /* every node masked for an unfinished instance                            */
+
+/* Vehicle / problem constants.  problems/EVRP.py:21-41.  The caller fills the folded fp32 constants with
+ * the SAME double-precision expressions the reference evaluates in Python, so that the state recipe is
+ * bit-reproducible.  evrp_phys_default() does that in C. */
+typedef struct {
+  float aero;        /* fp32(0.5*Cd*A*Ad*(velocity/3.6)**2)             problems/EVRP.py:247           */
+  float kd;          /* fp32(motor_d*battery_d)                          problems/EVRP.py:251           */
+  float kr;          /* fp32(motor_r*battery_r)                          problems/EVRP.py:252           */
+  float g, Cr, velocity, mc, w, max_load;
+  float start_soc, t_limit, charging_time, serve_time;
+  float charge_plus_serve;   /* fp32(charging_time + serve_time)         problems/EVRP.py:214           */
+  float inv_velocity, inv_3600; /* fp32(1/x), used only when div_mode==1                                  */
+  int32_t div_mode;  /* 0: x / scalar is an IEEE division (ATen CPU); 1: x * fp32(1/scalar) (ATen CUDA)  */
+  int32_t objective; /* 0: EM, reward = energy (EM-EVRP/problems/EVRP.py:280); 1: DM, reward = distance
+                        (DM-EVRP/problems/EVRP.py:231,280)                                               */
+} evrp_phys;
+
+void evrp_phys_default(evrp_phys* p, double velocity, double start_soc, double t_limit, double max_load);
+
+int evrp_abi_version(void);
+/* number of SMs / compute capability of the current device; <0 on error */
+int evrp_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) stand-alone environment step:  VehicleRoutingDataset.update_dynamic  problems/EVRP.py:226-280
+ *                                    VehicleRoutingDataset.update_mask     problems/EVRP.py:105-223
+ * dynamic [B,4,S] (load, demand, SOC, time), distances/slope [B,S,S], now/chosen int64 [B].
+ * ---------------------------------------------------------------------------------------------- */
+int evrp_update_dynamic(const evrp_phys* phys, const float* dynamic, const float* distances, const float* slope,
+                        const int64_t* now_idx, const int64_t* chosen_idx, int B, int S, int F,
+                        float* new_dynamic /*[B,4,S]*/, float* energy /*[B]*/, float* distance /*[B]*/,
+                        void* stream);
+
+/* `any_demand` is a 1-int device scratch word (zeroed by the call); the all-zero mask the reference returns
+ * when the whole batch is finished (problems/EVRP.py:127-128) is applied by a second tiny kernel. */
+int evrp_update_mask(const evrp_phys* phys, const float* dynamic, const float* distances, const float* slope,
+                     const int64_t* chosen_idx, int B, int S, int F, float* mask /*[B,S] 0/1*/,
+                     int32_t* any_demand, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) encoder + decoder precompute:  AttentionModel._init_embed        nets/DRLModel.py:192-200
+ *                                    GraphAttentionEncoder.forward     nets/GraphEncoder.py:202-214
+ *                                    AttentionModel._precompute        nets/DRLModel.py:345-362
+ * Weights arrive PACKED k-major ([in_features][out_features], out contiguous) so that every GEMM reads its
+ * B operand coalesced; evrp_b200/model.py::pack_weights builds them from the reference's state_dict keys
+ * (one transpose/concat per tensor, redone only when the parameters change).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float *Wqkv;             /* [128,384]  column h*16+d of block 0/1/2 = W_query/W_key/W_val[h,:,d]
+                                               (embedder.layers.l.0.module.*, nets/GraphEncoder.py:41-43)  */
+  const float *Wo;               /* [128,128]  W_out.view(H*16,128)          nets/GraphEncoder.py:104-107   */
+  const float *bn1_scale, *bn1_shift;   /* [128] eval-mode BatchNorm1d folded to y = x*scale + shift
+                                               (layers.l.1.normalizer, nets/GraphEncoder.py:142-145)        */
+  const float *ff1_w, *ff1_b;    /* [128,512],[512]  layers.l.2.module.0.weight^T / bias                    */
+  const float *ff2_w, *ff2_b;    /* [512,128],[128]  layers.l.2.module.2.weight^T / bias                    */
+  const float *bn2_scale, *bn2_shift;   /* layers.l.3.normalizer                                            */
+} evrp_layer_weights;
+
+typedef struct {
+  const float *depot_w, *depot_b;      /* [128,2],[128]  init_embed_depot_and_station (state_dict layout)   */
+  const float *station_w, *station_b;  /* [128,2],[128]  init_embed_station                                 */
+  const float *cust_w, *cust_b;        /* [128,3],[128]  init_embed                                         */
+  int32_t n_layers;
+  evrp_layer_weights layers[EVRP_MAX_LAYERS];
+  const float *node_proj;              /* [128,384]  project_node_embeddings.weight^T; columns 0..127 glimpse-K,
+                                          128..255 glimpse-V, 256..383 logit-K with project_out folded in:
+                                          lK_fold = project_out.weight^T @ W_logitK, so that
+                                          logits[j] = heads . lK[j]           (nets/DRLModel.py:436-444)     */
+  const float *fixed_ctx_w;            /* [128,128]  project_fixed_context.weight^T                         */
+} evrp_encoder_weights;
+
+size_t evrp_encoder_workspace_bytes(int B, int S);
+
+/* Eval-mode forward (BatchNorm folded to per-channel affine).  Outputs: emb [B,S,128] node embeddings,
+ * kvl [B,S,384] = per node (glimpse-K | glimpse-V | folded logit-K), fixed_ctx [B,128]. */
+int evrp_encoder_forward(const evrp_encoder_weights* w, const float* static_xy /*[B,2,S]*/,
+                         const float* dynamic /*[B,4,S]*/, int B, int S, int F,
+                         float* emb, float* kvl, float* fixed_ctx,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) persistent rollout:  AttentionModel._inner        nets/DRLModel.py:240-280
+ *                          route_feature                :203-237
+ *                          _get_log_p/_one_to_many_logits :379-452
+ *                          _select_node                 :316-342
+ *                          _calc_log_likelihood         :182-190
+ *                          + update_dynamic / update_mask fused (problems/EVRP.py:105-280)
+ * One launch for the whole rollout; instances retire individually; outputs beyond an instance's last
+ * step keep the zeros the caller memset (the reference pads finished rows with pi=0, ll=0, R=0).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float *w1_veh;   /* [3,512]    (FF_tour.0.weight[:, :128] @ tour.weight)^T, folded in fp64     */
+  const float *w1_max;   /* [128,512]  FF_tour.0.weight[:, 128:]^T                                      */
+  const float *b1;       /* [512]      FF_tour.0.bias                                                   */
+  const float *w2;       /* [512,128]  FF_tour.2.weight^T                                               */
+  const float *b2;       /* [128]      FF_tour.2.bias                                                   */
+} evrp_decoder_weights;
+
+#define EVRP_DECODE_GREEDY 0
+#define EVRP_DECODE_SAMPLE 1
+
+typedef struct {
+  int32_t decode_type;       /* EVRP_DECODE_*                          set_decode_type nets/DRLModel.py:104 */
+  float   temp;              /* softmax temperature                    nets/DRLModel.py:403                 */
+  float   tanh_clipping;     /* 10.0                                   nets/DRLModel.py:447                 */
+  int32_t max_steps;         /* output width Tcap (<= 1000)            nets/DRLModel.py:255                 */
+  uint64_t seed;             /* counter-based RNG seed for sampling                                         */
+  int32_t n_replicas;        /* sample_many: rollouts per instance sharing one encoder output (>=1);
+                                rollout row r uses instance r % B (replica-major, nets/DRLModel.py:291-294)   */
+} evrp_rollout_cfg;
+
+int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evrp_rollout_cfg* cfg,
+                 const float* emb /*[B,S,128]*/, const float* kvl /*[B,S,384]*/, const float* fixed_ctx /*[B,128]*/,
+                 const float* dynamic0 /*[B,4,S]*/, const float* distances /*[B,S,S]*/, const float* slope,
+                 int B, int S, int F,
+                 const int64_t* forced_actions /*[B*R,Tcap] or NULL*/, const float* uniforms /*[B*R,Tcap] or NULL*/,
+                 int64_t* pi /*[B*R,Tcap]*/, float* ll /*[B*R,Tcap]*/, float* reward /*[B*R,Tcap]*/,
+                 float* energy /*[B*R,Tcap] or NULL*/,
+                 uint32_t* saved_mask /*[B*R,Tcap,4] or NULL*/, float* saved_veh /*[B*R,Tcap,3] or NULL*/,
+                 int32_t* steps_used /*[B*R]*/, int32_t* t_max /*[1] atomicMax*/, int32_t* status /*[1]*/,
+                 void* stream);
+
+/* sample_many reduction (nets/DRLModel.py:301-311): per instance min cost over replicas + its tour. */
+int evrp_sample_min(const float* reward /*[B*R,Tcap]*/, const int64_t* pi, int B, int R, int Tcap,
+                    float* mincost /*[B]*/, int32_t* argmin /*[B]*/, int64_t* minpi /*[B,Tcap]*/, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

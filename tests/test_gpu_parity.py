@@ -1,0 +1,393 @@
+"""GPU parity tests (run by the driver with ``-m gpu`` on a B200).
+
+Every test calls the product through its public API (``evrp_b200.AttentionModel`` /
+``evrp_b200.VehicleRoutingDataset``), i.e. through the C ABI of libevrp_b200.so, and checks it against
+  (i) the committed golden outputs of the patched reference (tests/golden/*.npz) and
+  (ii) the numpy oracle (oracle/evrp_oracle.py) on the same seeded inputs.
+Bars (BASELINE.json north_star): masks and state bit-exact; costs 1e-4 relative (they are bit-exact whenever the
+tours match); log-probs 2e-5 absolute; greedy tours equal except audited near-ties; gradients 1e-3 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import evrp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+LOGP_TOL = 2e-5
+NEAR_TIE = 1e-4
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def bn_perturb_numpy(weights):
+    rs = np.random.RandomState(7)
+    out = {}
+    for k, v in weights.items():
+        if "normalizer.running_mean" in k:
+            v = (rs.randn(*v.shape) * 0.2).astype(np.float32)
+        elif "normalizer.running_var" in k:
+            v = (rs.rand(*v.shape) * 1.5 + 0.5).astype(np.float32)
+        elif "normalizer.weight" in k:
+            v = (rs.rand(*v.shape) + 0.5).astype(np.float32)
+        elif "normalizer.bias" in k:
+            v = (rs.randn(*v.shape) * 0.1).astype(np.float32)
+        out[k] = v
+    return out
+
+
+@pytest.fixture(scope="module")
+def evrp():
+    import evrp_b200
+    evrp_b200.lib()                       # raises if the CUDA library is missing: no fallback
+    return evrp_b200
+
+
+def args_for(N, F=5, obj="EM"):
+    import types
+    return types.SimpleNamespace(CVRP_lib_test=False, Start_SOC=80., t_limit=10., num_nodes=N, charging_num=F,
+                                 velocity=50., obj=obj)
+
+
+def make_model(evrp, N, weights, obj="EM"):
+    a = args_for(N, obj=obj)
+    ds = evrp.VehicleRoutingDataset(2, N, 10., 80., 50., 4, 4, 5, 1, a, objective=obj)
+    m = evrp.AttentionModel(128, 128, a, n_encode_layers=3, update_dynamic=ds.update_dynamic,
+                            update_mask=ds.update_mask)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()})
+    return m.cuda().eval(), ds
+
+
+def batch_of(g):
+    return tuple(torch.from_numpy(g[k]).cuda() for k in ("static", "dynamic", "distances", "slope"))
+
+
+def mask_from_bits(bits, S):
+    bits = bits.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    j = np.arange(S)
+    return ((bits[..., j >> 5] >> (j & 31)) & 1).astype(np.uint8)
+
+
+@pytest.fixture(scope="module")
+def weights():
+    return dict(load("weights_seed0.npz"))
+
+
+# ---------------------------------------------------------------------------------------------
+# a7 / a8: stand-alone environment step kernels, bit-exact against the reference trace
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["greedy_n20.npz", "greedy_n50.npz", "greedy_n100.npz"])
+def test_step_kernels_bit_exact(evrp, name):
+    g = load(name)
+    N = g["static"].shape[2] - 6
+    ds = evrp.VehicleRoutingDataset(2, N, 10., 80., 50., 4, 4, 5, 1, args_for(N))
+    _, _, D, G = batch_of(g)
+    pi = torch.from_numpy(g["pi"]).cuda()
+    dyn = torch.from_numpy(g["dynamic"]).cuda()
+    now = torch.zeros(pi.shape[0], dtype=torch.int64, device="cuda")
+    T = pi.shape[1]
+    for t in range(T):
+        new_dyn, r = ds.update_dynamic(dyn, D, G, now, pi[:, t])
+        assert np.array_equal(new_dyn.cpu().numpy(), g["t_dynamic"][:, t]), f"state differs at step {t}"
+        assert np.array_equal(r[:, 0].cpu().numpy(), g["R"][:, t]), f"reward differs at step {t}"
+        mask = ds.update_mask(new_dyn, D, G, pi[:, t])
+        want = g["t_mask"][:, t + 1] if t + 1 < T else np.zeros_like(g["t_mask"][:, 0])
+        assert np.array_equal(mask.cpu().numpy().astype(np.uint8), want), f"mask differs at step {t}"
+        dyn, now = new_dyn, pi[:, t]
+
+
+def test_step_kernels_vs_oracle_random_states(evrp):
+    """random (instance, state) pairs reached by a sampled oracle rollout, incl. ragged batch (B=37)"""
+    static, dynamic, elev = O.generate_instances(37, 30, seed=11)
+    D, G = O.pairwise_matrices(static, elev)
+    c = O.EVRPConsts()
+    ds = evrp.VehicleRoutingDataset(2, 30, 10., 80., 50., 4, 4, 5, 1, args_for(30))
+    rng = np.random.RandomState(5)
+    dyn = dynamic.copy(); now = np.zeros(37, np.int64); mask = np.ones((37, 36), np.float32)
+    Dc, Gc = torch.from_numpy(D).cuda(), torch.from_numpy(G).cuda()
+    for t in range(60):
+        if not mask.any():
+            break
+        p = mask / mask.sum(1, keepdims=True)
+        sel = np.array([rng.choice(36, p=p[b]) for b in range(37)])
+        nd, e, dist = O.update_dynamic(c, dyn, D, G, now, sel)
+        nm = O.update_mask(c, nd, D, G, sel)
+        gd, ge = ds.update_dynamic(torch.from_numpy(dyn).cuda(), Dc, Gc, torch.from_numpy(now).cuda(),
+                                   torch.from_numpy(sel).cuda())
+        gm = ds.update_mask(gd, Dc, Gc, torch.from_numpy(sel).cuda())
+        assert np.array_equal(gd.cpu().numpy(), nd) and np.array_equal(ge.cpu().numpy(), e)
+        assert np.array_equal(gm.cpu().numpy(), nm)
+        dyn, now, mask = nd, sel, nm
+
+
+# ---------------------------------------------------------------------------------------------
+# a1-a3: encoder + precompute against the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,bn", [("greedy_n20.npz", False), ("greedy_bn_n20.npz", True), ("greedy_n100.npz", False)])
+def test_encoder_matches_oracle(evrp, weights, name, bn):
+    g = load(name)
+    W = bn_perturb_numpy(weights) if bn else weights
+    N = g["static"].shape[2] - 6
+    m, _ = make_model(evrp, N, W)
+    static, dynamic, _, _ = batch_of(g)
+    emb, kvl, fixed = m.encode(static, dynamic)
+    ref = O.encoder(W, O.init_embed(W, g["static"], g["dynamic"], 5))
+    assert np.abs(emb.cpu().numpy() - ref).max() < 2e-5
+    fc, gK, gV, lK = O.precompute(W, ref)
+    B, S = ref.shape[:2]
+    kv = kvl.cpu().numpy()
+    assert np.abs(kv[..., :128] - gK.transpose(0, 2, 1, 3).reshape(B, S, 128)).max() < 2e-5
+    assert np.abs(kv[..., 128:256] - gV.transpose(0, 2, 1, 3).reshape(B, S, 128)).max() < 2e-5
+    lK_fold = lK @ W["project_out.weight"]            # (Wout^T Wl) emb = lK @ Wout
+    assert np.abs(kv[..., 256:] - lK_fold).max() < 5e-5
+    assert np.abs(fixed.cpu().numpy() - fc).max() < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# a4-a8 fused: teacher-forced rollout against the reference trace
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["greedy_n20.npz", "greedy_bn_n20.npz", "greedy_n50.npz", "greedy_n100.npz"])
+def test_teacher_forced_rollout(evrp, weights, name):
+    g = load(name)
+    W = bn_perturb_numpy(weights) if bool(g["bn_perturbed"]) else weights
+    S = g["static"].shape[2]
+    m, _ = make_model(evrp, S - 6, W)
+    o = m.forward_forced(batch_of(g), torch.from_numpy(g["pi"]), save_trace=True)
+    assert o["status"] == 0
+    assert np.array_equal(o["pi"].cpu().numpy(), g["pi"])
+    assert np.array_equal(o["R"].cpu().numpy(), g["R"])                       # rewards bit-exact
+    steps = o["steps"].cpu().numpy()
+    got = mask_from_bits(o["mask_bits"], S)
+    for b in range(len(steps)):                                               # masks bit-exact while the row is live
+        assert np.array_equal(got[b, :steps[b]], g["t_mask"][b, :steps[b]]), f"mask differs, instance {b}"
+    assert np.abs(o["ll"].cpu().numpy() - g["ll"]).max() < LOGP_TOL
+
+
+@pytest.mark.parametrize("name", ["greedy_n20.npz", "greedy_n50.npz", "greedy_n100.npz"])
+def test_free_running_greedy_tours(evrp, weights, name):
+    g = load(name)
+    S = g["static"].shape[2]
+    m, _ = make_model(evrp, S - 6, weights)
+    m.set_decode_type("greedy")
+    with torch.no_grad():
+        pi, ll, R = m(batch_of(g))
+    pi, R = pi.cpu().numpy(), R.cpu().numpy()
+    ref, lp = g["pi"], g["t_log_p"]
+    exact = 0
+    for b in range(ref.shape[0]):
+        T = min(pi.shape[1], ref.shape[1])
+        neq = np.nonzero(pi[b, :T] != ref[b, :T])[0]
+        if len(neq) == 0:
+            exact += 1
+            assert abs(R[b].sum() - g["R"][b].sum()) <= 1e-4 * abs(g["R"][b].sum())
+            continue
+        t = neq[0]
+        gap = abs(lp[b, t, pi[b, t]] - lp[b, t, ref[b, t]])
+        assert gap < NEAR_TIE, f"instance {b} diverges at step {t}, log-prob gap {gap} is not a near-tie"
+    assert exact >= 0.8 * ref.shape[0], f"only {exact}/{ref.shape[0]} tours identical"
+
+
+def test_dm_objective(evrp, weights):
+    g = load("dm_n20.npz")
+    m, _ = make_model(evrp, 20, weights, obj="DM")
+    o = m.forward_forced(batch_of(g), torch.from_numpy(g["pi"]))
+    assert np.array_equal(o["R"].cpu().numpy(), g["R"])          # reward := distance
+    assert np.array_equal(o["E"].cpu().numpy(), g["E"])          # energy carried as side output
+
+
+def test_three_tuple_input_matches_four_tuple(evrp, weights):
+    g = load("greedy_n20.npz")
+    m, _ = make_model(evrp, 20, weights)
+    m.set_decode_type("greedy")
+    st, dy, D, G = batch_of(g)
+    D2, G2 = evrp.policy_math.pairwise_matrices(st, torch.from_numpy(g["elevation"]).cuda())
+    assert (D2 - D).abs().max().item() <= 8e-6 and (G2 - G).abs().max().item() < 1e-8
+    with torch.no_grad():
+        pi3, _, R3 = m((st, dy, torch.from_numpy(g["elevation"]).cuda()))
+    assert pi3.shape[0] == st.shape[0] and torch.isfinite(R3).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# sampling, sample_many
+# ---------------------------------------------------------------------------------------------
+def test_sampled_rollout_consistent_with_oracle(evrp, weights):
+    g = load("greedy_n20.npz")
+    m, _ = make_model(evrp, 20, weights)
+    m.set_decode_type("sample")
+    with torch.no_grad():
+        pi, ll, R = m(batch_of(g))
+    o = O.rollout(weights, g["static"], g["dynamic"], g["distances"], g["slope"], forced=pi.cpu().numpy())
+    assert np.array_equal(o["R"], R.cpu().numpy())
+    assert np.abs(o["ll"] - ll.cpu().numpy()).max() < LOGP_TOL
+    assert (ll.cpu().numpy() > -1000).all()                      # nets/DRLModel.py:187
+
+
+def test_sampling_follows_the_policy_distribution(evrp, weights):
+    """first-step picks over many replicas vs the oracle's step-0 probabilities"""
+    g = load("greedy_n20.npz")
+    m, _ = make_model(evrp, 20, weights)
+    m.set_decode_type("sample")
+    batch = tuple(t[:2].contiguous() for t in batch_of(g))
+    emb, kvl, fixed = m.encode(batch[0], batch[1])
+    reps = 4096
+    o = m.rollout(emb, kvl, fixed, batch[1], batch[2], batch[3], n_replicas=reps)
+    first = o["pi"][:, 0].view(reps, 2).cpu().numpy()
+    tr = O.rollout(weights, g["static"][:2], g["dynamic"][:2], g["distances"][:2], g["slope"][:2], trace=True)
+    p0 = np.exp(tr["log_p"][:, 0])
+    for b in range(2):
+        freq = np.bincount(first[:, b], minlength=26) / reps
+        assert np.abs(freq - p0[b]).max() < 5 * np.sqrt(0.25 / reps)
+
+
+def test_injected_uniforms_inverse_cdf(evrp, weights):
+    g = load("greedy_n20.npz")
+    m, _ = make_model(evrp, 20, weights)
+    m.set_decode_type("sample")
+    st, dy, D, G = batch_of(g)
+    emb, kvl, fixed = m.encode(st, dy)
+    B = st.shape[0]
+    u = torch.rand(B, 200, generator=torch.Generator().manual_seed(3)).cuda()
+    o = m.rollout(emb, kvl, fixed, dy, D, G, uniforms=u, max_steps=200)
+    pi = o["pi"].cpu().numpy()
+    tr = O.rollout(weights, g["static"], g["dynamic"], g["distances"], g["slope"], forced=pi, trace=True)
+    un = u.cpu().numpy()
+    steps = o["steps"].cpu().numpy()
+    for b in range(B):
+        for t in range(steps[b]):
+            cdf = np.cumsum(np.exp(tr["log_p"][b, t].astype(np.float64)))
+            lo = cdf[pi[b, t] - 1] if pi[b, t] > 0 else 0.0
+            assert lo - 1e-5 <= un[b, t] * cdf[-1] <= cdf[pi[b, t]] + 1e-5
+
+
+def test_sample_many_min_over_replicas(evrp, weights):
+    g = load("greedy_n20.npz")
+    m, _ = make_model(evrp, 20, weights)
+    m.set_decode_type("sample")
+    batch = tuple(t[:8].contiguous() for t in batch_of(g))
+    mincost, minpi = m.sample_many(batch, batch_rep=64, iter_rep=2)
+    assert mincost.shape == (8,) and minpi.shape[0] == 8
+    o = O.rollout(weights, g["static"][:8], g["dynamic"][:8], g["distances"][:8], g["slope"][:8],
+                  forced=minpi.cpu().numpy())
+    assert np.allclose(o["R"].sum(1), mincost.cpu().numpy(), rtol=1e-5)
+    m.set_decode_type("greedy")
+    with torch.no_grad():
+        _, _, Rg = m(batch)
+    assert (mincost <= Rg.sum(1) * 1.5).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# a10: REINFORCE gradients, teacher-forced on the reference's sampled actions
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_reinforce_gradients(evrp, weights, mode):
+    g = load("sample_n20.npz")
+    W = bn_perturb_numpy(weights)
+    m, _ = make_model(evrp, 20, W)
+    m.train(mode == "train")
+    pi = torch.from_numpy(g["pi"]).cuda()
+    m.zero_grad()
+    pi2, ll, R = m(batch_of(g), forced_actions=pi)
+    assert torch.equal(pi2, pi) and np.array_equal(R.cpu().numpy(), g["R"])
+    assert np.abs(ll.detach().cpu().numpy() - g[f"ll_{mode}"]).max() < LOGP_TOL
+    loss = (torch.from_numpy(g["adv"]).cuda() * ll.sum(1)).mean()
+    loss.backward()
+    assert abs(loss.item() - float(g[f"loss_{mode}"])) < 1e-4 * abs(float(g[f"loss_{mode}"]))
+    num = den = 0.0
+    gmax = max(float(np.abs(g[f"g_{mode}/{k}"]).max()) for k, _ in m.named_parameters())
+    for k, p in m.named_parameters():
+        ref = torch.from_numpy(g[f"g_{mode}/{k}"]).cuda()
+        assert p.grad is not None, k
+        num += float((p.grad - ref).norm() ** 2); den += float(ref.norm() ** 2)
+        if float(ref.abs().max()) > 1e-4 * gmax:          # tensors whose true gradient is ~0 (bias before BN) carry noise only
+            assert float((p.grad - ref).norm() / ref.norm()) < 1e-3, k
+    assert (num / den) ** 0.5 < 1e-3
+    if mode == "train":                                    # running statistics updated like nn.BatchNorm1d
+        for k, v in m.state_dict().items():
+            if "running" in k:
+                assert np.allclose(v.cpu().numpy(), g["bn_after/" + k], rtol=1e-4, atol=1e-5), k
+
+
+def test_reinforce_step_runs_and_learns_signal(evrp, weights):
+    from evrp_b200 import train as T
+    g = load("greedy_n20.npz")
+    m, _ = make_model(evrp, 20, weights)
+    m.train(); m.set_decode_type("sample")
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    bl = T.ExponentialBaseline(0.8)
+    before = [p.detach().clone() for p in m.parameters()]
+    out = T.reinforce_step(m, bl, opt, batch_of(g), max_grad_norm=2.0)
+    assert torch.isfinite(out["loss"]) and out["T"] > 20
+    assert any(not torch.equal(a, b) for a, b in zip(before, m.parameters()))
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's full config-4 size (EM-EVRP-100, B=8192)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties_and_shard_invariance(evrp, weights):
+    B, N, F = 8192, 100, 5
+    static, dynamic, elev = O.generate_instances(B, N, seed=2024)
+    m, _ = make_model(evrp, N, weights)
+    m.set_decode_type("greedy")
+    st, dy, el = (torch.from_numpy(a).cuda() for a in (static, dynamic, elev))
+    D, G = evrp.policy_math.pairwise_matrices(st, el)
+    with torch.no_grad():
+        pi, ll, R = m((st, dy, D, G))
+        halves = [m((st[s], dy[s], D[s], G[s])) for s in (slice(0, B // 2), slice(B // 2, B))]
+    T = pi.shape[1]
+    # shard invariance: the batch result is the concatenation of its shards (zero-padded to the global T)
+    for (p, l, r), s in zip(halves, (slice(0, B // 2), slice(B // 2, B))):
+        assert torch.equal(torch.nn.functional.pad(p, (0, T - p.shape[1])), pi[s])
+        assert torch.equal(torch.nn.functional.pad(r, (0, T - r.shape[1])), R[s])
+    pin = pi.cpu().numpy()
+    # every customer is visited, tours end at the depot, finished rows are zero-padded
+    visited = np.zeros((B, N + F + 1), bool)
+    np.put_along_axis(visited, pin, True, 1)
+    assert visited[:, F + 1:].all()
+    assert (pin[:, -1] == 0).all()
+    assert (R >= 0).all() and torch.isfinite(ll).all() and (ll <= 0).all()
+    # replaying the tours through the oracle's environment reproduces the costs bit-exactly (sample of rows)
+    idx = np.arange(0, B, 512)
+    Dn, Gn = D[idx].cpu().numpy(), G[idx].cpu().numpy()
+    c = O.EVRPConsts()
+    dyn = dynamic[idx].copy(); now = np.zeros(len(idx), np.int64)
+    Rn = R.cpu().numpy()[idx]
+    for t in range(T):
+        dyn, e, _ = O.update_dynamic(c, dyn, Dn, Gn, now, pin[idx, t])
+        assert np.array_equal(e[:, 0], Rn[:, t])
+        now = pin[idx, t]
+    assert (dyn[:, 1] == 0).all()                         # all demand served
+
+
+def test_ragged_and_tiny_batches(evrp, weights):
+    g = load("greedy_n20.npz")
+    m, _ = make_model(evrp, 20, weights)
+    m.set_decode_type("greedy")
+    full = batch_of(g)
+    with torch.no_grad():
+        pi_full, _, R_full = m(full)
+        for B in (1, 3, 9):
+            pi, _, R = m(tuple(t[:B].contiguous() for t in full))
+            assert torch.equal(R.sum(1), R_full[:B].sum(1))
+            assert torch.equal(pi, pi_full[:B, :pi.shape[1]])
+
+
+def test_errors_are_loud(evrp, weights):
+    m, _ = make_model(evrp, 20, weights)
+    g = load("greedy_n20.npz")
+    bad = torch.from_numpy(g["pi"]).clone()
+    bad[:, 1] = bad[:, 0]                                  # revisiting the node just served is always masked
+    with pytest.raises(AssertionError):
+        m.forward_forced(batch_of(g), bad)
+    m.set_decode_type(None)
+    with pytest.raises(AssertionError):
+        m(batch_of(g))
+    big = torch.zeros(1, 2, 200).cuda(), torch.ones(1, 4, 200).cuda(), torch.zeros(1, 200, 200).cuda(), torch.zeros(1, 200, 200).cuda()
+    m.set_decode_type("greedy")
+    with pytest.raises(evrp.EvrpLibraryError):
+        m(big)
