@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libevrp_b200.so")
 
 EVRP_MAX_S = 128
+ABI_VERSION = 4
 EVRP_MAX_LAYERS = 8
 ST_NAN_LOGIT, ST_INFEASIBLE_PICK, ST_STEP_CAP, ST_NONUNIFORM_DYNAMIC, ST_NO_FEASIBLE = 1, 2, 4, 8, 16
 DECODE_GREEDY, DECODE_SAMPLE = 0, 1
@@ -28,13 +29,15 @@ class Phys(C.Structure):
 
 class LayerWeights(C.Structure):
     _fields_ = [(n, _FP) for n in ("Wqkv", "Wo", "bn1_scale", "bn1_shift", "ff1_w", "ff1_b", "ff2_w", "ff2_b",
-                                   "bn2_scale", "bn2_shift")]
+                                   "bn2_scale", "bn2_shift", "Wqkv_hi", "Wqkv_lo", "Wo_hi", "Wo_lo",
+                                   "ff1_hi", "ff1_lo", "ff2_hi", "ff2_lo")]
 
 
 class EncoderWeights(C.Structure):
     _fields_ = [(n, _FP) for n in ("depot_w", "depot_b", "station_w", "station_b", "cust_w", "cust_b")] + \
         [("n_layers", C.c_int32), ("layers", LayerWeights * EVRP_MAX_LAYERS),
-         ("node_proj", _FP), ("fixed_ctx_w", _FP)]
+         ("node_proj", _FP), ("fixed_ctx_w", _FP), ("node_proj_hi", _FP), ("node_proj_lo", _FP),
+         ("gemm_mode", C.c_int32)]
 
 
 class DecoderWeights(C.Structure):
@@ -83,7 +86,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.evrp_abi_version() != 3:
+        if L.evrp_abi_version() != ABI_VERSION:
             raise EvrpLibraryError("libevrp_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib

@@ -244,6 +244,11 @@ fixed_context_kernel(const float* __restrict__ emb, int S, const float* __restri
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// evrp_tc_gemm.cu
+int tc_gemm(int epi, const float* A, int lda, const float* Wh, const float* Wl, float* C, int ldc, int M, int N, int K,
+            const float* bias, const float* resid, int ldr, const float* scale, const float* shift, int sm_count,
+            cudaStream_t st);
+
 }  // namespace evrp
 
 extern "C" {
@@ -283,25 +288,44 @@ int evrp_encoder_forward(const evrp_encoder_weights* w, const float* static_xy, 
   EVRP_CUDA_OK(cudaFuncSetAttribute(self_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
   float* cur = ha;
   float* other = hb;
+  const bool tcm = (w->gemm_mode == 0);
+  int sm_count = 148;
+  if (tcm) {
+    int dev = 0;
+    EVRP_CUDA_OK(cudaGetDevice(&dev));
+    EVRP_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int rc;
   for (int l = 0; l < w->n_layers; ++l) {
     const evrp_layer_weights& L = w->layers[l];
-    int rc;
-    // Q|K|V = h @ Wqkv
-    if ((rc = launch_sgemm<0>(cur, D, L.Wqkv, 384, wide, 384, M, 384, D, nullptr, nullptr, 0, nullptr, nullptr, st))) return rc;
-    self_attention_kernel<<<B, 256, attn_smem, st>>>(wide, S, heads);
-    EVRP_LAUNCH_OK();
-    // h1 = BN1(h + heads @ Wo)
-    if ((rc = launch_sgemm<EPI_RESID | EPI_AFFINE>(heads, D, L.Wo, D, other, D, M, D, D, nullptr, cur, D, L.bn1_scale, L.bn1_shift, st))) return rc;
-    // f = relu(h1 @ W1^T + b1)
-    if ((rc = launch_sgemm<EPI_BIAS | EPI_RELU>(other, D, L.ff1_w, FF, wide, FF, M, FF, D, L.ff1_b, nullptr, 0, nullptr, nullptr, st))) return rc;
-    // h2 = BN2(h1 + f @ W2^T + b2)
     float* dst = (l == w->n_layers - 1) ? emb : cur;
-    if ((rc = launch_sgemm<EPI_BIAS | EPI_RESID | EPI_AFFINE>(wide, FF, L.ff2_w, D, dst, D, M, D, FF, L.ff2_b, other, D, L.bn2_scale, L.bn2_shift, st))) return rc;
+    if (tcm) {
+      // Q|K|V = h @ Wqkv
+      if ((rc = tc_gemm(0, cur, D, L.Wqkv_hi, L.Wqkv_lo, wide, 384, M, 384, D, nullptr, nullptr, 0, nullptr, nullptr, sm_count, st))) return rc;
+      self_attention_kernel<<<B, 256, attn_smem, st>>>(wide, S, heads);
+      EVRP_LAUNCH_OK();
+      // h1 = BN1(h + heads @ Wo)
+      if ((rc = tc_gemm(EPI_RESID | EPI_AFFINE, heads, D, L.Wo_hi, L.Wo_lo, other, D, M, D, D, nullptr, cur, D, L.bn1_scale, L.bn1_shift, sm_count, st))) return rc;
+      // f = relu(h1 @ W1^T + b1)
+      if ((rc = tc_gemm(EPI_BIAS | EPI_RELU, other, D, L.ff1_hi, L.ff1_lo, wide, FF, M, FF, D, L.ff1_b, nullptr, 0, nullptr, nullptr, sm_count, st))) return rc;
+      // h2 = BN2(h1 + f @ W2^T + b2)
+      if ((rc = tc_gemm(EPI_BIAS | EPI_RESID | EPI_AFFINE, wide, FF, L.ff2_hi, L.ff2_lo, dst, D, M, D, FF, L.ff2_b, other, D, L.bn2_scale, L.bn2_shift, sm_count, st))) return rc;
+    } else {
+      if ((rc = launch_sgemm<0>(cur, D, L.Wqkv, 384, wide, 384, M, 384, D, nullptr, nullptr, 0, nullptr, nullptr, st))) return rc;
+      self_attention_kernel<<<B, 256, attn_smem, st>>>(wide, S, heads);
+      EVRP_LAUNCH_OK();
+      if ((rc = launch_sgemm<EPI_RESID | EPI_AFFINE>(heads, D, L.Wo, D, other, D, M, D, D, nullptr, cur, D, L.bn1_scale, L.bn1_shift, st))) return rc;
+      if ((rc = launch_sgemm<EPI_BIAS | EPI_RELU>(other, D, L.ff1_w, FF, wide, FF, M, FF, D, L.ff1_b, nullptr, 0, nullptr, nullptr, st))) return rc;
+      if ((rc = launch_sgemm<EPI_BIAS | EPI_RESID | EPI_AFFINE>(wide, FF, L.ff2_w, D, dst, D, M, D, FF, L.ff2_b, other, D, L.bn2_scale, L.bn2_shift, st))) return rc;
+    }
     cur = dst;
   }
   if (w->n_layers == 0) EVRP_CUDA_OK(cudaMemcpyAsync(emb, ha, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, st));
-  int rc;
-  if ((rc = launch_sgemm<0>(emb, D, w->node_proj, 384, kvl, 384, M, 384, D, nullptr, nullptr, 0, nullptr, nullptr, st))) return rc;
+  if (tcm) {
+    if ((rc = tc_gemm(0, emb, D, w->node_proj_hi, w->node_proj_lo, kvl, 384, M, 384, D, nullptr, nullptr, 0, nullptr, nullptr, sm_count, st))) return rc;
+  } else {
+    if ((rc = launch_sgemm<0>(emb, D, w->node_proj, 384, kvl, 384, M, 384, D, nullptr, nullptr, 0, nullptr, nullptr, st))) return rc;
+  }
   fixed_context_kernel<<<B, 128, 0, st>>>(emb, S, w->fixed_ctx_w, fixed_ctx);
   EVRP_LAUNCH_OK();
   return 0;

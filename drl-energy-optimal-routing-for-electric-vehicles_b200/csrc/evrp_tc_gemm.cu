@@ -1,0 +1,345 @@
+// tcgen05 / TMEM / TMA GEMM for the encoder's dense contractions, fp32-faithful.
+//
+//   C[M,N] = epilogue( A[M,K] @ W[N,K]^T )      A: fp32 activations, row-major;  W: nn.Linear layout [out,in]
+//
+// Precision: greedy tours flip under TF32-level noise, so every operand is split into two
+// TF32 planes with round-to-nearest,  x = hi + lo  (|x - hi - lo| <= 2^-24 |x|), and the product is evaluated as
+//   A W^T ~= Ah Wh^T + Ah Wl^T + Al Wh^T            (3 x kind::tf32 MMAs, fp32 accumulation in TMEM)
+// The dropped Al Wl^T term is <= 2^-22 relative, i.e. fp32-rounding level.
+//
+// Kernel: persistent, one CTA per SM, warp-specialised (320 threads):
+//   warps 0-3  epilogue      tcgen05.ld TMEM -> registers -> bias / ReLU / residual / folded-BatchNorm -> global
+//   warps 4-7  A converters  global fp32 (coalesced float4) -> cvt.rna.tf32 hi/lo -> 128B-swizzled K-major smem
+//   warp  8    MMA issuer    one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M=128,N=128,K=8)
+//   warp  9    W producer    TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) of the pre-split weight planes
+// A CTA owns one 128-column chunk of N and strides over 128-row M tiles.  When K == 128 the whole weight chunk
+// (hi+lo, 128 KB) stays resident in shared memory for the CTA's life and only A streams (3-stage ring of 32-column
+// K blocks); for K == 512 (FF2) weights stream through the same ring.  Two 128-column TMEM accumulators let the
+// epilogue of tile i overlap the MMAs of tile i+1.
+#include <cuda.h>
+#include <math.h>
+#include "evrp_common.cuh"
+
+namespace evrp {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BKB = 32;          // tile; BKB fp32 = one 128-byte swizzle row
+constexpr int STAGES = 3;
+constexpr int PLANE = BM * BKB * 4;                  // 16 KB: one [128 x 32] fp32 plane
+constexpr int NTHREADS = 320;
+constexpr int EPI_BIAS = 1, EPI_RELU = 2, EPI_RESID = 4, EPI_AFFINE = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14),
+// LBO=1 [16,30), SBO = 1024 B >> 4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2,
+// A,B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+struct Epilogue {
+  const float* bias; const float* resid; int ldr; const float* scale; const float* shift;
+};
+
+struct __align__(8) Barriers {
+  uint64_t full[STAGES];      // stage filled (128 converter arrivals [+1 producer arrival carrying the TMA bytes])
+  uint64_t empty[STAGES];     // stage consumed (tcgen05.commit)
+  uint64_t w_ready;           // resident weights landed
+  uint64_t acc_full[2];       // accumulator ready for the epilogue (tcgen05.commit)
+  uint64_t acc_empty[2];      // accumulator drained (128 epilogue arrivals)
+  uint32_t tmem_base;
+};
+
+template <bool RESIDENT, int EPI>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
+                  const float* __restrict__ A, int lda, float* __restrict__ C, int ldc, int M, int K, int n_chunks,
+                  Epilogue ep) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // carve: [resident W: (K/32) x (hi,lo) planes] [ring: STAGES x (A hi, A lo [, W hi, W lo])] [barriers]
+  const int KB = K / BKB;
+  unsigned char* wres = smem;
+  unsigned char* ring = smem + (RESIDENT ? KB * 2 * PLANE : 0);
+  constexpr int STAGE_BYTES = RESIDENT ? 2 * PLANE : 4 * PLANE;
+  Barriers* bars = reinterpret_cast<Barriers*>(ring + STAGES * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x % n_chunks;
+  const int cta_in_chunk = blockIdx.x / n_chunks, ctas_per_chunk = gridDim.x / n_chunks;
+  const int n0 = chunk * BN;
+  const int m_tiles = (M + BM - 1) / BM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars->full[s], RESIDENT ? 128 : 129); mbar_init(&bars->empty[s], 1); }
+    mbar_init(&bars->w_ready, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars->acc_full[b], 1); mbar_init(&bars->acc_empty[b], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {   // TMEM: 2 accumulators x 128 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&bars->tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 9) {
+    // ================= weight producer (TMA) =================
+    if (lane == 0) {
+      if (RESIDENT) {
+        mbar_expect_tx(&bars->w_ready, (uint32_t)(KB * 2 * PLANE));
+        for (int kb = 0; kb < KB; ++kb) {
+          tma_load_2d(wres + (kb * 2 + 0) * PLANE, &mapWh, &bars->w_ready, kb * BKB, n0);
+          tma_load_2d(wres + (kb * 2 + 1) * PLANE, &mapWl, &bars->w_ready, kb * BKB, n0);
+        }
+      } else {
+        uint32_t it = 0;
+        for (int tile = cta_in_chunk; tile < m_tiles; tile += ctas_per_chunk) {
+          for (int kb = 0; kb < KB; ++kb, ++it) {
+            const int s = it % STAGES;
+            mbar_wait(&bars->empty[s], ((it / STAGES) & 1) ^ 1);
+            unsigned char* st = ring + s * STAGE_BYTES;
+            mbar_expect_tx(&bars->full[s], 2 * PLANE);
+            tma_load_2d(st + 2 * PLANE, &mapWh, &bars->full[s], kb * BKB, n0);
+            tma_load_2d(st + 3 * PLANE, &mapWl, &bars->full[s], kb * BKB, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      if (RESIDENT) mbar_wait(&bars->w_ready, 0);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = cta_in_chunk; tile < m_tiles; tile += ctas_per_chunk, ++tcount) {
+        const int buf = tcount & 1;
+        mbar_wait(&bars->acc_empty[buf], ((tcount >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&bars->full[s], (it / STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          unsigned char* st = ring + s * STAGE_BYTES;
+          const uint32_t a_hi = smem_u32(st), a_lo = smem_u32(st + PLANE);
+          const uint32_t w_hi = RESIDENT ? smem_u32(wres + (kb * 2) * PLANE) : smem_u32(st + 2 * PLANE);
+          const uint32_t w_lo = w_hi + PLANE;
+#pragma unroll
+          for (int k = 0; k < BKB / 8; ++k) {            // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row
+            const uint64_t dah = umma_desc(a_hi + k * 32), dal = umma_desc(a_lo + k * 32);
+            const uint64_t dwh = umma_desc(w_hi + k * 32), dwl = umma_desc(w_lo + k * 32);
+            umma_tf32(d_tmem, dah, dwh, (kb | k) ? 1u : 0u);
+            umma_tf32(d_tmem, dah, dwl, 1u);
+            umma_tf32(d_tmem, dal, dwh, 1u);
+          }
+          umma_commit(&bars->empty[s]);                  // frees the stage when these MMAs retire
+        }
+        umma_commit(&bars->acc_full[buf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= A converters: fp32 -> (hi, lo) TF32 planes, swizzled K-major =================
+    const int t = threadIdx.x - 128;                     // 0..127
+    const int c = t & 7, r0 = t >> 3;                    // 16-byte chunk within the 128-byte row, row within a 16-row slab
+    uint32_t it = 0;
+    for (int tile = cta_in_chunk; tile < m_tiles; tile += ctas_per_chunk) {
+      const int m0 = tile * BM;
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % STAGES;
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 16 + r0;
+          v[i] = (m0 + row < M) ? __ldg(reinterpret_cast<const float4*>(A + (size_t)(m0 + row) * lda + kb * BKB + c * 4))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        mbar_wait(&bars->empty[s], ((it / STAGES) & 1) ^ 1);
+        unsigned char* st = ring + s * STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 16 + r0;
+          const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
+          uint4 hi, lo;
+          hi.x = to_tf32(v[i].x); hi.y = to_tf32(v[i].y); hi.z = to_tf32(v[i].z); hi.w = to_tf32(v[i].w);
+          lo.x = to_tf32(v[i].x - __uint_as_float(hi.x)); lo.y = to_tf32(v[i].y - __uint_as_float(hi.y));
+          lo.z = to_tf32(v[i].z - __uint_as_float(hi.z)); lo.w = to_tf32(v[i].w - __uint_as_float(hi.w));
+          *reinterpret_cast<uint4*>(st + off) = hi;
+          *reinterpret_cast<uint4*>(st + PLANE + off) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05
+        mbar_arrive(&bars->full[s]);
+      }
+    }
+  } else {
+    // ================= epilogue: warp w reads TMEM lanes 32w..32w+31 (row = lane) =================
+    uint32_t tcount = 0;
+    for (int tile = cta_in_chunk; tile < m_tiles; tile += ctas_per_chunk, ++tcount) {
+      const int buf = tcount & 1;
+      const int m = tile * BM + warp * 32 + lane;
+      mbar_wait(&bars->acc_full[buf], (tcount >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int cb = 0; cb < BN; cb += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * BN + cb;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
+            "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (m < M) {
+          const int n = n0 + cb;
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) {
+            float v[4] = {__uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3])};
+            if (EPI & EPI_BIAS) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + n + q));
+              v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
+            }
+            if (EPI & EPI_RELU) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
+            if (EPI & EPI_RESID) {
+              const float4 rr = __ldg(reinterpret_cast<const float4*>(ep.resid + (size_t)m * ep.ldr + n + q));
+              v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
+            }
+            if (EPI & EPI_AFFINE) {
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(ep.scale + n + q));
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(ep.shift + n + q));
+              v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y); v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w);
+            }
+            *reinterpret_cast<float4*>(C + (size_t)m * ldc + n + q) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&bars->acc_empty[buf]);
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// W plane [N][K] fp32, K contiguous; box = 32 (K) x 128 (N), 128-byte swizzle
+static int make_weight_map(CUtensorMap* map, const float* W, int N, int K) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return -EVRP_E_BADARG;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+  cuuint32_t box[2] = {BKB, BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)W, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)(2000 + r);
+}
+
+template <bool RESIDENT, int EPI>
+static int launch(const CUtensorMap& mh, const CUtensorMap& ml, const float* A, int lda, float* C, int ldc, int M, int N,
+                  int K, const Epilogue& ep, int sm_count, cudaStream_t st) {
+  const int n_chunks = N / BN;
+  const int per_chunk = sm_count / n_chunks > 0 ? sm_count / n_chunks : 1;
+  const int m_tiles = (M + BM - 1) / BM;
+  const int ctas_per_chunk = per_chunk < m_tiles ? per_chunk : m_tiles;
+  const size_t smem = (RESIDENT ? (size_t)(K / BKB) * 2 * PLANE + STAGES * 2 * PLANE : (size_t)STAGES * 4 * PLANE) + sizeof(Barriers) + 1024;
+  auto kern = gemm3xtf32_kernel<RESIDENT, EPI>;
+  EVRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<n_chunks * ctas_per_chunk, NTHREADS, smem, st>>>(mh, ml, A, lda, C, ldc, M, K, n_chunks, ep);
+  EVRP_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace tc
+
+// C = epi(A @ W^T) with W given as pre-split TF32 planes Wh, Wl ([N][K]).  K in {128, 512}, N % 128 == 0.
+int tc_gemm(int epi, const float* A, int lda, const float* Wh, const float* Wl, float* C, int ldc, int M, int N, int K,
+            const float* bias, const float* resid, int ldr, const float* scale, const float* shift, int sm_count,
+            cudaStream_t st) {
+  using namespace tc;
+  if (N % BN || (K != 128 && K != 512)) return -EVRP_E_BADARG;
+  CUtensorMap mh, ml;
+  int rc;
+  if ((rc = make_weight_map(&mh, Wh, N, K))) return rc;
+  if ((rc = make_weight_map(&ml, Wl, N, K))) return rc;
+  Epilogue ep{bias, resid, ldr, scale, shift};
+  if (K == 128) {
+    switch (epi) {
+      case 0: return launch<true, 0>(mh, ml, A, lda, C, ldc, M, N, K, ep, sm_count, st);
+      case EPI_BIAS | EPI_RELU: return launch<true, EPI_BIAS | EPI_RELU>(mh, ml, A, lda, C, ldc, M, N, K, ep, sm_count, st);
+      case EPI_RESID | EPI_AFFINE: return launch<true, EPI_RESID | EPI_AFFINE>(mh, ml, A, lda, C, ldc, M, N, K, ep, sm_count, st);
+    }
+  } else if (epi == (EPI_BIAS | EPI_RESID | EPI_AFFINE)) {
+    return launch<false, EPI_BIAS | EPI_RESID | EPI_AFFINE>(mh, ml, A, lda, C, ldc, M, N, K, ep, sm_count, st);
+  }
+  return -EVRP_E_BADARG;
+}
+
+}  // namespace evrp

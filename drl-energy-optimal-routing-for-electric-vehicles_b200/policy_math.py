@@ -40,6 +40,18 @@ def folded_tour_weight(model):
     return (W1[:, :128].double() @ model.tour.weight.double()).to(W1.dtype)
 
 
+def split_tf32(w):
+    """w (fp32) -> (hi, lo) TF32 planes with round-to-nearest (ties away, = PTX cvt.rna.tf32.f32): w = hi + lo up to
+    2^-24 |w|.  Both planes have their 13 low mantissa bits cleared, so the tensor core reads them exactly."""
+    def rna(x):
+        bits = x.contiguous().view(torch.int32)
+        return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+    w = w.detach().float().contiguous()
+    hi = rna(w)
+    lo = rna(w - hi)
+    return hi.contiguous(), lo.contiguous()
+
+
 def pack_weights(model):
     keep = {}
     ew = _lib.EncoderWeights()
@@ -70,6 +82,15 @@ def pack_weights(model):
         lw.ff2_w, lw.ff2_b = dev(f"l{l}.ff2w", ff[2].weight.t()), dev(f"l{l}.ff2b", ff[2].bias)
         s, sh = _bn_fold(bn2)
         lw.bn2_scale, lw.bn2_shift = dev(f"l{l}.bn2s", s), dev(f"l{l}.bn2b", sh)
+        # tcgen05 path: [out][in] planes
+        for name, mat in (("Wqkv", torch.cat(cols, 1).t()), ("Wo", att.W_out.reshape(Hh * dk, d).t()),
+                          ("ff1", ff[0].weight), ("ff2", ff[2].weight)):
+            hi, lo = split_tf32(mat)
+            setattr(lw, name + "_hi", dev(f"l{l}.{name}_hi", hi))
+            setattr(lw, name + "_lo", dev(f"l{l}.{name}_lo", lo))
+    hi, lo = split_tf32(folded_node_projection(model))
+    ew.node_proj_hi, ew.node_proj_lo = dev("node_proj_hi", hi), dev("node_proj_lo", lo)
+    ew.gemm_mode = int(getattr(model, "gemm_mode", 0))
     ew.node_proj = dev("node_proj", folded_node_projection(model).t())
     ew.fixed_ctx_w = dev("fixed_ctx_w", model.project_fixed_context.weight.t())
     dw = _lib.DecoderWeights()

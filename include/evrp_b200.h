@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 3
+#define EVRP_ABI_VERSION 4
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -100,6 +100,12 @@ typedef struct {
   const float *ff1_w, *ff1_b;    /* [128,512],[512]  layers.l.2.module.0.weight^T / bias                    */
   const float *ff2_w, *ff2_b;    /* [512,128],[128]  layers.l.2.module.2.weight^T / bias                    */
   const float *bn2_scale, *bn2_shift;   /* layers.l.3.normalizer                                            */
+  /* tcgen05 path (gemm_mode 0): the same four weight matrices in nn.Linear layout [out][in] (in contiguous), each
+     split into two TF32 planes with round-to-nearest, w = hi + lo (evrp_b200/policy_math.py::split_tf32)     */
+  const float *Wqkv_hi, *Wqkv_lo;       /* [384,128] */
+  const float *Wo_hi, *Wo_lo;           /* [128,128] */
+  const float *ff1_hi, *ff1_lo;         /* [512,128] */
+  const float *ff2_hi, *ff2_lo;         /* [128,512] */
 } evrp_layer_weights;
 
 typedef struct {
@@ -113,6 +119,8 @@ typedef struct {
                                           lK_fold = project_out.weight^T @ W_logitK, so that
                                           logits[j] = heads . lK[j]           (nets/DRLModel.py:436-444)     */
   const float *fixed_ctx_w;            /* [128,128]  project_fixed_context.weight^T                         */
+  const float *node_proj_hi, *node_proj_lo;   /* [384,128] TF32 planes of node_proj^T (tcgen05 path)         */
+  int32_t gemm_mode;                   /* 0: tcgen05 3xTF32 (fp32-faithful, tensor cores); 1: fp32 FFMA GEMM   */
 } evrp_encoder_weights;
 
 size_t evrp_encoder_workspace_bytes(int B, int S);
