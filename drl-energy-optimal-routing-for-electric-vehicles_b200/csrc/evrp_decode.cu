@@ -7,42 +7,60 @@
 //   _calc_log_likelihood             nets/DRLModel.py:182-190
 //   update_dynamic / update_mask     problems/EVRP.py:105-280   (fused, bit-exact recipe of evrp_common.cuh)
 //
-// Layout: a CTA owns G=8 rollout rows (one warp each) for their whole life.  Per step
-//   1. CTA-wide batched FF_tour GEMMs over the 8 rows (weights streamed once per CTA-step from L2, coalesced,
-//      shared by the 8 rows),
-//   2. per-warp glimpse attention / logits over the FEASIBLE nodes only (compact index list from the 128-bit
-//      mask; K|V|logitK rows are 512-B coalesced float4 loads, issued in batches of 4 for memory-level
-//      parallelism; next step's K rows are L2-prefetched as soon as the new mask is known),
-//   3. warp-level masked log-softmax, argmax / inverse-CDF sample,
-//   4. state transition + look-ahead feasibility mask with the dynamic state in registers/shared memory.
-// Rows retire individually; only t_max and the status word are read back by the host.
+// Layout: a CTA (256 threads, 2 CTAs per SM) owns RPC=32 rollout rows for their whole life; each warp owns 4 rows.
+// Per step
+//   1. FF_tour as two CTA-wide register-tiled fp32 GEMMs over the 32 rows ([32x128]x[128x512], [32x512]x[512x128],
+//      8x8 / 8x4 register tiles; weights stream coalesced from L2 once per CTA-step and are shared by 32 rows; the
+//      running max, the hidden layer and the context stay in shared memory),
+//   2. per row (warp): glimpse attention / logits over the FEASIBLE nodes only (compact index list from the 128-bit
+//      mask; K|V|logitK rows are 512-B coalesced float4 loads issued 4 at a time; the rows are L2-prefetched as soon
+//      as the mask is known),
+//   3. warp-level masked log-softmax, first-index argmax / inverse-CDF sample,
+//   4. state transition + look-ahead feasibility mask (bit-exact fp32 recipe), state in shared memory.
+// Rows retire individually; the host reads back only t_max and the status word.
 #include <math.h>
 #include "evrp_common.cuh"
 
 namespace evrp {
 
-constexpr int G = 8;             // rollout rows per CTA (one warp each)
-constexpr int NT = G * 32;       // 256 threads
+constexpr int RPC = 32;          // rollout rows per CTA
+constexpr int RPW = 4;           // rows per warp
+constexpr int NT = 256;          // 8 warps
 constexpr int SP = EVRP_MAX_S;   // padded node count (128)
 constexpr int PSTR = SP + 4;     // head stride of the compat buffer (bank-conflict-free for the 4-lane groups)
 
-struct __align__(16) DecodeSmem {
-  float m[G][D];            // running max of visited embeddings          (route_feature :214)
-  float veh[G][4];          // load, soc/Start_SOC, time/t_limit          (:215-222)
-  float h1[G][FF];          // FF_tour hidden
-  float ctxp[2][G][D];      // FF_tour output, two K-halves
-  float pc[G][H][PSTR];     // compat -> attention probabilities, by list position
-  float logit[G][SP];       // clipped logits -> log_p, by list position
-  float dem[G][SP];         // demand row
-  float D0[G][SP], G0[G][SP], d3[G][SP], s3[G][SP];   // depot row + rule-7 constants
-  float dcur[G][SP], gcur[G][SP];                     // D[now,:], G[now,:]
-  unsigned char list[G][SP];                          // feasible node indices, ascending
+struct RowState {
+  float load, soc, tim, d4;
+  int now, done, inst, valid;
+  uint32_t mk[4];
 };
 
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
+struct WarpScratch {
+  float pc[H][PSTR];             // compat -> attention probabilities, by list position
+  float logit[SP];               // clipped logits / temp, by list position
+  float heads[D];                // glimpse heads (concat)
+  unsigned char list[SP];        // feasible node indices, ascending
+};
 
+struct AttScratch {
+  float ctx[RPC][D];             // FF_tour output (written after the second GEMM has consumed h1)
+  WarpScratch ws[NT / 32];
+};
+
+union FFUnion {
+  float h1[RPC][FF];             // FF_tour hidden (FF phase)
+  AttScratch att;                // per-row phase
+};
+
+struct __align__(16) DecodeSmem {
+  float m[RPC][D];               // running max of visited embeddings          (route_feature :214)
+  float dem[RPC][SP];            // demand rows
+  float veh[RPC][4];             // load, soc/Start_SOC, time/t_limit          (:215-222)
+  RowState rs[RPC];
+  FFUnion u;
+};
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 // register-array select without dynamic indexing (keeps the arrays out of local memory)
@@ -53,7 +71,7 @@ __global__ void __launch_bounds__(NT, 2)
 rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
                const float* __restrict__ emb, const float* __restrict__ kvl, const float* __restrict__ fixed_ctx,
                const float* __restrict__ dynamic0, const float* __restrict__ Dm, const float* __restrict__ Gm,
-               int B, int S, int F, int rows_total,
+               float* station_ws, int B, int S, int F, int rows_total,
                const int64_t* __restrict__ forced, const float* __restrict__ uniforms,
                int64_t* __restrict__ pi, float* __restrict__ ll, float* __restrict__ reward,
                float* __restrict__ energy, uint32_t* __restrict__ saved_mask, float* __restrict__ saved_veh,
@@ -61,220 +79,277 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DecodeSmem& sm = *reinterpret_cast<DecodeSmem*>(smem_raw);
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-  const int row = blockIdx.x * G + wid;
-  const bool valid = row < rows_total;
-  const int inst = valid ? row % B : 0;
   const int Tcap = cfg.max_steps;
-  const float* Db = Dm + (size_t)inst * S * S;
-  const float* Gb = Gm + (size_t)inst * S * S;
-  const float* embb = emb + (size_t)inst * S * D;
-  const float* kvlb = kvl + (size_t)inst * S * 384;
   const int nblk = (S + 31) >> 5;
+  const float sqrt_d = sqrtf((float)D);
 
   // ---------------- prologue: per-row state ----------------
-  float load = 1.f, soc = 0.f, tim = 0.f;
-  uint32_t mk[4] = {0u, 0u, 0u, 0u};
-  int now = 0;
-  bool done = !valid;
-  float d4 = 0.f;
-  {
+  for (int r = 0; r < RPW; ++r) {
+    const int lr = wid * RPW + r;
+    const int row = blockIdx.x * RPC + lr;
+    const bool valid = row < rows_total;
+    const int inst = valid ? row % B : 0;
+    const float* Db = Dm + (size_t)inst * S * S;
+    const float* Gb = Gm + (size_t)inst * S * S;
     const float* dy = dynamic0 + (size_t)inst * 4 * S;
-    load = dy[0]; soc = dy[2 * S]; tim = dy[3 * S];
+    const float load = dy[0], soc = dy[2 * S], tim = dy[3 * S];
     bool nonuni = false;
+    float d4 = 0.f;
+    uint32_t mk[4];
 #pragma unroll
     for (int jb = 0; jb < 4; ++jb) {
       const int j = jb * 32 + lane;
-      float dmv = 0.f, D0v = 0.f, G0v = 0.f, d3v = 0.f, s3v = 0.f;
+      float dmv = 0.f;
       if (j < S) {
         dmv = dy[S + j];
         nonuni |= (dy[j] != load) || (dy[2 * S + j] != soc) || (dy[3 * S + j] != tim);
-        D0v = Db[j]; G0v = Gb[j];
-        int k = 0; float best = Db[(size_t)1 * S + j];
+        int k = 0; float best = Db[(size_t)1 * S + j];       // rule-7 constants (problems/EVRP.py:196-202)
         for (int i = 1; i < F; ++i) { const float v = Db[(size_t)(1 + i) * S + j]; if (v < best) { best = v; k = i; } }
-        d3v = (j == 0) ? 0.f : best;
-        s3v = Gb[(size_t)(1 + k) * S + j];
+        if (valid) {
+          station_ws[((size_t)inst * 2 + 0) * SP + j] = (j == 0) ? 0.f : best;
+          station_ws[((size_t)inst * 2 + 1) * SP + j] = Gb[(size_t)(1 + k) * S + j];
+        }
         if (j == 0) d4 = Db[(size_t)(1 + k) * S + 0];
       }
-      sm.dem[wid][j] = dmv; sm.D0[wid][j] = D0v; sm.G0[wid][j] = G0v; sm.d3[wid][j] = d3v; sm.s3[wid][j] = s3v;
-      sm.dcur[wid][j] = D0v; sm.gcur[wid][j] = G0v;           // now = 0 at t = 0 (:257)
+      sm.dem[lr][j] = dmv;
       mk[jb] = __ballot_sync(FULL, j < S);                     // mask = ones (:256)
     }
     d4 = __shfl_sync(FULL, d4, 0);
     if (valid && __any_sync(FULL, nonuni) && lane == 0) atomicOr(status, EVRP_ST_NONUNIFORM_DYNAMIC);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) sm.m[wid][lane * 4 + i] = 0.f;   // zeros before the first pick (:224)
+    for (int i = 0; i < 4; ++i) sm.m[lr][lane * 4 + i] = 0.f;  // zeros before the first pick (:224)
+    if (lane == 0) {
+      RowState& rs = sm.rs[lr];
+      rs.load = load; rs.soc = soc; rs.tim = tim; rs.d4 = d4;
+      rs.now = 0; rs.done = valid ? 0 : 1; rs.inst = inst; rs.valid = valid ? 1 : 0;
+      rs.mk[0] = mk[0]; rs.mk[1] = mk[1]; rs.mk[2] = mk[2]; rs.mk[3] = mk[3];
+      sm.veh[lr][0] = 0.f; sm.veh[lr][1] = 0.f; sm.veh[lr][2] = 0.f; sm.veh[lr][3] = 0.f;
+    }
   }
-  const float sqrt_d = sqrtf((float)D);
+  __syncthreads();
   int t = 0;
-  bool first = true;
 
   // ---------------- step loop ----------------
   while (true) {
-    if (__syncthreads_and(done ? 1 : 0)) break;
-    if (!done && lane == 0) {
-      sm.veh[wid][0] = load;
-      sm.veh[wid][1] = __fdiv_rn(soc, phys.start_soc);
-      sm.veh[wid][2] = __fdiv_rn(tim, phys.t_limit);
-      if (saved_veh) {
-        float* sv = saved_veh + ((size_t)row * Tcap + t) * 3;
-        sv[0] = load; sv[1] = sm.veh[wid][1]; sv[2] = sm.veh[wid][2];
+    int my_done = 1;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) my_done &= sm.rs[wid * RPW + r].done;
+    if (__syncthreads_and(my_done)) break;
+    // vehicle scalars + trace
+    if (lane < RPW) {
+      const int lr = wid * RPW + lane;
+      const RowState& rs = sm.rs[lr];
+      if (!rs.done) {
+        const float v1 = __fdiv_rn(rs.soc, phys.start_soc), v2 = __fdiv_rn(rs.tim, phys.t_limit);
+        sm.veh[lr][0] = rs.load; sm.veh[lr][1] = v1; sm.veh[lr][2] = v2;
+        const size_t row = (size_t)blockIdx.x * RPC + lr;
+        if (saved_veh) { float* sv = saved_veh + (row * Tcap + t) * 3; sv[0] = rs.load; sv[1] = v1; sv[2] = v2; }
+        if (saved_mask) {
+          uint32_t* smk = saved_mask + (row * Tcap + t) * 4;
+          smk[0] = rs.mk[0]; smk[1] = rs.mk[1]; smk[2] = rs.mk[2]; smk[3] = rs.mk[3];
+        }
       }
     }
-    if (!done && saved_mask && lane < 4) saved_mask[((size_t)row * Tcap + t) * 4 + lane] = sel4(mk, lane);
     __syncthreads();
 
-    // ---- FF_tour layer 1: h1[g][n] = relu(b1 + W1veh^T veh_g + W1max^T m_g), n = tid, tid+256 ----
+    // ---- FF_tour layer 1: h1[r][n] = relu(b1[n] + W1veh^T veh_r + W1max^T m_r); 8 rows x 8 cols per thread ----
     {
-      float acc0[G], acc1[G];
-      const float ba = __ldg(w.b1 + tid), bb = __ldg(w.b1 + 256 + tid);
-      const float va0 = __ldg(w.w1_veh + tid), va1 = __ldg(w.w1_veh + FF + tid), va2 = __ldg(w.w1_veh + 2 * FF + tid);
-      const float vb0 = __ldg(w.w1_veh + 256 + tid), vb1 = __ldg(w.w1_veh + FF + 256 + tid), vb2 = __ldg(w.w1_veh + 2 * FF + 256 + tid);
+      const int cg = tid & 63, rg = tid >> 6;
+      const int c0 = cg * 8, r0 = rg * 8;
+      float acc[8][8];
+      {
+        float bb[8], v0[8], v1[8], v2[8];
+        *reinterpret_cast<float4*>(&bb[0]) = ldg4(w.b1 + c0); *reinterpret_cast<float4*>(&bb[4]) = ldg4(w.b1 + c0 + 4);
+        *reinterpret_cast<float4*>(&v0[0]) = ldg4(w.w1_veh + c0); *reinterpret_cast<float4*>(&v0[4]) = ldg4(w.w1_veh + c0 + 4);
+        *reinterpret_cast<float4*>(&v1[0]) = ldg4(w.w1_veh + FF + c0); *reinterpret_cast<float4*>(&v1[4]) = ldg4(w.w1_veh + FF + c0 + 4);
+        *reinterpret_cast<float4*>(&v2[0]) = ldg4(w.w1_veh + 2 * FF + c0); *reinterpret_cast<float4*>(&v2[4]) = ldg4(w.w1_veh + 2 * FF + c0 + 4);
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const float x0 = sm.veh[g][0], x1 = sm.veh[g][1], x2 = sm.veh[g][2];
-        acc0[g] = fmaf(va2, x2, fmaf(va1, x1, fmaf(va0, x0, ba)));
-        acc1[g] = fmaf(vb2, x2, fmaf(vb1, x1, fmaf(vb0, x0, bb)));
+        for (int r = 0; r < 8; ++r) {
+          const float4 vh = *reinterpret_cast<const float4*>(&sm.veh[r0 + r][0]);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(v2[c], vh.z, fmaf(v1[c], vh.y, fmaf(v0[c], vh.x, bb[c])));
+        }
       }
-      const float* wp = w.w1_max + tid;
+      const float* wp = w.w1_max + c0;
 #pragma unroll 2
-      for (int k = 0; k < D; k += 4) {
-        float wa[4], wb[4];
+      for (int k = 0; k < D; k += 2) {
+        float wa[8], wb[8];
+        *reinterpret_cast<float4*>(&wa[0]) = ldg4(wp + (size_t)k * FF); *reinterpret_cast<float4*>(&wa[4]) = ldg4(wp + (size_t)k * FF + 4);
+        *reinterpret_cast<float4*>(&wb[0]) = ldg4(wp + (size_t)(k + 1) * FF); *reinterpret_cast<float4*>(&wb[4]) = ldg4(wp + (size_t)(k + 1) * FF + 4);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { wa[i] = __ldg(wp + (size_t)(k + i) * FF); wb[i] = __ldg(wp + (size_t)(k + i) * FF + 256); }
+        for (int r = 0; r < 8; ++r) {
+          const float2 a = *reinterpret_cast<const float2*>(&sm.m[r0 + r][k]);
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const float4 mm = *reinterpret_cast<const float4*>(&sm.m[g][k]);
-          acc0[g] = fmaf(wa[0], mm.x, acc0[g]); acc1[g] = fmaf(wb[0], mm.x, acc1[g]);
-          acc0[g] = fmaf(wa[1], mm.y, acc0[g]); acc1[g] = fmaf(wb[1], mm.y, acc1[g]);
-          acc0[g] = fmaf(wa[2], mm.z, acc0[g]); acc1[g] = fmaf(wb[2], mm.z, acc1[g]);
-          acc0[g] = fmaf(wa[3], mm.w, acc0[g]); acc1[g] = fmaf(wb[3], mm.w, acc1[g]);
+          for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(wa[c], a.x, acc[r][c]);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(wb[c], a.y, acc[r][c]);
         }
       }
 #pragma unroll
-      for (int g = 0; g < G; ++g) { sm.h1[g][tid] = fmaxf(acc0[g], 0.f); sm.h1[g][256 + tid] = fmaxf(acc1[g], 0.f); }
+      for (int r = 0; r < 8; ++r) {
+        *reinterpret_cast<float4*>(&sm.u.h1[r0 + r][c0]) =
+            make_float4(fmaxf(acc[r][0], 0.f), fmaxf(acc[r][1], 0.f), fmaxf(acc[r][2], 0.f), fmaxf(acc[r][3], 0.f));
+        *reinterpret_cast<float4*>(&sm.u.h1[r0 + r][c0 + 4]) =
+            make_float4(fmaxf(acc[r][4], 0.f), fmaxf(acc[r][5], 0.f), fmaxf(acc[r][6], 0.f), fmaxf(acc[r][7], 0.f));
+      }
     }
     __syncthreads();
-    // ---- FF_tour layer 2: ctx[g][d] = b2 + W2^T h1_g ; thread = (d, K-half) ----
+    // ---- FF_tour layer 2: ctx[r][d] = W2^T h1_r (b2 added in the query); 8 rows x 4 cols x K-half per thread ----
     {
-      const int d = tid & 127, half = tid >> 7;
-      float acc[G];
+      const int kh = tid & 1, cg = (tid >> 1) & 31, rg = tid >> 6;
+      const int c0 = cg * 4, r0 = rg * 8;
+      float acc[8][4];
 #pragma unroll
-      for (int g = 0; g < G; ++g) acc[g] = 0.f;
-      const float* wp = w.w2 + (size_t)half * 256 * D + d;
-#pragma unroll 2
+      for (int r = 0; r < 8; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+      const float* wp = w.w2 + (size_t)kh * 256 * D + c0;
+      const int kbase = kh * 256;
+#pragma unroll 1
       for (int k = 0; k < 256; k += 4) {
-        float ww[4];
+        float4 ww[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ww[i] = __ldg(wp + (size_t)(k + i) * D);
+        for (int i = 0; i < 4; ++i) ww[i] = ldg4(wp + (size_t)(k + i) * D);
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const float4 hh = *reinterpret_cast<const float4*>(&sm.h1[g][half * 256 + k]);
-          acc[g] = fmaf(ww[0], hh.x, acc[g]); acc[g] = fmaf(ww[1], hh.y, acc[g]);
-          acc[g] = fmaf(ww[2], hh.z, acc[g]); acc[g] = fmaf(ww[3], hh.w, acc[g]);
+        for (int r = 0; r < 8; ++r) {
+          const float4 hh = *reinterpret_cast<const float4*>(&sm.u.h1[r0 + r][kbase + k]);
+          acc[r][0] = fmaf(ww[0].x, hh.x, acc[r][0]); acc[r][1] = fmaf(ww[0].y, hh.x, acc[r][1]);
+          acc[r][2] = fmaf(ww[0].z, hh.x, acc[r][2]); acc[r][3] = fmaf(ww[0].w, hh.x, acc[r][3]);
+          acc[r][0] = fmaf(ww[1].x, hh.y, acc[r][0]); acc[r][1] = fmaf(ww[1].y, hh.y, acc[r][1]);
+          acc[r][2] = fmaf(ww[1].z, hh.y, acc[r][2]); acc[r][3] = fmaf(ww[1].w, hh.y, acc[r][3]);
+          acc[r][0] = fmaf(ww[2].x, hh.z, acc[r][0]); acc[r][1] = fmaf(ww[2].y, hh.z, acc[r][1]);
+          acc[r][2] = fmaf(ww[2].z, hh.z, acc[r][2]); acc[r][3] = fmaf(ww[2].w, hh.z, acc[r][3]);
+          acc[r][0] = fmaf(ww[3].x, hh.w, acc[r][0]); acc[r][1] = fmaf(ww[3].y, hh.w, acc[r][1]);
+          acc[r][2] = fmaf(ww[3].z, hh.w, acc[r][2]); acc[r][3] = fmaf(ww[3].w, hh.w, acc[r][3]);
         }
       }
 #pragma unroll
-      for (int g = 0; g < G; ++g) sm.ctxp[half][g][d] = acc[g];
+      for (int r = 0; r < 8; ++r) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] += __shfl_xor_sync(FULL, acc[r][c], 1);   // the two K halves sit in lane pairs
+      }
+      __syncthreads();                                   // every read of h1 is done: its storage becomes ctx + scratch
+      if (kh == 0) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          *reinterpret_cast<float4*>(&sm.u.att.ctx[r0 + r][c0]) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      }
     }
     __syncthreads();
 
-    if (!done) {
+    // ---- per-row phase: each warp walks its rows ----
+    WarpScratch& ws = sm.u.att.ws[wid];
+    const int hd = lane >> 2, sub = lane & 3;
+#pragma unroll 1
+    for (int r = 0; r < RPW; ++r) {
+      const int lr = wid * RPW + r;
+      RowState& rs = sm.rs[lr];
+      if (rs.done) continue;                             // warp-uniform
+      const int row = blockIdx.x * RPC + lr;
+      const int inst = rs.inst;
+      const int now = rs.now;
+      const float* Db = Dm + (size_t)inst * S * S;
+      const float* Gb = Gm + (size_t)inst * S * S;
+      const float* embb = emb + (size_t)inst * S * D;
+      const float* kvlb = kvl + (size_t)inst * S * 384;
+      uint32_t mk[4] = {rs.mk[0], rs.mk[1], rs.mk[2], rs.mk[3]};
       // ---- feasible list (ascending node index) ----
       int nf = 0;
 #pragma unroll
       for (int jb = 0; jb < 4; ++jb) {
         const uint32_t bits = mk[jb];
-        if ((bits >> lane) & 1u) sm.list[wid][nf + __popc(bits & ((1u << lane) - 1u))] = (unsigned char)(jb * 32 + lane);
+        if ((bits >> lane) & 1u) ws.list[nf + __popc(bits & ((1u << lane) - 1u))] = (unsigned char)(jb * 32 + lane);
         nf += __popc(bits);
       }
       __syncwarp();
       // V and logit-K rows of this step: warm L2 while the compat pass runs
       for (int i = lane; i < nf; i += 32) {
-        const float* r = kvlb + (size_t)sm.list[wid][i] * 384 + 128;
+        const float* p = kvlb + (size_t)ws.list[i] * 384 + 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) prefetch_l2(r + c * 32);
+        for (int c = 0; c < 8; ++c) prefetch_l2(p + c * 32);
       }
       // ---- query (:394): (fixed_ctx + ctx) + emb[now] ; lane holds 4 channels of head lane/4 ----
       float q[4];
       {
         const float4 fc = ldg4(fixed_ctx + (size_t)inst * D + lane * 4);
         const float4 en = ldg4(embb + (size_t)now * D + lane * 4);
-        const float4 c0 = *reinterpret_cast<const float4*>(&sm.ctxp[0][wid][lane * 4]);
-        const float4 c1 = *reinterpret_cast<const float4*>(&sm.ctxp[1][wid][lane * 4]);
+        const float4 cx = *reinterpret_cast<const float4*>(&sm.u.att.ctx[lr][lane * 4]);
         const float4 b2 = ldg4(w.b2 + lane * 4);
-        q[0] = (fc.x + ((c0.x + c1.x) + b2.x)) + en.x;
-        q[1] = (fc.y + ((c0.y + c1.y) + b2.y)) + en.y;
-        q[2] = (fc.z + ((c0.z + c1.z) + b2.z)) + en.z;
-        q[3] = (fc.w + ((c0.w + c1.w) + b2.w)) + en.w;
+        q[0] = (fc.x + (cx.x + b2.x)) + en.x;
+        q[1] = (fc.y + (cx.y + b2.y)) + en.y;
+        q[2] = (fc.z + (cx.z + b2.z)) + en.z;
+        q[3] = (fc.w + (cx.w + b2.w)) + en.w;
       }
-      const int hd = lane >> 2, sub = lane & 3;
       // ---- compat[h][i] = q_h . K[j_i, h] / 4 ----
       for (int i0 = 0; i0 < nf; i0 += 4) {
         float4 kv[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int j = sm.list[wid][min(i0 + a, nf - 1)];
-          kv[a] = ldg4(kvlb + (size_t)j * 384 + lane * 4);
-        }
+        for (int a = 0; a < 4; ++a) kv[a] = ldg4(kvlb + (size_t)ws.list[min(i0 + a, nf - 1)] * 384 + lane * 4);
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
           float p = fmaf(q[3], kv[a].w, fmaf(q[2], kv[a].z, fmaf(q[1], kv[a].y, q[0] * kv[a].x)));
           p += __shfl_xor_sync(FULL, p, 1);
           p += __shfl_xor_sync(FULL, p, 2);
-          if (sub == 0 && i0 + a < nf) sm.pc[wid][hd][i0 + a] = p * 0.25f;
+          if (sub == 0 && i0 + a < nf) ws.pc[hd][i0 + a] = p * 0.25f;
         }
       }
       __syncwarp();
       // ---- per-head softmax over the list; lane (hd, sub) strides i = sub, sub+4, ... ----
       {
         float mx = -INFINITY;
-        for (int i = sub; i < nf; i += 4) mx = fmaxf(mx, sm.pc[wid][hd][i]);
+        for (int i = sub; i < nf; i += 4) mx = fmaxf(mx, ws.pc[hd][i]);
         mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 1));
         mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 2));
         float sum = 0.f;
-        for (int i = sub; i < nf; i += 4) { const float e = expf(sm.pc[wid][hd][i] - mx); sm.pc[wid][hd][i] = e; sum += e; }
+        for (int i = sub; i < nf; i += 4) { const float e = expf(ws.pc[hd][i] - mx); ws.pc[hd][i] = e; sum += e; }
         sum += __shfl_xor_sync(FULL, sum, 1);
         sum += __shfl_xor_sync(FULL, sum, 2);
-        for (int i = sub; i < nf; i += 4) sm.pc[wid][hd][i] = __fdiv_rn(sm.pc[wid][hd][i], sum);
+        for (int i = sub; i < nf; i += 4) ws.pc[hd][i] = __fdiv_rn(ws.pc[hd][i], sum);
       }
       __syncwarp();
-      // ---- heads = attn @ V ; lane keeps its 4 channels ----
-      float hv[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int i0 = 0; i0 < nf; i0 += 4) {
-        float4 vv[4]; float pr[4];
+      // ---- heads = attn @ V ; lane owns 4 channels ----
+      {
+        float hv[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i0 = 0; i0 < nf; i0 += 4) {
+          float4 vv[4]; float pr[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int ii = min(i0 + a, nf - 1);
-          const int j = sm.list[wid][ii];
-          vv[a] = ldg4(kvlb + (size_t)j * 384 + 128 + lane * 4);
-          pr[a] = (i0 + a < nf) ? sm.pc[wid][hd][ii] : 0.f;
-        }
+          for (int a = 0; a < 4; ++a) {
+            const int ii = min(i0 + a, nf - 1);
+            vv[a] = ldg4(kvlb + (size_t)ws.list[ii] * 384 + 128 + lane * 4);
+            pr[a] = (i0 + a < nf) ? ws.pc[hd][ii] : 0.f;
+          }
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          hv[0] = fmaf(pr[a], vv[a].x, hv[0]); hv[1] = fmaf(pr[a], vv[a].y, hv[1]);
-          hv[2] = fmaf(pr[a], vv[a].z, hv[2]); hv[3] = fmaf(pr[a], vv[a].w, hv[3]);
+          for (int a = 0; a < 4; ++a) {
+            hv[0] = fmaf(pr[a], vv[a].x, hv[0]); hv[1] = fmaf(pr[a], vv[a].y, hv[1]);
+            hv[2] = fmaf(pr[a], vv[a].z, hv[2]); hv[3] = fmaf(pr[a], vv[a].w, hv[3]);
+          }
         }
+        *reinterpret_cast<float4*>(&ws.heads[lane * 4]) = make_float4(hv[0], hv[1], hv[2], hv[3]);
       }
-      // ---- logits[i] = heads . lK[j_i] / sqrt(128) -> tanh clip -> / temp   (project_out folded into lK) ----
-      for (int i0 = 0; i0 < nf; i0 += 4) {
-        float4 lv[4];
+      __syncwarp();
+      // ---- logits[i] = heads . lK[j_i] / sqrt(128) -> tanh clip -> / temp  (project_out folded into lK).
+      //      8 lanes per node: lane (grp, s8) covers channels 4*s8 + 32*c, c = 0..3; 4 nodes per pass ----
+      {
+        const int grp = lane >> 3, s8 = lane & 7;
+        float4 hq[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int j = sm.list[wid][min(i0 + a, nf - 1)];
-          lv[a] = ldg4(kvlb + (size_t)j * 384 + 256 + lane * 4);
-        }
-        float p[4];
+        for (int c = 0; c < 4; ++c) hq[c] = *reinterpret_cast<const float4*>(&ws.heads[s8 * 4 + c * 32]);
+        for (int i0 = 0; i0 < nf; i0 += 4) {
+          const int ii = min(i0 + grp, nf - 1);
+          const float* p = kvlb + (size_t)ws.list[ii] * 384 + 256 + s8 * 4;
+          float4 lv[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) p[a] = fmaf(hv[3], lv[a].w, fmaf(hv[2], lv[a].z, fmaf(hv[1], lv[a].y, hv[0] * lv[a].x)));
+          for (int c = 0; c < 4; ++c) lv[c] = ldg4(p + c * 32);
+          float acc = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-          for (int a = 0; a < 4; ++a) p[a] += __shfl_xor_sync(FULL, p[a], o);
-        }
-        if (lane < 4 && i0 + lane < nf) {
-          float z = __fdiv_rn(sel4(p, lane), sqrt_d);
-          if (cfg.tanh_clipping > 0.f) z = tanhf(z) * cfg.tanh_clipping;
-          sm.logit[wid][i0 + lane] = __fdiv_rn(z, cfg.temp);
+          for (int c = 0; c < 4; ++c)
+            acc = fmaf(hq[c].w, lv[c].w, fmaf(hq[c].z, lv[c].z, fmaf(hq[c].y, lv[c].y, fmaf(hq[c].x, lv[c].x, acc))));
+          acc += __shfl_xor_sync(FULL, acc, 1);
+          acc += __shfl_xor_sync(FULL, acc, 2);
+          acc += __shfl_xor_sync(FULL, acc, 4);
+          if (s8 == 0 && i0 + grp < nf) {
+            float z = __fdiv_rn(acc, sqrt_d);
+            if (cfg.tanh_clipping > 0.f) z = tanhf(z) * cfg.tanh_clipping;
+            ws.logit[i0 + grp] = __fdiv_rn(z, cfg.temp);
+          }
         }
       }
       __syncwarp();
@@ -282,25 +357,25 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       float zl[4];
       float mx = -INFINITY;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int i = r * 32 + lane;
-        zl[r] = (i < nf) ? sm.logit[wid][i] : -INFINITY;
-        mx = fmaxf(mx, zl[r]);
+      for (int rr = 0; rr < 4; ++rr) {
+        const int i = rr * 32 + lane;
+        zl[rr] = (i < nf) ? ws.logit[i] : -INFINITY;
+        mx = fmaxf(mx, zl[rr]);
       }
       mx = warp_max(mx);
       float se = 0.f;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) if (r * 32 + lane < nf) se += expf(zl[r] - mx);
+      for (int rr = 0; rr < 4; ++rr) if (rr * 32 + lane < nf) se += expf(zl[rr] - mx);
       se = warp_sum(se);
       const float lgs = logf(se);
       const float lse = lgs + mx;
       float lp[4], pr[4];
       bool bad = false;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        lp[r] = (zl[r] - mx) - lgs;                            // x - max - log(sum(exp(x - max)))
-        pr[r] = (r * 32 + lane < nf) ? expf(lp[r]) : -1.f;     // probs = log_p.exp() (:265)
-        bad |= (r * 32 + lane < nf) && !(lp[r] == lp[r]);
+      for (int rr = 0; rr < 4; ++rr) {
+        lp[rr] = (zl[rr] - mx) - lgs;                          // x - max - log(sum(exp(x - max)))
+        pr[rr] = (rr * 32 + lane < nf) ? expf(lp[rr]) : -1.f;  // probs = log_p.exp() (:265)
+        bad |= (rr * 32 + lane < nf) && !(lp[rr] == lp[rr]);
       }
       if (__any_sync(FULL, bad) && lane == 0) atomicOr(status, EVRP_ST_NAN_LOGIT);
       // ---- pick ----
@@ -322,7 +397,7 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
         // first-index argmax of probs (torch.max(1), :327)
         float bv = pr[0]; int bi = lane;
 #pragma unroll
-        for (int r = 1; r < 4; ++r) if (pr[r] > bv) { bv = pr[r]; bi = r * 32 + lane; }
+        for (int rr = 1; rr < 4; ++rr) if (pr[rr] > bv) { bv = pr[rr]; bi = rr * 32 + lane; }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           const float ov = __shfl_xor_sync(FULL, bv, o);
@@ -337,7 +412,7 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
           const int i = lane * 4 + a;
-          const float pv = (i < nf) ? expf(sm.logit[wid][i] - lse) : 0.f;
+          const float pv = (i < nf) ? expf(ws.logit[i] - lse) : 0.f;
           s += pv; c[a] = s;
         }
         float incl = s;
@@ -355,13 +430,29 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       }
       int c_node; float lp_sel;
       if (sel_i >= 0) {
-        c_node = sm.list[wid][sel_i];
+        c_node = ws.list[sel_i];
         lp_sel = __shfl_sync(FULL, sel4(lp, sel_i >> 5), sel_i & 31);
       } else { c_node = -1 - sel_i; lp_sel = -INFINITY; }
 
+      // ---- loads for the transition and the new mask, issued together ----
+      const float dist = __ldg(Db + (size_t)now * S + c_node);
+      const float slp = __ldg(Gb + (size_t)now * S + c_node);
+      const float4 ec = ldg4(embb + (size_t)c_node * D + lane * 4);
+      float dcj[4], gcj[4], d0j[4], g0j[4], d3j[4], s3j[4], dmj[4];
+#pragma unroll
+      for (int jb = 0; jb < 4; ++jb) {
+        const int j = jb * 32 + lane;
+        const bool in = (jb < nblk) && (j < S);
+        dcj[jb] = in ? __ldg(Db + (size_t)c_node * S + j) : 0.f;
+        gcj[jb] = in ? __ldg(Gb + (size_t)c_node * S + j) : 0.f;
+        d0j[jb] = in ? __ldg(Db + j) : 0.f;
+        g0j[jb] = in ? __ldg(Gb + j) : 0.f;
+        d3j[jb] = in ? station_ws[((size_t)inst * 2 + 0) * SP + j] : 0.f;
+        s3j[jb] = in ? station_ws[((size_t)inst * 2 + 1) * SP + j] : 0.f;
+      }
       // ---- state transition (problems/EVRP.py:226-280) on warp-uniform scalars ----
-      const float dist = sm.dcur[wid][c_node];
-      const float slp = sm.gcur[wid][c_node];
+      float load = rs.load, soc = rs.soc, tim = rs.tim;
+      const float d4 = rs.d4;
       const float tc = travel_time(phys, dist);
       const float e = leg_energy(phys, vehicle_mass(phys, load), slp, tc);
       const bool is_depot = (c_node == 0), is_station = (c_node > 0 && c_node <= F), is_cust = (c_node > F);
@@ -371,16 +462,15 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       if (is_cust) tim = __fsub_rn(tim, phys.serve_time);
       soc = __fsub_rn(soc, e);
       if (c_node <= F) soc = phys.start_soc;
-      __syncwarp();
       if (is_cust) {
-        const float dmc = sm.dem[wid][c_node];
+        const float dmc = sm.dem[lr][c_node];
         const float nl = fmaxf(__fsub_rn(load, dmc), 0.f);
         const float nd = fmaxf(__fsub_rn(dmc, load), 0.f);
         __syncwarp();
-        if (lane == 0) { sm.dem[wid][c_node] = nd; sm.dem[wid][0] = __fadd_rn(-1.f, nl); }
+        if (lane == 0) { sm.dem[lr][c_node] = nd; sm.dem[lr][0] = __fadd_rn(-1.f, nl); }
         load = nl;
       }
-      if (is_depot) { load = 1.f; if (lane == 0) sm.dem[wid][0] = 0.f; }
+      if (is_depot) { load = 1.f; if (lane == 0) sm.dem[lr][0] = 0.f; }
       __syncwarp();
       if (lane == 0) {
         const size_t o = (size_t)row * Tcap + t;
@@ -390,28 +480,25 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       }
       // ---- running max of visited embeddings (route_feature :207-214) ----
       {
-        const float4 ec = ldg4(embb + (size_t)c_node * D + lane * 4);
-        float4 mm = *reinterpret_cast<float4*>(&sm.m[wid][lane * 4]);
-        if (first) mm = ec;
+        float4 mm = *reinterpret_cast<float4*>(&sm.m[lr][lane * 4]);
+        if (t == 0) mm = ec;
         else { mm.x = fmaxf(mm.x, ec.x); mm.y = fmaxf(mm.y, ec.y); mm.z = fmaxf(mm.z, ec.z); mm.w = fmaxf(mm.w, ec.w); }
-        *reinterpret_cast<float4*>(&sm.m[wid][lane * 4]) = mm;
-        first = false;
+        *reinterpret_cast<float4*>(&sm.m[lr][lane * 4]) = mm;
       }
       // ---- new mask (problems/EVRP.py:105-223) ----
       bool any_dem = false, cust_dem = false;
-      float dmj[4];
 #pragma unroll
       for (int jb = 0; jb < 4; ++jb) {
         const int j = jb * 32 + lane;
-        dmj[jb] = sm.dem[wid][j];
+        dmj[jb] = sm.dem[lr][j];
         any_dem |= (j < S) && (dmj[jb] != 0.f);
         cust_dem |= (j < S) && (j >= F) && (dmj[jb] != 0.f);
       }
       any_dem = __any_sync(FULL, any_dem);
       cust_dem = __any_sync(FULL, cust_dem);
-      ++t;
+      bool done = false;
       if (!any_dem) {
-        done = true;                                   // this row's tour is complete (:127)
+        done = true;                                     // this row's tour is complete (:127)
       } else {
         const bool combined = (load == 0.f) || !cust_dem;
         bool cust_ok = false;
@@ -422,9 +509,6 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
           const int j = jb * 32 + lane;
           bool mbit = false;
           if (j < S) {
-            const float dcj = __ldg(Db + (size_t)c_node * S + j);
-            const float gcj = __ldg(Gb + (size_t)c_node * S + j);
-            sm.dcur[wid][j] = dcj; sm.gcur[wid][j] = gcj;
             const float dm = dmj[jb];
             mbit = (dm != 0.f) && (dm < load);
             if (j == c_node) mbit = false;
@@ -433,20 +517,21 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
             if (is_cust && j <= F) mbit = true;
             if (is_depot && j == 0) mbit = false;
             if (combined) mbit = (j == 0);
-            if (!reachable(phys, j, F, load, load, dm, soc, tim, dcj, gcj, sm.D0[wid][j], sm.G0[wid][j],
-                           sm.d3[wid][j], sm.s3[wid][j], d4)) mbit = false;
-            if (j > F && mbit) cust_ok = true;
           }
+          if (__any_sync(FULL, mbit)) {                  // look-ahead rules 5-7 only where something is still open
+            if (mbit && !reachable(phys, j, F, load, load, dmj[jb], soc, tim, dcj[jb], gcj[jb], d0j[jb], g0j[jb],
+                                   d3j[jb], s3j[jb], d4)) mbit = false;
+          }
+          if (j > F && mbit) cust_ok = true;
           nm[jb] = __ballot_sync(FULL, mbit);
         }
         cust_ok = __any_sync(FULL, cust_ok);
-        if (!cust_ok) nm[0] |= 1u;                     // rule 8 (:220-221)
+        if (!cust_ok) nm[0] |= 1u;                       // rule 8 (:220-221)
         mk[0] = nm[0]; mk[1] = nm[1]; mk[2] = nm[2]; mk[3] = nm[3];
-        now = c_node;
         if ((mk[0] | mk[1] | mk[2] | mk[3]) == 0u) {
           if (lane == 0) atomicOr(status, EVRP_ST_NO_FEASIBLE);
           done = true;
-        } else if (t >= Tcap) {
+        } else if (t + 1 >= Tcap) {
           if (lane == 0) atomicOr(status, EVRP_ST_STEP_CAP);
           done = true;
         } else {
@@ -454,16 +539,21 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
 #pragma unroll
           for (int jb = 0; jb < 4; ++jb) {
             if ((mk[jb] >> lane) & 1u) {
-              const float* r = kvlb + (size_t)(jb * 32 + lane) * 384;
+              const float* p = kvlb + (size_t)(jb * 32 + lane) * 384;
 #pragma unroll
-              for (int c = 0; c < 4; ++c) prefetch_l2(r + c * 32);
+              for (int c = 0; c < 4; ++c) prefetch_l2(p + c * 32);
             }
           }
         }
       }
-      if (done && lane == 0) { steps_used[row] = t; atomicMax(t_max, t); }
+      if (lane == 0) {
+        rs.load = load; rs.soc = soc; rs.tim = tim; rs.now = c_node;
+        rs.mk[0] = mk[0]; rs.mk[1] = mk[1]; rs.mk[2] = mk[2]; rs.mk[3] = mk[3];
+        if (done) { rs.done = 1; steps_used[row] = t + 1; atomicMax(t_max, t + 1); }
+      }
       __syncwarp();
     }
+    ++t;
   }
 }
 
@@ -479,7 +569,7 @@ sample_min_kernel(const float* __restrict__ reward, const int64_t* __restrict__ 
   for (int r = lane; r < R; r += 32) {
     const float* rw = reward + ((size_t)r * B + b) * Tcap;
     float s = 0.f;
-    for (int t = 0; t < Tcap; ++t) s += rw[t];          // cost = R.sum(1) (:301), sequential fp32 like ATen's row sum for short rows
+    for (int t = 0; t < Tcap; ++t) s += rw[t];          // cost = R.sum(1) (:301)
     if (s < best || (s == best && r < bi)) { best = s; bi = r; }
   }
 #pragma unroll
@@ -497,26 +587,33 @@ sample_min_kernel(const float* __restrict__ reward, const int64_t* __restrict__ 
 
 extern "C" {
 
+size_t evrp_rollout_workspace_bytes(int B, int S) {
+  (void)S;
+  return (size_t)B * 2 * EVRP_MAX_S * sizeof(float);
+}
+
 int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evrp_rollout_cfg* cfg,
                  const float* emb, const float* kvl, const float* fixed_ctx, const float* dynamic0,
                  const float* distances, const float* slope, int B, int S, int F, const int64_t* forced_actions,
                  const float* uniforms, int64_t* pi, float* ll, float* reward, float* energy, uint32_t* saved_mask,
-                 float* saved_veh, int32_t* steps_used, int32_t* t_max, int32_t* status, void* stream) {
+                 float* saved_veh, int32_t* steps_used, int32_t* t_max, int32_t* status, void* workspace,
+                 size_t workspace_bytes, void* stream) {
   using namespace evrp;
   if (!phys || !w || !cfg || !emb || !kvl || !fixed_ctx || !dynamic0 || !distances || !slope || !pi || !ll ||
-      !reward || !steps_used || !t_max || !status || B < 0 || S < 2 || F < 1 || F >= S || cfg->max_steps < 1 ||
-      cfg->n_replicas < 1 || !(cfg->temp > 0.f))
+      !reward || !steps_used || !t_max || !status || !workspace || B < 0 || S < 2 || F < 1 || F >= S ||
+      cfg->max_steps < 1 || cfg->n_replicas < 1 || !(cfg->temp > 0.f))
     return -EVRP_E_BADARG;
   if (S > EVRP_MAX_S) return -EVRP_E_TOO_MANY_NODES;
+  if (workspace_bytes < evrp_rollout_workspace_bytes(B, S)) return -EVRP_E_WORKSPACE;
   if (B == 0) return 0;
   const int rows = B * cfg->n_replicas;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = sizeof(DecodeSmem);
   EVRP_CUDA_OK(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (rows + G - 1) / G;
-  rollout_kernel<<<grid, NT, smem, st>>>(*phys, *w, *cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope, B, S, F,
-                                         rows, forced_actions, uniforms, pi, ll, reward, energy, saved_mask,
-                                         saved_veh, steps_used, t_max, status);
+  const int grid = (rows + RPC - 1) / RPC;
+  rollout_kernel<<<grid, NT, smem, st>>>(*phys, *w, *cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope,
+                                         (float*)workspace, B, S, F, rows, forced_actions, uniforms, pi, ll, reward,
+                                         energy, saved_mask, saved_veh, steps_used, t_max, status);
   EVRP_LAUNCH_OK();
   return 0;
 }

@@ -183,35 +183,50 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
     }
   } else if (warp >= 4) {
     // ================= A converters: fp32 -> (hi, lo) TF32 planes, swizzled K-major =================
+    // Loads run PF k-blocks ahead of the conversion (register ring) so that global latency is off the critical path.
     const int t = threadIdx.x - 128;                     // 0..127
     const int c = t & 7, r0 = t >> 3;                    // 16-byte chunk within the 128-byte row, row within a 16-row slab
-    uint32_t it = 0;
-    for (int tile = cta_in_chunk; tile < m_tiles; tile += ctas_per_chunk) {
+    constexpr int PF = 3;
+    const int my_tiles = (m_tiles - cta_in_chunk + ctas_per_chunk - 1) / ctas_per_chunk;
+    const uint32_t total = (uint32_t)my_tiles * KB;
+    float4 v[PF][8];
+    auto issue = [&](uint32_t j, float4 (&dst)[8]) {
+      const int tile = cta_in_chunk + (int)(j / KB) * ctas_per_chunk, kb = (int)(j % KB);
       const int m0 = tile * BM;
-      for (int kb = 0; kb < KB; ++kb, ++it) {
-        const int s = it % STAGES;
-        float4 v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = i * 16 + r0;
-          v[i] = (m0 + row < M) ? __ldg(reinterpret_cast<const float4*>(A + (size_t)(m0 + row) * lda + kb * BKB + c * 4))
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        mbar_wait(&bars->empty[s], ((it / STAGES) & 1) ^ 1);
-        unsigned char* st = ring + s * STAGE_BYTES;
+      for (int i = 0; i < 8; ++i) {
+        const int row = i * 16 + r0;
+        dst[i] = (j < total && m0 + row < M)
+                     ? __ldg(reinterpret_cast<const float4*>(A + (size_t)(m0 + row) * lda + kb * BKB + c * 4))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = i * 16 + r0;
-          const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
-          uint4 hi, lo;
-          hi.x = to_tf32(v[i].x); hi.y = to_tf32(v[i].y); hi.z = to_tf32(v[i].z); hi.w = to_tf32(v[i].w);
-          lo.x = to_tf32(v[i].x - __uint_as_float(hi.x)); lo.y = to_tf32(v[i].y - __uint_as_float(hi.y));
-          lo.z = to_tf32(v[i].z - __uint_as_float(hi.z)); lo.w = to_tf32(v[i].w - __uint_as_float(hi.w));
-          *reinterpret_cast<uint4*>(st + off) = hi;
-          *reinterpret_cast<uint4*>(st + PLANE + off) = lo;
+    for (int p = 0; p < PF; ++p) issue(p, v[p]);
+    for (uint32_t it0 = 0; it0 < total; it0 += PF) {
+#pragma unroll
+      for (int p = 0; p < PF; ++p) {
+        const uint32_t it = it0 + p;
+        if (it < total) {
+          const int s = it % STAGES;
+          mbar_wait(&bars->empty[s], ((it / STAGES) & 1) ^ 1);
+          unsigned char* st = ring + s * STAGE_BYTES;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 16 + r0;
+            const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
+            const float4 x = v[p][i];
+            uint4 hi, lo;
+            hi.x = to_tf32(x.x); hi.y = to_tf32(x.y); hi.z = to_tf32(x.z); hi.w = to_tf32(x.w);
+            lo.x = to_tf32(x.x - __uint_as_float(hi.x)); lo.y = to_tf32(x.y - __uint_as_float(hi.y));
+            lo.z = to_tf32(x.z - __uint_as_float(hi.z)); lo.w = to_tf32(x.w - __uint_as_float(hi.w));
+            *reinterpret_cast<uint4*>(st + off) = hi;
+            *reinterpret_cast<uint4*>(st + PLANE + off) = lo;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05
+          mbar_arrive(&bars->full[s]);
+          issue(it + PF, v[p]);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05
-        mbar_arrive(&bars->full[s]);
       }
     }
   } else {

@@ -208,6 +208,7 @@ class AttentionModel(nn.Module):
             tcap = forced.shape[1]
         else:
             tcap = int(max_steps or min(self.max_steps, 8 * S))
+        wsp = torch.empty(L.evrp_rollout_workspace_bytes(B, S), dtype=torch.uint8, device=dev)
         while True:
             cfg = _lib.RolloutCfg(_lib.DECODE_SAMPLE if decode_type == "sample" else _lib.DECODE_GREEDY,
                                   float(self.temp), float(self.tanh_clipping), tcap,
@@ -228,7 +229,8 @@ class AttentionModel(nn.Module):
                                 _lib.ptr(dynamic), _lib.ptr(distances), _lib.ptr(slope), B, S, self.charging_num,
                                 _lib.ptr(forced), _lib.ptr(uniforms), _lib.ptr(pi), _lib.ptr(ll), _lib.ptr(R),
                                 _lib.ptr(E), _lib.ptr(smask), _lib.ptr(sveh), _lib.ptr(steps),
-                                _lib.ptr(meta[0:1]), _lib.ptr(meta[1:2]), _lib.stream_ptr())
+                                _lib.ptr(meta[0:1]), _lib.ptr(meta[1:2]), _lib.ptr(wsp), wsp.numel(),
+                                _lib.stream_ptr())
             _lib.check(rc, "evrp_rollout")
             if ev is not None:
                 ev[1].record()

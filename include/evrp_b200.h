@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 4
+#define EVRP_ABI_VERSION 5
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -172,7 +172,9 @@ int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evr
                  float* energy /*[B*R,Tcap] or NULL*/,
                  uint32_t* saved_mask /*[B*R,Tcap,4] or NULL*/, float* saved_veh /*[B*R,Tcap,3] or NULL*/,
                  int32_t* steps_used /*[B*R]*/, int32_t* t_max /*[1] atomicMax*/, int32_t* status /*[1]*/,
-                 void* stream);
+                 void* workspace /* evrp_rollout_workspace_bytes(B,S): rule-7 station constants per instance */,
+                 size_t workspace_bytes, void* stream);
+size_t evrp_rollout_workspace_bytes(int B, int S);
 
 /* sample_many reduction (nets/DRLModel.py:301-311): per instance min cost over replicas + its tour. */
 int evrp_sample_min(const float* reward /*[B*R,Tcap]*/, const int64_t* pi, int B, int R, int Tcap,
