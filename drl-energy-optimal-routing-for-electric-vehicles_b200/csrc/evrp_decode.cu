@@ -278,13 +278,14 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
         q[2] = (fc.z + (cx.z + b2.z)) + en.z;
         q[3] = (fc.w + (cx.w + b2.w)) + en.w;
       }
-      // ---- compat[h][i] = q_h . K[j_i, h] / 4 ----
-      for (int i0 = 0; i0 < nf; i0 += 4) {
-        float4 kv[4];
+      // ---- compat[h][i] = q_h . K[j_i, h] / 4 ; CH rows (CH x 512 B) in flight per warp ----
+      constexpr int CH = 8;
+      for (int i0 = 0; i0 < nf; i0 += CH) {
+        float4 kv[CH];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) kv[a] = ldg4(kvlb + (size_t)ws.list[min(i0 + a, nf - 1)] * 384 + lane * 4);
+        for (int a = 0; a < CH; ++a) kv[a] = ldg4(kvlb + (size_t)ws.list[min(i0 + a, nf - 1)] * 384 + lane * 4);
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
+        for (int a = 0; a < CH; ++a) {
           float p = fmaf(q[3], kv[a].w, fmaf(q[2], kv[a].z, fmaf(q[1], kv[a].y, q[0] * kv[a].x)));
           p += __shfl_xor_sync(FULL, p, 1);
           p += __shfl_xor_sync(FULL, p, 2);
@@ -308,16 +309,16 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       // ---- heads = attn @ V ; lane owns 4 channels ----
       {
         float hv[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int i0 = 0; i0 < nf; i0 += 4) {
-          float4 vv[4]; float pr[4];
+        for (int i0 = 0; i0 < nf; i0 += CH) {
+          float4 vv[CH]; float pr[CH];
 #pragma unroll
-          for (int a = 0; a < 4; ++a) {
+          for (int a = 0; a < CH; ++a) {
             const int ii = min(i0 + a, nf - 1);
             vv[a] = ldg4(kvlb + (size_t)ws.list[ii] * 384 + 128 + lane * 4);
             pr[a] = (i0 + a < nf) ? ws.pc[hd][ii] : 0.f;
           }
 #pragma unroll
-          for (int a = 0; a < 4; ++a) {
+          for (int a = 0; a < CH; ++a) {
             hv[0] = fmaf(pr[a], vv[a].x, hv[0]); hv[1] = fmaf(pr[a], vv[a].y, hv[1]);
             hv[2] = fmaf(pr[a], vv[a].z, hv[2]); hv[3] = fmaf(pr[a], vv[a].w, hv[3]);
           }
@@ -332,23 +333,30 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
         float4 hq[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) hq[c] = *reinterpret_cast<const float4*>(&ws.heads[s8 * 4 + c * 32]);
-        for (int i0 = 0; i0 < nf; i0 += 4) {
-          const int ii = min(i0 + grp, nf - 1);
-          const float* p = kvlb + (size_t)ws.list[ii] * 384 + 256 + s8 * 4;
-          float4 lv[4];
+        for (int i0 = 0; i0 < nf; i0 += 16) {            // 4 nodes per sub-pass, 4 sub-passes in flight
+          float4 lv[4][4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) lv[c] = ldg4(p + c * 32);
-          float acc = 0.f;
+          for (int u = 0; u < 4; ++u) {
+            const int ii = min(i0 + u * 4 + grp, nf - 1);
+            const float* p = kvlb + (size_t)ws.list[ii] * 384 + 256 + s8 * 4;
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
-            acc = fmaf(hq[c].w, lv[c].w, fmaf(hq[c].z, lv[c].z, fmaf(hq[c].y, lv[c].y, fmaf(hq[c].x, lv[c].x, acc))));
-          acc += __shfl_xor_sync(FULL, acc, 1);
-          acc += __shfl_xor_sync(FULL, acc, 2);
-          acc += __shfl_xor_sync(FULL, acc, 4);
-          if (s8 == 0 && i0 + grp < nf) {
-            float z = __fdiv_rn(acc, sqrt_d);
-            if (cfg.tanh_clipping > 0.f) z = tanhf(z) * cfg.tanh_clipping;
-            ws.logit[i0 + grp] = __fdiv_rn(z, cfg.temp);
+            for (int c = 0; c < 4; ++c) lv[u][c] = ldg4(p + c * 32);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              acc = fmaf(hq[c].w, lv[u][c].w, fmaf(hq[c].z, lv[u][c].z, fmaf(hq[c].y, lv[u][c].y, fmaf(hq[c].x, lv[u][c].x, acc))));
+            acc += __shfl_xor_sync(FULL, acc, 1);
+            acc += __shfl_xor_sync(FULL, acc, 2);
+            acc += __shfl_xor_sync(FULL, acc, 4);
+            const int i = i0 + u * 4 + grp;
+            if (s8 == 0 && i < nf) {
+              float z = __fdiv_rn(acc, sqrt_d);
+              if (cfg.tanh_clipping > 0.f) z = tanhf(z) * cfg.tanh_clipping;
+              ws.logit[i] = __fdiv_rn(z, cfg.temp);
+            }
           }
         }
       }
@@ -534,16 +542,6 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
         } else if (t + 1 >= Tcap) {
           if (lane == 0) atomicOr(status, EVRP_ST_STEP_CAP);
           done = true;
-        } else {
-          // next step's glimpse keys: start pulling them into L2 now (the FF_tour GEMMs cover the latency)
-#pragma unroll
-          for (int jb = 0; jb < 4; ++jb) {
-            if ((mk[jb] >> lane) & 1u) {
-              const float* p = kvlb + (size_t)(jb * 32 + lane) * 384;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) prefetch_l2(p + c * 32);
-            }
-          }
         }
       }
       if (lane == 0) {

@@ -1,0 +1,190 @@
+"""CPU tests of the drop-in boundary and host logic (no compute kernel is launched here)."""
+import ctypes
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import evrp_b200
+from evrp_b200 import _lib, policy_math as PM
+from oracle import evrp_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def args_for(N, F=5):
+    return types.SimpleNamespace(CVRP_lib_test=False, Start_SOC=80., t_limit=10., num_nodes=N, charging_num=F)
+
+
+def bn_perturb(sd, seed=7):
+    rs = np.random.RandomState(seed)
+    out = {}
+    for k, v in sd.items():
+        v = v.clone()
+        if "normalizer.running_mean" in k:
+            v = torch.from_numpy((rs.randn(*v.shape) * 0.2).astype(np.float32))
+        elif "normalizer.running_var" in k:
+            v = torch.from_numpy((rs.rand(*v.shape) * 1.5 + 0.5).astype(np.float32))
+        elif "normalizer.weight" in k:
+            v = torch.from_numpy((rs.rand(*v.shape) + 0.5).astype(np.float32))
+        elif "normalizer.bias" in k:
+            v = torch.from_numpy((rs.randn(*v.shape) * 0.1).astype(np.float32))
+        out[k] = v
+    return out
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    L = evrp_b200.lib()
+    header = open(os.path.join(ROOT, "include", "evrp_b200.h")).read()
+    declared = set(re.findall(r"\b(evrp_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in include/evrp_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), "ctypes binding and header disagree"
+    assert L.evrp_abi_version() == _lib.ABI_VERSION
+
+
+def test_phys_constants_match_python_expressions():
+    L = evrp_b200.lib()
+    c = _lib.Phys()
+    L.evrp_phys_default(ctypes.byref(c), 50., 80., 10., 4.)
+    p = _lib.make_phys()
+    for name, _ in _lib.Phys._fields_:
+        assert getattr(c, name) == getattr(p, name), name
+    oc = O.EVRPConsts()
+    assert np.float32(p.aero) == oc.aero and np.float32(p.kd) == oc.kd and np.float32(p.kr) == oc.kr
+
+
+def test_constructor_reproduces_reference_initialisation():
+    """torch.manual_seed(0) + construction == the reference's AttentionModel weights, bit for bit"""
+    W = np.load(os.path.join(GOLDEN, "weights_seed0.npz"))
+    torch.manual_seed(0)
+    m = evrp_b200.AttentionModel(128, 128, args_for(20), n_encode_layers=3)
+    sd = m.state_dict()
+    assert set(sd.keys()) == set(W.files) and len(list(m.parameters())) == 50
+    assert sum(p.numel() for p in m.parameters()) == 874112
+    for k in W.files:
+        assert np.array_equal(sd[k].numpy(), W[k]), k
+
+
+def test_dataset_reproduces_reference_rng_stream():
+    g = np.load(os.path.join(GOLDEN, "greedy_n20.npz"))
+    ds = evrp_b200.VehicleRoutingDataset(32, 20, 10., 80., 50., 4, 4, 5, 12345, args_for(20), device="cpu")
+    assert np.array_equal(ds.static.numpy(), g["static"])
+    assert np.array_equal(ds.dynamic.numpy(), g["dynamic"])
+    assert np.array_equal(ds.Elevation.numpy(), g["elevation"])
+    assert np.array_equal(ds.distances.numpy(), g["distances"]) and np.array_equal(ds.slope.numpy(), g["slope"])
+    item = ds[3]
+    assert len(item) == 4 and item[2].shape == (26, 26)
+    big = evrp_b200.VehicleRoutingDataset(12801, 21, 10., 80., 50., 4, 4, 5, 1, args_for(21), device="cpu")
+    assert len(big[0]) == 3                                   # problems/EVRP.py:99-102 arity rule
+
+
+def test_no_cpu_fallback():
+    m = evrp_b200.AttentionModel(128, 128, args_for(20), n_encode_layers=3)
+    m.set_decode_type("greedy")
+    g = np.load(os.path.join(GOLDEN, "greedy_n20.npz"))
+    batch = tuple(torch.from_numpy(g[k]) for k in ("static", "dynamic", "distances", "slope"))
+    with pytest.raises(evrp_b200.EvrpLibraryError):
+        m(batch)
+    ds = evrp_b200.VehicleRoutingDataset(4, 20, 10., 80., 50., 4, 4, 5, 1, args_for(20), device="cpu")
+    with pytest.raises(evrp_b200.EvrpLibraryError):
+        ds.update_mask(batch[1], batch[2], batch[3], torch.zeros(32, dtype=torch.int64))
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libevrp_b200.so")
+    with pytest.raises(evrp_b200.EvrpLibraryError):
+        _lib.lib()
+
+
+def test_foreign_callbacks_are_rejected():
+    m = evrp_b200.AttentionModel(128, 128, args_for(20), n_encode_layers=3,
+                                 update_dynamic=lambda *a: None, update_mask=lambda *a: None)
+    assert not m._fused_path_ok()
+
+
+def test_weight_packing_and_folds():
+    torch.manual_seed(0)
+    m = evrp_b200.AttentionModel(128, 128, args_for(20), n_encode_layers=3)
+    m.load_state_dict(bn_perturb(m.state_dict()))
+    m.eval()
+    pk = m.packed_weights()
+    assert pk is m.packed_weights()                           # cached until a parameter changes
+    assert pk["l0.Wqkv"].shape == (128, 384) and pk["l0.ff1w"].shape == (128, 512) and pk["node_proj"].shape == (128, 384)
+    x = torch.randn(7, 128)
+    att = m.embedder.layers[0][0].module
+    q_ref = torch.matmul(x, att.W_query).permute(1, 0, 2).reshape(7, 128)
+    assert torch.allclose(x @ pk["l0.Wqkv"][:, :128], q_ref, atol=1e-5)
+    bn = m.embedder.layers[0][1].normalizer
+    assert torch.allclose(bn(x), x * pk["l0.bn1s"] + pk["l0.bn1b"], atol=1e-5)
+    heads = torch.randn(7, 128)
+    lk_ref = m.project_node_embeddings(x)[:, 256:]
+    logits_ref = (m.project_out(heads) * lk_ref).sum(1)
+    assert torch.allclose((heads * (x @ pk["node_proj"][:, 256:])).sum(1), logits_ref, atol=1e-4)
+    veh = torch.randn(7, 3)
+    h_ref = m.FF_tour[0](torch.cat([m.tour(veh), x], 1))
+    h_fold = veh @ pk["w1_veh"] + x @ pk["w1_max"] + pk["b1"]
+    assert torch.allclose(h_fold, h_ref, atol=1e-4)
+    with torch.no_grad():
+        m.tour.weight.add_(1.0)
+    assert m.packed_weights() is not pk                       # version counter invalidates the cache
+
+
+def test_tf32_split_is_exact_to_fp32_rounding():
+    w = torch.randn(512, 128) * 3
+    hi, lo = PM.split_tf32(w)
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0 and int((lo.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert float(((w - (hi + lo)).abs() / w.abs().clamp_min(1e-30)).max()) <= 2 ** -22
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_training_math_matches_reference_gradients(mode):
+    """policy_math.encode_torch + teacher_forced_ll against the reference's REINFORCE gradients (CPU, fp32)"""
+    g = np.load(os.path.join(GOLDEN, "sample_n20.npz"))
+    torch.manual_seed(0)
+    m = evrp_b200.AttentionModel(128, 128, args_for(20), n_encode_layers=3)
+    m.load_state_dict(bn_perturb(m.state_dict()))
+    W = {k: v.detach().numpy() for k, v in m.state_dict().items()}
+    o = O.rollout(W, g["static"], g["dynamic"], g["distances"], g["slope"], forced=g["pi"], trace=True)
+    B, T = g["pi"].shape
+    S = 26
+    mask = o["mask"].astype(bool)
+    bits = np.zeros((B, T, 4), np.int64)
+    for j in range(S):
+        bits[..., j >> 5] |= mask[..., j].astype(np.int64) << (j & 31)
+    bits = torch.from_numpy(bits.astype(np.uint32).view(np.int32).reshape(B, T, 4))
+    before = np.concatenate([g["dynamic"][:, None], o["dynamic"][:, :-1]], 1)
+    veh = torch.from_numpy(np.stack([before[:, :, 0, 0], before[:, :, 2, 0] / np.float32(80),
+                                     before[:, :, 3, 0] / np.float32(10)], -1).astype(np.float32))
+    m.train(mode == "train")
+    emb, kvl, fixed = PM.encode_torch(m, torch.from_numpy(g["static"]), torch.from_numpy(g["dynamic"]))
+    ll = PM.teacher_forced_ll(m, emb, kvl, fixed, torch.from_numpy(g["pi"]), bits, veh,
+                              torch.full((B,), T, dtype=torch.int32))
+    assert float((ll - torch.from_numpy(g[f"ll_{mode}"])).abs().max()) < 2e-5
+    (torch.from_numpy(g["adv"]) * ll.sum(1)).mean().backward()
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        ref = torch.from_numpy(g[f"g_{mode}/{k}"])
+        num += float((p.grad - ref).norm() ** 2); den += float(ref.norm() ** 2)
+    assert (num / den) ** 0.5 < 1e-4
+
+
+def test_cvrplib_parser(tmp_path):
+    txt = "NAME : toy\nTYPE : CVRP\nDIMENSION : 4\nEDGE_WEIGHT_TYPE : EUC_2D\nCAPACITY : 100\nNODE_COORD_SECTION\n" \
+          "1 30 40\n2 37 52\n3 49 43\n4 52 64\nDEMAND_SECTION\n1 0\n2 19\n3 30\n4 16\nDEPOT_SECTION\n1\n-1\nEOF\n"
+    f = tmp_path / "toy.txt"
+    f.write_text(txt)
+    coords, dem, cap = evrp_b200.parse_cvrplib(str(f))
+    assert coords == [(30, 40), (37, 52), (49, 43), (52, 64)] and dem == [0, 19, 30, 16] and cap == 100
+    a = args_for(3); a.CVRP_lib_test = True; a.CVRP_lib_path = str(f)
+    ds = evrp_b200.VehicleRoutingDataset(5, 3, 10., 80., 50., 4, 4, 5, 1, a, device="cpu")
+    assert len(ds) == 1 and ds.static.shape == (1, 2, 9)
+    assert torch.allclose(ds.dynamic[0, 1, 6:], torch.tensor([0.19, 0.30, 0.16]))
+    assert torch.equal(ds.static[0, :, 0], torch.tensor([30., 40.]))

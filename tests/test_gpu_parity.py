@@ -136,17 +136,21 @@ def test_encoder_matches_oracle(evrp, weights, name, bn):
     N = g["static"].shape[2] - 6
     m, _ = make_model(evrp, N, W)
     static, dynamic, _, _ = batch_of(g)
-    emb, kvl, fixed = m.encode(static, dynamic)
     ref = O.encoder(W, O.init_embed(W, g["static"], g["dynamic"], 5))
-    assert np.abs(emb.cpu().numpy() - ref).max() < 2e-5
+    m.gemm_mode = 1                                   # fp32 FFMA GEMMs: fp32-rounding-level agreement
+    emb1, _, _ = m.encode(static, dynamic)
+    assert np.abs(emb1.cpu().numpy() - ref).max() < 1e-5
+    m.gemm_mode = 0                                   # tcgen05 3xTF32 (default): TMEM accumulation truncates, ~1e-5
+    emb, kvl, fixed = m.encode(static, dynamic)
+    assert np.abs(emb.cpu().numpy() - ref).max() < 5e-5
     fc, gK, gV, lK = O.precompute(W, ref)
     B, S = ref.shape[:2]
     kv = kvl.cpu().numpy()
-    assert np.abs(kv[..., :128] - gK.transpose(0, 2, 1, 3).reshape(B, S, 128)).max() < 2e-5
-    assert np.abs(kv[..., 128:256] - gV.transpose(0, 2, 1, 3).reshape(B, S, 128)).max() < 2e-5
+    assert np.abs(kv[..., :128] - gK.transpose(0, 2, 1, 3).reshape(B, S, 128)).max() < 5e-5
+    assert np.abs(kv[..., 128:256] - gV.transpose(0, 2, 1, 3).reshape(B, S, 128)).max() < 5e-5
     lK_fold = lK @ W["project_out.weight"]            # (Wout^T Wl) emb = lK @ Wout
-    assert np.abs(kv[..., 256:] - lK_fold).max() < 5e-5
-    assert np.abs(fixed.cpu().numpy() - fc).max() < 2e-5
+    assert np.abs(kv[..., 256:] - lK_fold).max() < 1e-4
+    assert np.abs(fixed.cpu().numpy() - fc).max() < 5e-5
 
 
 # ---------------------------------------------------------------------------------------------
