@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(NT, 2)
 rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
                const float* __restrict__ emb, const float* __restrict__ kvl, const float* __restrict__ fixed_ctx,
                const float* __restrict__ dynamic0, const float* __restrict__ Dm, const float* __restrict__ Gm,
-               float* station_ws, int B, int S, int F, int rows_total,
+               float* station_ws, int B, int S, int F, int rows_total, int rows_per_cta,
                const int64_t* __restrict__ forced, const float* __restrict__ uniforms,
                int64_t* __restrict__ pi, float* __restrict__ ll, float* __restrict__ reward,
                float* __restrict__ energy, uint32_t* __restrict__ saved_mask, float* __restrict__ saved_veh,
@@ -85,9 +85,9 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
 
   // ---------------- prologue: per-row state ----------------
   for (int r = 0; r < RPW; ++r) {
-    const int lr = wid * RPW + r;
-    const int row = blockIdx.x * RPC + lr;
-    const bool valid = row < rows_total;
+    const int lr = r * (NT / 32) + wid;                       // warp w owns local rows w, 8+w, 16+w, 24+w
+    const int row = blockIdx.x * rows_per_cta + lr;
+    const bool valid = (lr < rows_per_cta) && (row < rows_total);
     const int inst = valid ? row % B : 0;
     const float* Db = Dm + (size_t)inst * S * S;
     const float* Gb = Gm + (size_t)inst * S * S;
@@ -133,16 +133,16 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
   while (true) {
     int my_done = 1;
 #pragma unroll
-    for (int r = 0; r < RPW; ++r) my_done &= sm.rs[wid * RPW + r].done;
+    for (int r = 0; r < RPW; ++r) my_done &= sm.rs[r * (NT / 32) + wid].done;
     if (__syncthreads_and(my_done)) break;
     // vehicle scalars + trace
     if (lane < RPW) {
-      const int lr = wid * RPW + lane;
+      const int lr = lane * (NT / 32) + wid;
       const RowState& rs = sm.rs[lr];
       if (!rs.done) {
         const float v1 = __fdiv_rn(rs.soc, phys.start_soc), v2 = __fdiv_rn(rs.tim, phys.t_limit);
         sm.veh[lr][0] = rs.load; sm.veh[lr][1] = v1; sm.veh[lr][2] = v2;
-        const size_t row = (size_t)blockIdx.x * RPC + lr;
+        const size_t row = (size_t)blockIdx.x * rows_per_cta + lr;
         if (saved_veh) { float* sv = saved_veh + (row * Tcap + t) * 3; sv[0] = rs.load; sv[1] = v1; sv[2] = v2; }
         if (saved_mask) {
           uint32_t* smk = saved_mask + (row * Tcap + t) * 4;
@@ -240,10 +240,10 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
     const int hd = lane >> 2, sub = lane & 3;
 #pragma unroll 1
     for (int r = 0; r < RPW; ++r) {
-      const int lr = wid * RPW + r;
+      const int lr = r * (NT / 32) + wid;
       RowState& rs = sm.rs[lr];
       if (rs.done) continue;                             // warp-uniform
-      const int row = blockIdx.x * RPC + lr;
+      const int row = blockIdx.x * rows_per_cta + lr;
       const int inst = rs.inst;
       const int now = rs.now;
       const float* Db = Dm + (size_t)inst * S * S;
@@ -608,9 +608,19 @@ int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evr
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = sizeof(DecodeSmem);
   EVRP_CUDA_OK(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = (rows + RPC - 1) / RPC;
+  // balance: fill whole waves of (2 CTAs x SMs) slots and spread the rows evenly over them (<= RPC rows per CTA)
+  int dev = 0, sms = 148;
+  EVRP_CUDA_OK(cudaGetDevice(&dev));
+  EVRP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int slots = 2 * sms;
+  const int min_ctas = (rows + RPC - 1) / RPC;
+  const int waves = (min_ctas + slots - 1) / slots;
+  int grid = waves * slots;
+  if (grid > rows) grid = rows;
+  const int rows_per_cta = (rows + grid - 1) / grid;
+  grid = (rows + rows_per_cta - 1) / rows_per_cta;
   rollout_kernel<<<grid, NT, smem, st>>>(*phys, *w, *cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope,
-                                         (float*)workspace, B, S, F, rows, forced_actions, uniforms, pi, ll, reward,
+                                         (float*)workspace, B, S, F, rows, rows_per_cta, forced_actions, uniforms, pi, ll, reward,
                                          energy, saved_mask, saved_veh, steps_used, t_max, status);
   EVRP_LAUNCH_OK();
   return 0;

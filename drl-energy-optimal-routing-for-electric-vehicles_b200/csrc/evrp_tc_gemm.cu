@@ -234,15 +234,20 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
     uint32_t tcount = 0;
     for (int tile = cta_in_chunk; tile < m_tiles; tile += ctas_per_chunk, ++tcount) {
       const int buf = tcount & 1;
-      const int m = tile * BM + warp * 32 + lane;
       mbar_wait(&bars->acc_full[buf], (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // tcgen05.ld.16x256b.x8: 16 TMEM lanes x 64 columns per instruction.  Thread T receives, for i = 0..7,
+      //   r[4i], r[4i+1]   = row T/4,     columns 8i + 2(T%4), +1
+      //   r[4i+2], r[4i+3] = row T/4 + 8, same columns
+      // so every warp-wide 8-byte store writes 8 rows x one full 32-byte sector (no partial-sector traffic).
+      const int tq = lane & 3, tr = lane >> 2;
 #pragma unroll 1
-      for (int cb = 0; cb < BN; cb += 32) {
+      for (int part = 0; part < 4; ++part) {
+        const int slab = part >> 1, cb = (part & 1) * 64;
         uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + buf * BN + cb;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32 + slab * 16) << 16) + buf * BN + cb;
         asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, "
             "%23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -251,26 +256,27 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
               "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (m < M) {
-          const int n = n0 + cb;
+        const int mbase = tile * BM + warp * 32 + slab * 16 + tr;
 #pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            float v[4] = {__uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3])};
-            if (EPI & EPI_BIAS) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(ep.bias + n + q));
-              v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
+        for (int i = 0; i < 8; ++i) {
+          const int n = n0 + cb + 8 * i + 2 * tq;
+          float2 bb = make_float2(0.f, 0.f), sc = make_float2(1.f, 1.f), sh = make_float2(0.f, 0.f);
+          if (EPI & EPI_BIAS) bb = __ldg(reinterpret_cast<const float2*>(ep.bias + n));
+          if (EPI & EPI_AFFINE) { sc = __ldg(reinterpret_cast<const float2*>(ep.scale + n)); sh = __ldg(reinterpret_cast<const float2*>(ep.shift + n)); }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int m = mbase + 8 * h;
+            if (m < M) {
+              float v0 = __uint_as_float(r[4 * i + 2 * h]), v1 = __uint_as_float(r[4 * i + 2 * h + 1]);
+              if (EPI & EPI_BIAS) { v0 += bb.x; v1 += bb.y; }
+              if (EPI & EPI_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+              if (EPI & EPI_RESID) {
+                const float2 rr = __ldg(reinterpret_cast<const float2*>(ep.resid + (size_t)m * ep.ldr + n));
+                v0 += rr.x; v1 += rr.y;
+              }
+              if (EPI & EPI_AFFINE) { v0 = fmaf(v0, sc.x, sh.x); v1 = fmaf(v1, sc.y, sh.y); }
+              *reinterpret_cast<float2*>(C + (size_t)m * ldc + n) = make_float2(v0, v1);
             }
-            if (EPI & EPI_RELU) { v[0] = fmaxf(v[0], 0.f); v[1] = fmaxf(v[1], 0.f); v[2] = fmaxf(v[2], 0.f); v[3] = fmaxf(v[3], 0.f); }
-            if (EPI & EPI_RESID) {
-              const float4 rr = __ldg(reinterpret_cast<const float4*>(ep.resid + (size_t)m * ep.ldr + n + q));
-              v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w;
-            }
-            if (EPI & EPI_AFFINE) {
-              const float4 sc = __ldg(reinterpret_cast<const float4*>(ep.scale + n + q));
-              const float4 sh = __ldg(reinterpret_cast<const float4*>(ep.shift + n + q));
-              v[0] = fmaf(v[0], sc.x, sh.x); v[1] = fmaf(v[1], sc.y, sh.y); v[2] = fmaf(v[2], sc.z, sh.z); v[3] = fmaf(v[3], sc.w, sh.w);
-            }
-            *reinterpret_cast<float4*>(C + (size_t)m * ldc + n + q) = make_float4(v[0], v[1], v[2], v[3]);
           }
         }
       }
