@@ -136,6 +136,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1024)
     ap.add_argument("--ref-sample", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=3, help="timed REINFORCE steps (0 = skip)")
+    ap.add_argument("--train-batch", type=int, default=1024)
     a = ap.parse_args()
     if a.impl == "reference":
         return run_reference(a)
@@ -220,6 +222,33 @@ def main():
         inst_steps_all = sm[3].item()
     else:
         ms_total, e2e_ms, roll_avg_ms, inst_steps_all = tm[0].item(), tm[1].item(), tm[2].item(), tm[3].item()
+    # ---------------- REINFORCE training step (BASELINE configs[4] shape: EM-EVRP-100, batch 1024 per GPU) ----------
+    train = None
+    if a.train_steps > 0:
+        from evrp_b200 import train as Tr
+        tb = a.train_batch
+        tm_model = evrp_b200.AttentionModel(128, 128, args, n_encode_layers=3, update_dynamic=ds.update_dynamic,
+                                            update_mask=ds.update_mask)
+        tm_model.load_state_dict({k: torch.from_numpy(v) for k, v in golden_weights().items()})
+        tm_model = tm_model.to(dev).train()
+        tm_model.set_decode_type("sample")
+        opt = torch.optim.Adam(tm_model.parameters(), lr=1e-4)
+        bl = Tr.ExponentialBaseline(0.8)
+        tbatch = (st[:tb].contiguous(), dy[:tb].contiguous(), D[:tb].contiguous(), G[:tb].contiguous())
+        for _ in range(2):
+            Tr.reinforce_step(tm_model, bl, opt, tbatch, 2.0)
+        barrier()
+        tt0 = time.perf_counter()
+        for _ in range(a.train_steps):
+            out = Tr.reinforce_step(tm_model, bl, opt, tbatch, 2.0)
+        barrier()
+        tsec = torch.tensor([time.perf_counter() - tt0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
+        train = {"metric": "REINFORCE train step/sec (EM-EVRP-100)", "value": a.train_steps / tsec.item(),
+                 "unit": "step/s", "per_gpu_batch": tb, "global_batch": tb * world, "decode_steps": int(out["T"]),
+                 "includes": "sampled rollout kernel + teacher-forced log-probs + fused loss kernel + backward + "
+                             "flat NCCL gradient all-reduce + clip + Adam"}
     if rank == 0:
         pk, pk_src = peaks()
         a_step = 1568 * S + 2048                                   # SURVEY §8d algorithmic bytes per instance-step
@@ -248,6 +277,8 @@ def main():
                              "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
                              "kernel_ms": roll_avg_ms, "kernel_share_of_step": roll_avg_ms / (ms_total / a.steps),
                              "algorithmic_bytes_per_launch": alg_bytes_per_launch}}
+        if train is not None:
+            line["train"] = train
         if world == 1 and not a.no_cpu_baseline:
             r, cores, dt, Tc = cpu_port_rate(N, a.cpu_sample)
             line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",

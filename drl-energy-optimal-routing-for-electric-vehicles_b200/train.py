@@ -238,6 +238,39 @@ class WarmupBaseline(Baseline):
 
 
 # ------------------------------------------------------------------------------------------------
+# fused REINFORCE loss (csrc/evrp_loss.cu)
+# ------------------------------------------------------------------------------------------------
+class ReinforceLoss(torch.autograd.Function):
+    """loss = mean_global((R.sum(1) - baseline).detach() * ll.sum(1))  (trainer.py:116-121) in ONE pair of kernels:
+    the forward also produces d loss / d ll, so the backward is a single scale."""
+
+    @staticmethod
+    def forward(ctx, ll, R, baseline, inv_global_batch):
+        from . import _lib
+        L = _lib.lib()
+        ll_c, R_c = ll.detach().contiguous(), R.detach().contiguous()
+        B, T = ll_c.shape
+        dev = ll_c.device
+        bl = torch.as_tensor(baseline, dtype=torch.float32, device=dev).detach().reshape(-1).contiguous()
+        assert bl.numel() in (1, B)
+        reward, adv, scratch = (torch.empty(B, device=dev) for _ in range(3))
+        grad_ll = torch.empty(B, T, device=dev)
+        loss = torch.empty(1, device=dev)
+        rc = L.evrp_reinforce_loss(_lib.ptr(ll_c), _lib.ptr(R_c), _lib.ptr(bl), int(bl.numel() == 1), B, T,
+                                   float(inv_global_batch), _lib.ptr(reward), _lib.ptr(adv), _lib.ptr(grad_ll),
+                                   _lib.ptr(loss), _lib.ptr(scratch), _lib.stream_ptr())
+        _lib.check(rc, "evrp_reinforce_loss")
+        ctx.save_for_backward(grad_ll)
+        ctx.mark_non_differentiable(reward, adv)
+        return loss[0], reward, adv
+
+    @staticmethod
+    def backward(ctx, g_loss, g_reward, g_adv):
+        (grad_ll,) = ctx.saved_tensors
+        return grad_ll * g_loss, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
 # one optimisation step
 # ------------------------------------------------------------------------------------------------
 def clip_grad_norms(param_groups, max_norm=math.inf):
@@ -259,11 +292,11 @@ def reinforce_step(actor, baseline, optimizer, batch, max_grad_norm=2.0, forced_
         bl_val, bl_loss = baseline.eval(x, reward)
     else:
         bl_val, bl_loss = bl_val.to(reward.device), 0
-    advantage = reward - bl_val
-    local = (advantage.detach() * ll.sum(1))
-    n_global = torch.tensor(float(local.numel()), device=local.device)
+    n_global = torch.tensor(float(reward.numel()), device=reward.device)
     allreduce_sum_(n_global)
-    loss = local.sum() / n_global + bl_loss          # each rank holds its share of the global mean
+    # fused kernel: reward / advantage / loss and d loss / d ll; each rank holds its share of the GLOBAL mean
+    loss, reward, advantage = ReinforceLoss.apply(ll, R, bl_val, 1.0 / float(n_global))
+    loss = loss + bl_loss
     optimizer.zero_grad()
     loss.backward()
     allreduce_gradients([p for g in optimizer.param_groups for p in g['params']])

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 5
+#define EVRP_ABI_VERSION 6
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -179,6 +179,16 @@ size_t evrp_rollout_workspace_bytes(int B, int S);
 /* sample_many reduction (nets/DRLModel.py:301-311): per instance min cost over replicas + its tour. */
 int evrp_sample_min(const float* reward /*[B*R,Tcap]*/, const int64_t* pi, int B, int R, int Tcap,
                     float* mincost /*[B]*/, int32_t* argmin /*[B]*/, int64_t* minpi /*[B,Tcap]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (4) fused REINFORCE loss / advantage (trainer.py:116-121):  reward = R.sum(1); advantage = reward - baseline;
+ *     loss = sum_b(advantage * ll.sum(1)) * inv_global_batch;  grad_ll[b,t] = advantage[b] * inv_global_batch.
+ *     `baseline` is [B] (rollout baseline) or one scalar (exponential baseline); `scratch` is [B] floats.
+ * ---------------------------------------------------------------------------------------------- */
+int evrp_reinforce_loss(const float* ll /*[B,T]*/, const float* R /*[B,T]*/, const float* baseline,
+                        int baseline_is_scalar, int B, int T, float inv_global_batch, float* reward /*[B]*/,
+                        float* advantage /*[B]*/, float* grad_ll /*[B,T]*/, float* loss /*[1]*/, float* scratch /*[B]*/,
+                        void* stream);
 
 #ifdef __cplusplus
 }

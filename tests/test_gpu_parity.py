@@ -318,6 +318,25 @@ def test_reinforce_gradients(evrp, weights, mode):
                 assert np.allclose(v.cpu().numpy(), g["bn_after/" + k], rtol=1e-4, atol=1e-5), k
 
 
+def test_fused_reinforce_loss_kernel(evrp):
+    """csrc/evrp_loss.cu against trainer.py:116-121 written out in torch (value and d loss / d ll)"""
+    from evrp_b200 import train as T
+    g = torch.Generator().manual_seed(1)
+    B, Tn = 37, 53
+    ll = (-torch.rand(B, Tn, generator=g)).cuda().requires_grad_(True)
+    R = (torch.rand(B, Tn, generator=g) * 30).cuda()
+    for bl in (torch.rand(B, generator=g).cuda() * 700, torch.tensor(650.0).cuda()):
+        ll.grad = None
+        loss, reward, adv = T.ReinforceLoss.apply(ll, R, bl, 1.0 / 74)       # global batch = 2 ranks x 37
+        loss.backward()
+        ll2 = ll.detach().clone().requires_grad_(True)
+        ref = ((R.sum(1) - bl).detach() * ll2.sum(1)).sum() / 74
+        ref.backward()
+        assert torch.allclose(reward, R.sum(1), rtol=1e-6) and torch.allclose(adv, R.sum(1) - bl, rtol=1e-5, atol=1e-3)
+        assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+        assert torch.allclose(ll.grad, ll2.grad, rtol=1e-5, atol=1e-6)
+
+
 def test_reinforce_step_runs_and_learns_signal(evrp, weights):
     from evrp_b200 import train as T
     g = load("greedy_n20.npz")
