@@ -18,6 +18,7 @@
 // epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 #include "evrp_common.cuh"
 
 namespace evrp {
@@ -71,6 +72,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
 }
+// A operand taken from TMEM (lane = row, 32-bit column = k): no shared-memory read for A
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -93,7 +107,12 @@ struct __align__(8) Barriers {
   uint32_t tmem_base;
 };
 
-template <bool RESIDENT, int EPI>
+// A_TMEM: the converters write the activation planes into tensor memory (tcgen05.st) and the MMAs read A from
+// TMEM, so shared memory only carries the weight planes (halves the shared-memory traffic per MMA).
+constexpr int ACC_COLS = 2 * BN;                     // two accumulators
+constexpr int A_STAGE_COLS = 2 * BKB;                // hi | lo planes of one 32-wide K block
+
+template <bool RESIDENT, int EPI, bool A_TMEM>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
                   const float* __restrict__ A, int lda, float* __restrict__ C, int ldc, int M, int K, int n_chunks,
@@ -104,7 +123,9 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
   const int KB = K / BKB;
   unsigned char* wres = smem;
   unsigned char* ring = smem + (RESIDENT ? KB * 2 * PLANE : 0);
-  constexpr int STAGE_BYTES = RESIDENT ? 2 * PLANE : 4 * PLANE;
+  // per-stage shared memory: A planes (SS mode only) followed by W planes (streamed mode only)
+  constexpr int A_BYTES = A_TMEM ? 0 : 2 * PLANE;
+  constexpr int STAGE_BYTES = A_BYTES + (RESIDENT ? 0 : 2 * PLANE);
   Barriers* bars = reinterpret_cast<Barriers*>(ring + STAGES * STAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x % n_chunks;
@@ -119,7 +140,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {   // TMEM: 2 accumulators x 128 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&bars->tmem_base)) : "memory");
+    if (A_TMEM) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars->tmem_base)) : "memory");
+    else asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&bars->tmem_base)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -144,8 +166,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
             mbar_wait(&bars->empty[s], ((it / STAGES) & 1) ^ 1);
             unsigned char* st = ring + s * STAGE_BYTES;
             mbar_expect_tx(&bars->full[s], 2 * PLANE);
-            tma_load_2d(st + 2 * PLANE, &mapWh, &bars->full[s], kb * BKB, n0);
-            tma_load_2d(st + 3 * PLANE, &mapWl, &bars->full[s], kb * BKB, n0);
+            tma_load_2d(st + A_BYTES, &mapWh, &bars->full[s], kb * BKB, n0);
+            tma_load_2d(st + A_BYTES + PLANE, &mapWl, &bars->full[s], kb * BKB, n0);
           }
         }
       }
@@ -166,19 +188,73 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           unsigned char* st = ring + s * STAGE_BYTES;
           const uint32_t a_hi = smem_u32(st), a_lo = smem_u32(st + PLANE);
-          const uint32_t w_hi = RESIDENT ? smem_u32(wres + (kb * 2) * PLANE) : smem_u32(st + 2 * PLANE);
+          const uint32_t w_hi = RESIDENT ? smem_u32(wres + (kb * 2) * PLANE) : smem_u32(st + A_BYTES);
           const uint32_t w_lo = w_hi + PLANE;
+          const uint32_t ta_hi = tmem_base + ACC_COLS + s * A_STAGE_COLS, ta_lo = ta_hi + BKB;
 #pragma unroll
           for (int k = 0; k < BKB / 8; ++k) {            // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row
-            const uint64_t dah = umma_desc(a_hi + k * 32), dal = umma_desc(a_lo + k * 32);
             const uint64_t dwh = umma_desc(w_hi + k * 32), dwl = umma_desc(w_lo + k * 32);
-            umma_tf32(d_tmem, dah, dwh, (kb | k) ? 1u : 0u);
-            umma_tf32(d_tmem, dah, dwl, 1u);
-            umma_tf32(d_tmem, dal, dwh, 1u);
+            if (A_TMEM) {
+              umma_tf32_ts(d_tmem, ta_hi + k * 8, dwh, (kb | k) ? 1u : 0u);
+              umma_tf32_ts(d_tmem, ta_hi + k * 8, dwl, 1u);
+              umma_tf32_ts(d_tmem, ta_lo + k * 8, dwh, 1u);
+            } else {
+              const uint64_t dah = umma_desc(a_hi + k * 32), dal = umma_desc(a_lo + k * 32);
+              umma_tf32(d_tmem, dah, dwh, (kb | k) ? 1u : 0u);
+              umma_tf32(d_tmem, dah, dwl, 1u);
+              umma_tf32(d_tmem, dal, dwh, 1u);
+            }
           }
           umma_commit(&bars->empty[s]);                  // frees the stage when these MMAs retire
         }
         umma_commit(&bars->acc_full[buf]);
+      }
+    }
+  } else if (warp >= 4 && A_TMEM) {
+    // ================= A converters (TMEM): thread = row; fp32 -> (hi, lo) TF32 planes -> tcgen05.st ============
+    const int t = threadIdx.x - 128;                     // 0..127 = row of the tile = TMEM lane
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    constexpr int PF = 2;
+    const int my_tiles = (m_tiles - cta_in_chunk + ctas_per_chunk - 1) / ctas_per_chunk;
+    const uint32_t total = (uint32_t)my_tiles * KB;
+    float4 v[PF][8];
+    auto issue = [&](uint32_t j, float4 (&dst)[8]) {
+      const int tile = cta_in_chunk + (int)(j / KB) * ctas_per_chunk, kb = (int)(j % KB);
+      const int m = tile * BM + t;
+      const bool ok = (j < total) && (m < M);
+      const float4* src = reinterpret_cast<const float4*>(A + (size_t)(ok ? m : 0) * lda + kb * BKB);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[i] = ok ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+#pragma unroll
+    for (int p = 0; p < PF; ++p) issue(p, v[p]);
+    for (uint32_t it0 = 0; it0 < total; it0 += PF) {
+#pragma unroll
+      for (int p = 0; p < PF; ++p) {
+        const uint32_t it = it0 + p;
+        if (it < total) {
+          const int s = it % STAGES;
+          mbar_wait(&bars->empty[s], ((it / STAGES) & 1) ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t ta = tmem_base + lane_base + ACC_COLS + s * A_STAGE_COLS;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 x = v[p][half * 4 + i];
+              hi[4 * i + 0] = to_tf32(x.x); hi[4 * i + 1] = to_tf32(x.y); hi[4 * i + 2] = to_tf32(x.z); hi[4 * i + 3] = to_tf32(x.w);
+              lo[4 * i + 0] = to_tf32(x.x - __uint_as_float(hi[4 * i + 0])); lo[4 * i + 1] = to_tf32(x.y - __uint_as_float(hi[4 * i + 1]));
+              lo[4 * i + 2] = to_tf32(x.z - __uint_as_float(hi[4 * i + 2])); lo[4 * i + 3] = to_tf32(x.w - __uint_as_float(hi[4 * i + 3]));
+            }
+            tmem_st16(ta + half * 16, hi);
+            tmem_st16(ta + BKB + half * 16, lo);
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          mbar_arrive(&bars->full[s]);
+          issue(it + PF, v[p]);
+        }
       }
     }
   } else if (warp >= 4) {
@@ -286,7 +362,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
   }
   __syncthreads();
   if (warp == 8) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    if (A_TMEM) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -323,19 +400,34 @@ static int make_weight_map(CUtensorMap* map, const float* W, int N, int K) {
   return r == CUDA_SUCCESS ? 0 : -(int)(2000 + r);
 }
 
-template <bool RESIDENT, int EPI>
-static int launch(const CUtensorMap& mh, const CUtensorMap& ml, const float* A, int lda, float* C, int ldc, int M, int N,
+template <bool RESIDENT, int EPI, bool A_TMEM>
+static int launch_impl(const CUtensorMap& mh, const CUtensorMap& ml, const float* A, int lda, float* C, int ldc, int M, int N,
                   int K, const Epilogue& ep, int sm_count, cudaStream_t st) {
   const int n_chunks = N / BN;
   const int per_chunk = sm_count / n_chunks > 0 ? sm_count / n_chunks : 1;
   const int m_tiles = (M + BM - 1) / BM;
   const int ctas_per_chunk = per_chunk < m_tiles ? per_chunk : m_tiles;
-  const size_t smem = (RESIDENT ? (size_t)(K / BKB) * 2 * PLANE + STAGES * 2 * PLANE : (size_t)STAGES * 4 * PLANE) + sizeof(Barriers) + 1024;
-  auto kern = gemm3xtf32_kernel<RESIDENT, EPI>;
+  const size_t a_bytes = A_TMEM ? 0 : 2 * PLANE;
+  const size_t smem = (RESIDENT ? (size_t)(K / BKB) * 2 * PLANE + STAGES * a_bytes : (size_t)STAGES * (a_bytes + 2 * PLANE)) +
+                      sizeof(Barriers) + 1024;
+  auto kern = gemm3xtf32_kernel<RESIDENT, EPI, A_TMEM>;
   EVRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<n_chunks * ctas_per_chunk, NTHREADS, smem, st>>>(mh, ml, A, lda, C, ldc, M, K, n_chunks, ep);
   EVRP_LAUNCH_OK();
   return 0;
+}
+
+static bool a_in_tmem() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("EVRP_TC_A_SMEM"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v != 0;
+}
+
+template <bool RESIDENT, int EPI>
+static int launch(const CUtensorMap& mh, const CUtensorMap& ml, const float* A, int lda, float* C, int ldc, int M, int N,
+                  int K, const Epilogue& ep, int sm_count, cudaStream_t st) {
+  return a_in_tmem() ? launch_impl<RESIDENT, EPI, true>(mh, ml, A, lda, C, ldc, M, N, K, ep, sm_count, st)
+                     : launch_impl<RESIDENT, EPI, false>(mh, ml, A, lda, C, ldc, M, N, K, ep, sm_count, st);
 }
 
 }  // namespace tc
