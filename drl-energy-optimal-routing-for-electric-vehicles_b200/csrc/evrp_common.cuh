@@ -84,6 +84,15 @@ __device__ __forceinline__ float uniform01(uint64_t seed, uint64_t row, uint32_t
   return (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
 }
 
+// Packed fp32 FMA (Blackwell FFMA2, PTX fma.rn.f32x2): d.{x,y} = a.{x,y} * b.{x,y} + d.{x,y}; each lane is an
+// ordinary IEEE fp32 fused multiply-add, so results are bit-identical to two scalar fmaf calls at half the issue cost.
+__device__ __forceinline__ void ffma2(float2& d, const float2& a, const float2& b) {
+  uint64_t& dd = reinterpret_cast<uint64_t&>(d);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;"
+      : "+l"(dd) : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+}
+__device__ __forceinline__ void ffma2s(float2& d, const float2& a, float s) { ffma2(d, a, make_float2(s, s)); }
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));

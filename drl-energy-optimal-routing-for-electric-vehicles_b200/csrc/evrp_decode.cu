@@ -152,45 +152,49 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
     }
     __syncthreads();
 
-    // ---- FF_tour layer 1: h1[r][n] = relu(b1[n] + W1veh^T veh_r + W1max^T m_r); 8 rows x 8 cols per thread ----
+    // ---- FF_tour layer 1: h1[r][n] = relu(b1[n] + W1veh^T veh_r + W1max^T m_r); 8 rows x 8 cols per thread,
+    //      accumulators packed as float2 pairs and updated with FFMA2 (2 fp32 FMAs per issue slot) ----
     {
       const int cg = tid & 63, rg = tid >> 6;
       const int c0 = cg * 8, r0 = rg * 8;
-      float acc[8][8];
+      float2 acc[8][4];
       {
-        float bb[8], v0[8], v1[8], v2[8];
-        *reinterpret_cast<float4*>(&bb[0]) = ldg4(w.b1 + c0); *reinterpret_cast<float4*>(&bb[4]) = ldg4(w.b1 + c0 + 4);
-        *reinterpret_cast<float4*>(&v0[0]) = ldg4(w.w1_veh + c0); *reinterpret_cast<float4*>(&v0[4]) = ldg4(w.w1_veh + c0 + 4);
-        *reinterpret_cast<float4*>(&v1[0]) = ldg4(w.w1_veh + FF + c0); *reinterpret_cast<float4*>(&v1[4]) = ldg4(w.w1_veh + FF + c0 + 4);
-        *reinterpret_cast<float4*>(&v2[0]) = ldg4(w.w1_veh + 2 * FF + c0); *reinterpret_cast<float4*>(&v2[4]) = ldg4(w.w1_veh + 2 * FF + c0 + 4);
+        float2 bb[4], v0[4], v1[4], v2[4];
+        *reinterpret_cast<float4*>(&bb[0]) = ldg4(w.b1 + c0); *reinterpret_cast<float4*>(&bb[2]) = ldg4(w.b1 + c0 + 4);
+        *reinterpret_cast<float4*>(&v0[0]) = ldg4(w.w1_veh + c0); *reinterpret_cast<float4*>(&v0[2]) = ldg4(w.w1_veh + c0 + 4);
+        *reinterpret_cast<float4*>(&v1[0]) = ldg4(w.w1_veh + FF + c0); *reinterpret_cast<float4*>(&v1[2]) = ldg4(w.w1_veh + FF + c0 + 4);
+        *reinterpret_cast<float4*>(&v2[0]) = ldg4(w.w1_veh + 2 * FF + c0); *reinterpret_cast<float4*>(&v2[2]) = ldg4(w.w1_veh + 2 * FF + c0 + 4);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const float4 vh = *reinterpret_cast<const float4*>(&sm.veh[r0 + r][0]);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(v2[c], vh.z, fmaf(v1[c], vh.y, fmaf(v0[c], vh.x, bb[c])));
+          for (int c = 0; c < 4; ++c) {
+            acc[r][c] = bb[c];
+            ffma2s(acc[r][c], v0[c], vh.x); ffma2s(acc[r][c], v1[c], vh.y); ffma2s(acc[r][c], v2[c], vh.z);
+          }
         }
       }
       const float* wp = w.w1_max + c0;
 #pragma unroll 2
       for (int k = 0; k < D; k += 2) {
-        float wa[8], wb[8];
-        *reinterpret_cast<float4*>(&wa[0]) = ldg4(wp + (size_t)k * FF); *reinterpret_cast<float4*>(&wa[4]) = ldg4(wp + (size_t)k * FF + 4);
-        *reinterpret_cast<float4*>(&wb[0]) = ldg4(wp + (size_t)(k + 1) * FF); *reinterpret_cast<float4*>(&wb[4]) = ldg4(wp + (size_t)(k + 1) * FF + 4);
+        float2 wa[4], wb[4];
+        *reinterpret_cast<float4*>(&wa[0]) = ldg4(wp + (size_t)k * FF); *reinterpret_cast<float4*>(&wa[2]) = ldg4(wp + (size_t)k * FF + 4);
+        *reinterpret_cast<float4*>(&wb[0]) = ldg4(wp + (size_t)(k + 1) * FF); *reinterpret_cast<float4*>(&wb[2]) = ldg4(wp + (size_t)(k + 1) * FF + 4);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const float2 a = *reinterpret_cast<const float2*>(&sm.m[r0 + r][k]);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(wa[c], a.x, acc[r][c]);
+          for (int c = 0; c < 4; ++c) ffma2s(acc[r][c], wa[c], a.x);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(wb[c], a.y, acc[r][c]);
+          for (int c = 0; c < 4; ++c) ffma2s(acc[r][c], wb[c], a.y);
         }
       }
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
         *reinterpret_cast<float4*>(&sm.u.h1[r0 + r][c0]) =
-            make_float4(fmaxf(acc[r][0], 0.f), fmaxf(acc[r][1], 0.f), fmaxf(acc[r][2], 0.f), fmaxf(acc[r][3], 0.f));
+            make_float4(fmaxf(acc[r][0].x, 0.f), fmaxf(acc[r][0].y, 0.f), fmaxf(acc[r][1].x, 0.f), fmaxf(acc[r][1].y, 0.f));
         *reinterpret_cast<float4*>(&sm.u.h1[r0 + r][c0 + 4]) =
-            make_float4(fmaxf(acc[r][4], 0.f), fmaxf(acc[r][5], 0.f), fmaxf(acc[r][6], 0.f), fmaxf(acc[r][7], 0.f));
+            make_float4(fmaxf(acc[r][2].x, 0.f), fmaxf(acc[r][2].y, 0.f), fmaxf(acc[r][3].x, 0.f), fmaxf(acc[r][3].y, 0.f));
       }
     }
     __syncthreads();
@@ -198,39 +202,38 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
     {
       const int kh = tid & 1, cg = (tid >> 1) & 31, rg = tid >> 6;
       const int c0 = cg * 4, r0 = rg * 8;
-      float acc[8][4];
+      float2 acc[8][2];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+      for (int r = 0; r < 8; ++r) { acc[r][0] = make_float2(0.f, 0.f); acc[r][1] = make_float2(0.f, 0.f); }
       const float* wp = w.w2 + (size_t)kh * 256 * D + c0;
       const int kbase = kh * 256;
 #pragma unroll 1
       for (int k = 0; k < 256; k += 4) {
-        float4 ww[4];
+        float2 ww[4][2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ww[i] = ldg4(wp + (size_t)(k + i) * D);
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(&ww[i][0]) = ldg4(wp + (size_t)(k + i) * D);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const float4 hh = *reinterpret_cast<const float4*>(&sm.u.h1[r0 + r][kbase + k]);
-          acc[r][0] = fmaf(ww[0].x, hh.x, acc[r][0]); acc[r][1] = fmaf(ww[0].y, hh.x, acc[r][1]);
-          acc[r][2] = fmaf(ww[0].z, hh.x, acc[r][2]); acc[r][3] = fmaf(ww[0].w, hh.x, acc[r][3]);
-          acc[r][0] = fmaf(ww[1].x, hh.y, acc[r][0]); acc[r][1] = fmaf(ww[1].y, hh.y, acc[r][1]);
-          acc[r][2] = fmaf(ww[1].z, hh.y, acc[r][2]); acc[r][3] = fmaf(ww[1].w, hh.y, acc[r][3]);
-          acc[r][0] = fmaf(ww[2].x, hh.z, acc[r][0]); acc[r][1] = fmaf(ww[2].y, hh.z, acc[r][1]);
-          acc[r][2] = fmaf(ww[2].z, hh.z, acc[r][2]); acc[r][3] = fmaf(ww[2].w, hh.z, acc[r][3]);
-          acc[r][0] = fmaf(ww[3].x, hh.w, acc[r][0]); acc[r][1] = fmaf(ww[3].y, hh.w, acc[r][1]);
-          acc[r][2] = fmaf(ww[3].z, hh.w, acc[r][2]); acc[r][3] = fmaf(ww[3].w, hh.w, acc[r][3]);
+          ffma2s(acc[r][0], ww[0][0], hh.x); ffma2s(acc[r][1], ww[0][1], hh.x);
+          ffma2s(acc[r][0], ww[1][0], hh.y); ffma2s(acc[r][1], ww[1][1], hh.y);
+          ffma2s(acc[r][0], ww[2][0], hh.z); ffma2s(acc[r][1], ww[2][1], hh.z);
+          ffma2s(acc[r][0], ww[3][0], hh.w); ffma2s(acc[r][1], ww[3][1], hh.w);
         }
       }
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] += __shfl_xor_sync(FULL, acc[r][c], 1);   // the two K halves sit in lane pairs
+        for (int c = 0; c < 2; ++c) {                   // the two K halves sit in lane pairs
+          acc[r][c].x += __shfl_xor_sync(FULL, acc[r][c].x, 1);
+          acc[r][c].y += __shfl_xor_sync(FULL, acc[r][c].y, 1);
+        }
       }
       __syncthreads();                                   // every read of h1 is done: its storage becomes ctx + scratch
       if (kh == 0) {
 #pragma unroll
         for (int r = 0; r < 8; ++r)
-          *reinterpret_cast<float4*>(&sm.u.att.ctx[r0 + r][c0]) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+          *reinterpret_cast<float4*>(&sm.u.att.ctx[r0 + r][c0]) = make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y);
       }
     }
     __syncthreads();
