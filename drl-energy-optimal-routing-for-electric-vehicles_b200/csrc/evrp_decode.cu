@@ -67,6 +67,9 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 template <typename T>
 __device__ __forceinline__ T sel4(const T (&a)[4], int i) { return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : a[3]; }
 
+// MODE: 0 greedy, 1 sample, 2 teacher-forced (separate instantiations keep each kernel's code small: the row phase
+// is instruction-cache sensitive)
+template <int MODE>
 __global__ void __launch_bounds__(NT, 2)
 rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
                const float* __restrict__ emb, const float* __restrict__ kvl, const float* __restrict__ fixed_ctx,
@@ -391,7 +394,7 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       if (__any_sync(FULL, bad) && lane == 0) atomicOr(status, EVRP_ST_NAN_LOGIT);
       // ---- pick ----
       int sel_i = 0;
-      if (forced) {
+      if (MODE == 2) {
         const int j = (int)forced[(size_t)row * Tcap + t];
         const bool ok = (j >= 0 && j < S) && ((sel4(mk, j >> 5) >> (j & 31)) & 1u);
         if (!ok) { if (lane == 0) atomicOr(status, EVRP_ST_INFEASIBLE_PICK); sel_i = -1 - max(0, min(j, S - 1)); }
@@ -404,7 +407,7 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
           }
           sel_i = pos;
         }
-      } else if (cfg.decode_type == EVRP_DECODE_GREEDY) {
+      } else if (MODE == 0) {
         // first-index argmax of probs (torch.max(1), :327)
         float bv = pr[0]; int bi = lane;
 #pragma unroll
@@ -514,13 +517,12 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
         const bool combined = (load == 0.f) || !cust_dem;
         bool cust_ok = false;
         uint32_t nm[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int jb = 0; jb < 4; ++jb) {
-          if (jb >= nblk) break;                         // warp-uniform
+#pragma unroll 1
+        for (int jb = 0; jb < nblk; ++jb) {              // rolled: one instance of the look-ahead code (i-cache)
           const int j = jb * 32 + lane;
           bool mbit = false;
+          const float dm = sel4(dmj, jb);
           if (j < S) {
-            const float dm = dmj[jb];
             mbit = (dm != 0.f) && (dm < load);
             if (j == c_node) mbit = false;
             if (c_node <= F && j >= 1 && j <= F) mbit = false;
@@ -530,11 +532,12 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
             if (combined) mbit = (j == 0);
           }
           if (__any_sync(FULL, mbit)) {                  // look-ahead rules 5-7 only where something is still open
-            if (mbit && !reachable(phys, j, F, load, load, dmj[jb], soc, tim, dcj[jb], gcj[jb], d0j[jb], g0j[jb],
-                                   d3j[jb], s3j[jb], d4)) mbit = false;
+            if (mbit && !reachable(phys, j, F, load, load, dm, soc, tim, sel4(dcj, jb), sel4(gcj, jb), sel4(d0j, jb),
+                                   sel4(g0j, jb), sel4(d3j, jb), sel4(s3j, jb), d4)) mbit = false;
           }
           if (j > F && mbit) cust_ok = true;
-          nm[jb] = __ballot_sync(FULL, mbit);
+          const uint32_t bal = __ballot_sync(FULL, mbit);
+          if (jb == 0) nm[0] = bal; else if (jb == 1) nm[1] = bal; else if (jb == 2) nm[2] = bal; else nm[3] = bal;
         }
         cust_ok = __any_sync(FULL, cust_ok);
         if (!cust_ok) nm[0] |= 1u;                       // rule 8 (:220-221)
@@ -610,7 +613,9 @@ int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evr
   const int rows = B * cfg->n_replicas;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = sizeof(DecodeSmem);
-  EVRP_CUDA_OK(cudaFuncSetAttribute(rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int mode = forced_actions ? 2 : (cfg->decode_type == EVRP_DECODE_SAMPLE ? 1 : 0);
+  auto kern = mode == 2 ? rollout_kernel<2> : mode == 1 ? rollout_kernel<1> : rollout_kernel<0>;
+  EVRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // balance: fill whole waves of (2 CTAs x SMs) slots and spread the rows evenly over them (<= RPC rows per CTA)
   int dev = 0, sms = 148;
   EVRP_CUDA_OK(cudaGetDevice(&dev));
@@ -622,7 +627,7 @@ int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evr
   if (grid > rows) grid = rows;
   const int rows_per_cta = (rows + grid - 1) / grid;
   grid = (rows + rows_per_cta - 1) / rows_per_cta;
-  rollout_kernel<<<grid, NT, smem, st>>>(*phys, *w, *cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope,
+  kern<<<grid, NT, smem, st>>>(*phys, *w, *cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope,
                                          (float*)workspace, B, S, F, rows, rows_per_cta, forced_actions, uniforms, pi, ll, reward,
                                          energy, saved_mask, saved_veh, steps_used, t_max, status);
   EVRP_LAUNCH_OK();
