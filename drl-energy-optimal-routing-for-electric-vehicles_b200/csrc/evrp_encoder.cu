@@ -163,16 +163,17 @@ self_attention_kernel(const float* __restrict__ qkv, int S, float* __restrict__ 
   for (int i0 = 0; i0 < S; i0 += 64) {          // two query rows per lane per pass
     const int ia = i0 + lane, ib = i0 + 32 + lane;
     const bool va = ia < S, vb = ib < S;
-    float qa[DK], qb[DK], oa[DK], ob[DK];
+    // the two query rows of a lane are packed into float2 lanes so that every FMA is an FFMA2
+    float2 q2[DK], o2[DK];
 #pragma unroll
     for (int c4 = 0; c4 < DK; c4 += 4) {
       const float4 t = va ? *reinterpret_cast<const float4*>(base + (size_t)ia * 384 + h * DK + c4) : make_float4(0, 0, 0, 0);
       const float4 u = vb ? *reinterpret_cast<const float4*>(base + (size_t)ib * 384 + h * DK + c4) : make_float4(0, 0, 0, 0);
-      qa[c4] = t.x; qa[c4 + 1] = t.y; qa[c4 + 2] = t.z; qa[c4 + 3] = t.w;
-      qb[c4] = u.x; qb[c4 + 1] = u.y; qb[c4 + 2] = u.z; qb[c4 + 3] = u.w;
+      q2[c4] = make_float2(t.x, u.x); q2[c4 + 1] = make_float2(t.y, u.y);
+      q2[c4 + 2] = make_float2(t.z, u.z); q2[c4 + 3] = make_float2(t.w, u.w);
     }
 #pragma unroll
-    for (int c = 0; c < DK; ++c) { oa[c] = 0.f; ob[c] = 0.f; }
+    for (int c = 0; c < DK; ++c) o2[c] = make_float2(0.f, 0.f);
     float ma = -INFINITY, mb = -INFINITY, la = 0.f, lb = 0.f;
     for (int j = 0; j < S; ++j) {
       float kk[DK], vv[DK];
@@ -183,29 +184,32 @@ self_attention_kernel(const float* __restrict__ qkv, int S, float* __restrict__ 
         kk[c4] = t.x; kk[c4 + 1] = t.y; kk[c4 + 2] = t.z; kk[c4 + 3] = t.w;
         vv[c4] = u.x; vv[c4 + 1] = u.y; vv[c4 + 2] = u.z; vv[c4 + 3] = u.w;
       }
-      float sa = 0.f, sb = 0.f;
+      float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < DK; ++c) { sa = fmaf(qa[c], kk[c], sa); sb = fmaf(qb[c], kk[c], sb); }
-      sa *= 0.25f; sb *= 0.25f;                               // norm_factor = 1/sqrt(16), exact
+      for (int c = 0; c < DK; ++c) ffma2s(s2, q2[c], kk[c]);
+      const float sa = s2.x * 0.25f, sb = s2.y * 0.25f;       // norm_factor = 1/sqrt(16), exact
       if (sa > ma) {                                          // online softmax: rescale on a new maximum
         const float r = expf(ma - sa);                        // exp(-inf) = 0 on the first hit
         la *= r;
 #pragma unroll
-        for (int c = 0; c < DK; ++c) oa[c] *= r;
+        for (int c = 0; c < DK; ++c) o2[c].x *= r;
         ma = sa;
       }
       if (sb > mb) {
         const float r = expf(mb - sb);
         lb *= r;
 #pragma unroll
-        for (int c = 0; c < DK; ++c) ob[c] *= r;
+        for (int c = 0; c < DK; ++c) o2[c].y *= r;
         mb = sb;
       }
-      const float pa = expf(sa - ma), pb = expf(sb - mb);
-      la += pa; lb += pb;
+      const float2 p2 = make_float2(expf(sa - ma), expf(sb - mb));
+      la += p2.x; lb += p2.y;
 #pragma unroll
-      for (int c = 0; c < DK; ++c) { oa[c] = fmaf(pa, vv[c], oa[c]); ob[c] = fmaf(pb, vv[c], ob[c]); }
+      for (int c = 0; c < DK; ++c) ffma2(o2[c], p2, make_float2(vv[c], vv[c]));
     }
+    float oa[DK], ob[DK];
+#pragma unroll
+    for (int c = 0; c < DK; ++c) { oa[c] = o2[c].x; ob[c] = o2[c].y; }
     if (va) {
       const float inv = 1.f / la;
       float* o = heads + ((size_t)b * S + ia) * D + h * DK;

@@ -104,8 +104,11 @@ struct __align__(8) Barriers {
   uint64_t w_ready;           // resident weights landed
   uint64_t acc_full[2];       // accumulator ready for the epilogue (tcgen05.commit)
   uint64_t acc_empty[2];      // accumulator drained (128 epilogue arrivals)
+  uint64_t raw_full[4];       // raw fp32 activation tile landed (TMA bytes)        [A_TMEM mode]
+  uint64_t raw_empty[4];      // raw tile consumed by the 128 converter threads      [A_TMEM mode]
   uint32_t tmem_base;
 };
+constexpr int RAW_STAGES = 4;                        // raw activation staging ring (16 KB each)
 
 // A_TMEM: the converters write the activation planes into tensor memory (tcgen05.st) and the MMAs read A from
 // TMEM, so shared memory only carries the weight planes (halves the shared-memory traffic per MMA).
@@ -115,7 +118,7 @@ constexpr int A_STAGE_COLS = 2 * BKB;                // hi | lo planes of one 32
 template <bool RESIDENT, int EPI, bool A_TMEM>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
-                  const float* __restrict__ A, int lda, float* __restrict__ C, int ldc, int M, int K, int n_chunks,
+                  const __grid_constant__ CUtensorMap mapA, const float* __restrict__ A, int lda, float* __restrict__ C, int ldc, int M, int K, int n_chunks,
                   Epilogue ep) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -126,7 +129,10 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
   // per-stage shared memory: A planes (SS mode only) followed by W planes (streamed mode only)
   constexpr int A_BYTES = A_TMEM ? 0 : 2 * PLANE;
   constexpr int STAGE_BYTES = A_BYTES + (RESIDENT ? 0 : 2 * PLANE);
-  Barriers* bars = reinterpret_cast<Barriers*>(ring + STAGES * STAGE_BYTES);
+  // A_TMEM mode: raw fp32 activation tiles [128 x 32] land here by TMA (128B-swizzled), the converters read
+  // their row back conflict-free and push the TF32 planes to tensor memory
+  unsigned char* raw = ring + STAGES * STAGE_BYTES;
+  Barriers* bars = reinterpret_cast<Barriers*>(raw + (A_TMEM ? RAW_STAGES * PLANE : 0));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x % n_chunks;
   const int cta_in_chunk = blockIdx.x / n_chunks, ctas_per_chunk = gridDim.x / n_chunks;
@@ -137,6 +143,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
     for (int s = 0; s < STAGES; ++s) { mbar_init(&bars->full[s], RESIDENT ? 128 : 129); mbar_init(&bars->empty[s], 1); }
     mbar_init(&bars->w_ready, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(&bars->acc_full[b], 1); mbar_init(&bars->acc_empty[b], 128); }
+    for (int r = 0; r < RAW_STAGES; ++r) { mbar_init(&bars->raw_full[r], 1); mbar_init(&bars->raw_empty[r], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {   // TMEM: 2 accumulators x 128 columns
@@ -150,7 +157,7 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == 9) {
-    // ================= weight producer (TMA) =================
+    // ================= TMA producer: weight planes (+ raw activation tiles in A_TMEM mode) =================
     if (lane == 0) {
       if (RESIDENT) {
         mbar_expect_tx(&bars->w_ready, (uint32_t)(KB * 2 * PLANE));
@@ -158,16 +165,25 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
           tma_load_2d(wres + (kb * 2 + 0) * PLANE, &mapWh, &bars->w_ready, kb * BKB, n0);
           tma_load_2d(wres + (kb * 2 + 1) * PLANE, &mapWl, &bars->w_ready, kb * BKB, n0);
         }
-      } else {
+      }
+      if (!RESIDENT || A_TMEM) {
         uint32_t it = 0;
         for (int tile = cta_in_chunk; tile < m_tiles; tile += ctas_per_chunk) {
           for (int kb = 0; kb < KB; ++kb, ++it) {
-            const int s = it % STAGES;
-            mbar_wait(&bars->empty[s], ((it / STAGES) & 1) ^ 1);
-            unsigned char* st = ring + s * STAGE_BYTES;
-            mbar_expect_tx(&bars->full[s], 2 * PLANE);
-            tma_load_2d(st + A_BYTES, &mapWh, &bars->full[s], kb * BKB, n0);
-            tma_load_2d(st + A_BYTES + PLANE, &mapWl, &bars->full[s], kb * BKB, n0);
+            if (A_TMEM) {
+              const int rsg = it % RAW_STAGES;
+              mbar_wait(&bars->raw_empty[rsg], ((it / RAW_STAGES) & 1) ^ 1);
+              mbar_expect_tx(&bars->raw_full[rsg], PLANE);
+              tma_load_2d(raw + rsg * PLANE, &mapA, &bars->raw_full[rsg], kb * BKB, tile * BM);   // OOB rows -> 0
+            }
+            if (!RESIDENT) {
+              const int s = it % STAGES;
+              mbar_wait(&bars->empty[s], ((it / STAGES) & 1) ^ 1);
+              unsigned char* st = ring + s * STAGE_BYTES;
+              mbar_expect_tx(&bars->full[s], 2 * PLANE);
+              tma_load_2d(st + A_BYTES, &mapWh, &bars->full[s], kb * BKB, n0);
+              tma_load_2d(st + A_BYTES + PLANE, &mapWl, &bars->full[s], kb * BKB, n0);
+            }
           }
         }
       }
@@ -211,51 +227,39 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
       }
     }
   } else if (warp >= 4 && A_TMEM) {
-    // ================= A converters (TMEM): thread = row; fp32 -> (hi, lo) TF32 planes -> tcgen05.st ============
+    // ================= A converters (TMEM): thread = row; raw fp32 (smem, TMA-fed) -> (hi, lo) TF32 -> tcgen05.st ====
     const int t = threadIdx.x - 128;                     // 0..127 = row of the tile = TMEM lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    constexpr int PF = 2;
     const int my_tiles = (m_tiles - cta_in_chunk + ctas_per_chunk - 1) / ctas_per_chunk;
     const uint32_t total = (uint32_t)my_tiles * KB;
-    float4 v[PF][8];
-    auto issue = [&](uint32_t j, float4 (&dst)[8]) {
-      const int tile = cta_in_chunk + (int)(j / KB) * ctas_per_chunk, kb = (int)(j % KB);
-      const int m = tile * BM + t;
-      const bool ok = (j < total) && (m < M);
-      const float4* src = reinterpret_cast<const float4*>(A + (size_t)(ok ? m : 0) * lda + kb * BKB);
+    for (uint32_t it = 0; it < total; ++it) {
+      const int rsg = it % RAW_STAGES, s = it % STAGES;
+      mbar_wait(&bars->raw_full[rsg], (it / RAW_STAGES) & 1);
+      const unsigned char* rp = raw + rsg * PLANE + t * 128;
+      float4 x[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dst[i] = ok ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
+      for (int c = 0; c < 8; ++c) x[c] = *reinterpret_cast<const float4*>(rp + ((c ^ (t & 7)) << 4));   // TMA 128B swizzle
+      // the converted values below depend on x[], so the loads have completed before the release further down
+      mbar_wait(&bars->empty[s], ((it / STAGES) & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t ta = tmem_base + lane_base + ACC_COLS + s * A_STAGE_COLS;
 #pragma unroll
-    for (int p = 0; p < PF; ++p) issue(p, v[p]);
-    for (uint32_t it0 = 0; it0 < total; it0 += PF) {
+      for (int half = 0; half < 2; ++half) {
+        uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int p = 0; p < PF; ++p) {
-        const uint32_t it = it0 + p;
-        if (it < total) {
-          const int s = it % STAGES;
-          mbar_wait(&bars->empty[s], ((it / STAGES) & 1) ^ 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t ta = tmem_base + lane_base + ACC_COLS + s * A_STAGE_COLS;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 x = v[p][half * 4 + i];
-              hi[4 * i + 0] = to_tf32(x.x); hi[4 * i + 1] = to_tf32(x.y); hi[4 * i + 2] = to_tf32(x.z); hi[4 * i + 3] = to_tf32(x.w);
-              lo[4 * i + 0] = to_tf32(x.x - __uint_as_float(hi[4 * i + 0])); lo[4 * i + 1] = to_tf32(x.y - __uint_as_float(hi[4 * i + 1]));
-              lo[4 * i + 2] = to_tf32(x.z - __uint_as_float(hi[4 * i + 2])); lo[4 * i + 3] = to_tf32(x.w - __uint_as_float(hi[4 * i + 3]));
-            }
-            tmem_st16(ta + half * 16, hi);
-            tmem_st16(ta + BKB + half * 16, lo);
-          }
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          mbar_arrive(&bars->full[s]);
-          issue(it + PF, v[p]);
+        for (int i = 0; i < 4; ++i) {
+          const float4 v = x[half * 4 + i];
+          hi[4 * i + 0] = to_tf32(v.x); hi[4 * i + 1] = to_tf32(v.y); hi[4 * i + 2] = to_tf32(v.z); hi[4 * i + 3] = to_tf32(v.w);
+          lo[4 * i + 0] = to_tf32(v.x - __uint_as_float(hi[4 * i + 0])); lo[4 * i + 1] = to_tf32(v.y - __uint_as_float(hi[4 * i + 1]));
+          lo[4 * i + 2] = to_tf32(v.z - __uint_as_float(hi[4 * i + 2])); lo[4 * i + 3] = to_tf32(v.w - __uint_as_float(hi[4 * i + 3]));
         }
+        tmem_st16(ta + half * 16, hi);
+        tmem_st16(ta + BKB + half * 16, lo);
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(&bars->full[s]);
+      mbar_arrive(&bars->raw_empty[rsg]);                // raw tile consumed (values already pushed to TMEM)
     }
   } else if (warp >= 4) {
     // ================= A converters: fp32 -> (hi, lo) TF32 planes, swizzled K-major =================
@@ -386,12 +390,13 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// W plane [N][K] fp32, K contiguous; box = 32 (K) x 128 (N), 128-byte swizzle
-static int make_weight_map(CUtensorMap* map, const float* W, int N, int K) {
+// row-major fp32 matrix [rows][ld] (weights plane [N][K] or activations [M][lda]); box = 32 (K) x 128 (rows),
+// 128-byte swizzle; out-of-bounds rows are zero-filled (ragged last M tile)
+static int make_weight_map(CUtensorMap* map, const float* W, int N, int K, int ld = 0) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return -EVRP_E_BADARG;
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld ? ld : K) * 4};
   cuuint32_t box[2] = {BKB, BN};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)W, dims, strides, box, estr,
@@ -401,7 +406,7 @@ static int make_weight_map(CUtensorMap* map, const float* W, int N, int K) {
 }
 
 template <bool RESIDENT, int EPI, bool A_TMEM>
-static int launch_impl(const CUtensorMap& mh, const CUtensorMap& ml, const float* A, int lda, float* C, int ldc, int M, int N,
+static int launch_impl(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& ma, const float* A, int lda, float* C, int ldc, int M, int N,
                   int K, const Epilogue& ep, int sm_count, cudaStream_t st) {
   const int n_chunks = N / BN;
   const int per_chunk = sm_count / n_chunks > 0 ? sm_count / n_chunks : 1;
@@ -409,10 +414,10 @@ static int launch_impl(const CUtensorMap& mh, const CUtensorMap& ml, const float
   const int ctas_per_chunk = per_chunk < m_tiles ? per_chunk : m_tiles;
   const size_t a_bytes = A_TMEM ? 0 : 2 * PLANE;
   const size_t smem = (RESIDENT ? (size_t)(K / BKB) * 2 * PLANE + STAGES * a_bytes : (size_t)STAGES * (a_bytes + 2 * PLANE)) +
-                      sizeof(Barriers) + 1024;
+                      (A_TMEM ? (size_t)RAW_STAGES * PLANE : 0) + sizeof(Barriers) + 1024;
   auto kern = gemm3xtf32_kernel<RESIDENT, EPI, A_TMEM>;
   EVRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<n_chunks * ctas_per_chunk, NTHREADS, smem, st>>>(mh, ml, A, lda, C, ldc, M, K, n_chunks, ep);
+  kern<<<n_chunks * ctas_per_chunk, NTHREADS, smem, st>>>(mh, ml, ma, A, lda, C, ldc, M, K, n_chunks, ep);
   EVRP_LAUNCH_OK();
   return 0;
 }
@@ -424,10 +429,10 @@ static bool a_in_tmem() {
 }
 
 template <bool RESIDENT, int EPI>
-static int launch(const CUtensorMap& mh, const CUtensorMap& ml, const float* A, int lda, float* C, int ldc, int M, int N,
-                  int K, const Epilogue& ep, int sm_count, cudaStream_t st) {
-  return a_in_tmem() ? launch_impl<RESIDENT, EPI, true>(mh, ml, A, lda, C, ldc, M, N, K, ep, sm_count, st)
-                     : launch_impl<RESIDENT, EPI, false>(mh, ml, A, lda, C, ldc, M, N, K, ep, sm_count, st);
+static int launch(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& ma, const float* A, int lda, float* C,
+                  int ldc, int M, int N, int K, const Epilogue& ep, int sm_count, cudaStream_t st) {
+  return a_in_tmem() ? launch_impl<RESIDENT, EPI, true>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st)
+                     : launch_impl<RESIDENT, EPI, false>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
 }
 
 }  // namespace tc
@@ -438,19 +443,20 @@ int tc_gemm(int epi, const float* A, int lda, const float* Wh, const float* Wl, 
             cudaStream_t st) {
   using namespace tc;
   if (N % BN || (K != 128 && K != 512)) return -EVRP_E_BADARG;
-  CUtensorMap mh, ml;
+  CUtensorMap mh, ml, ma;
   int rc;
   if ((rc = make_weight_map(&mh, Wh, N, K))) return rc;
   if ((rc = make_weight_map(&ml, Wl, N, K))) return rc;
+  if ((rc = make_weight_map(&ma, A, M, K, lda))) return rc;
   Epilogue ep{bias, resid, ldr, scale, shift};
   if (K == 128) {
     switch (epi) {
-      case 0: return launch<true, 0>(mh, ml, A, lda, C, ldc, M, N, K, ep, sm_count, st);
-      case EPI_BIAS | EPI_RELU: return launch<true, EPI_BIAS | EPI_RELU>(mh, ml, A, lda, C, ldc, M, N, K, ep, sm_count, st);
-      case EPI_RESID | EPI_AFFINE: return launch<true, EPI_RESID | EPI_AFFINE>(mh, ml, A, lda, C, ldc, M, N, K, ep, sm_count, st);
+      case 0: return launch<true, 0>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
+      case EPI_BIAS | EPI_RELU: return launch<true, EPI_BIAS | EPI_RELU>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
+      case EPI_RESID | EPI_AFFINE: return launch<true, EPI_RESID | EPI_AFFINE>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
     }
   } else if (epi == (EPI_BIAS | EPI_RESID | EPI_AFFINE)) {
-    return launch<false, EPI_BIAS | EPI_RESID | EPI_AFFINE>(mh, ml, A, lda, C, ldc, M, N, K, ep, sm_count, st);
+    return launch<false, EPI_BIAS | EPI_RESID | EPI_AFFINE>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
   }
   return -EVRP_E_BADARG;
 }
