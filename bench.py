@@ -191,12 +191,13 @@ def main():
     t0 = time.perf_counter()
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record()
-    inst_steps = 0
+    inst_steps_dev = torch.zeros((), dtype=torch.int64, device=dev)
     for _ in range(a.steps):
         o = step_resident()
-        inst_steps += int(o["steps"].sum())
+        inst_steps_dev += o["steps"].sum()
     e_end.record()
     barrier()
+    inst_steps = int(inst_steps_dev)
     t1 = time.perf_counter()
     clocks = sampler.stop(t0, t1)
     ms_total = e_start.elapsed_time(e_end)

@@ -57,6 +57,8 @@ struct __align__(16) DecodeSmem {
   float dem[RPC][SP];            // demand rows
   float veh[RPC][4];             // load, soc/Start_SOC, time/t_limit          (:215-222)
   RowState rs[RPC];
+  int next_row;                  // per-step work counter: warps pull rows dynamically (balances ragged feasible sets)
+  int pad[3];
   FFUnion u;
 };
 
@@ -138,6 +140,7 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
 #pragma unroll
     for (int r = 0; r < RPW; ++r) my_done &= sm.rs[r * (NT / 32) + wid].done;
     if (__syncthreads_and(my_done)) break;
+    if (tid == 0) sm.next_row = 0;
     // vehicle scalars + trace
     if (lane < RPW) {
       const int lr = lane * (NT / 32) + wid;
@@ -245,8 +248,11 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
     WarpScratch& ws = sm.u.att.ws[wid];
     const int hd = lane >> 2, sub = lane & 3;
 #pragma unroll 1
-    for (int r = 0; r < RPW; ++r) {
-      const int lr = r * (NT / 32) + wid;
+    while (true) {
+      int lr = 0;
+      if (lane == 0) lr = atomicAdd(&sm.next_row, 1);
+      lr = __shfl_sync(FULL, lr, 0);
+      if (lr >= rows_per_cta) break;
       RowState& rs = sm.rs[lr];
       if (rs.done) continue;                             // warp-uniform
       const int row = blockIdx.x * rows_per_cta + lr;

@@ -110,6 +110,7 @@ class AttentionModel(nn.Module):
         self.project_fixed_context = nn.Linear(embedding_dim, embedding_dim, bias=False)
         self.project_out = nn.Linear(embedding_dim, embedding_dim, bias=False)
         self._pack_cache = None
+        self._enc_ws = None
         self.max_steps = 1000                     # nets/DRLModel.py:255
         self.sample_seed = 0
         self._calls = 0
@@ -184,7 +185,9 @@ class AttentionModel(nn.Module):
         kvl = torch.empty(B, S, 384, device=dev)
         fixed = torch.empty(B, 128, device=dev)
         nbytes = L.evrp_encoder_workspace_bytes(B, S)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = self._enc_ws                                   # scratch activations: reused across calls
+        if ws is None or ws.numel() < nbytes or ws.device != dev:
+            ws = self._enc_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         rc = L.evrp_encoder_forward(pk["enc_struct"], _lib.ptr(static), _lib.ptr(dynamic), B, S, self.charging_num,
                                     _lib.ptr(emb), _lib.ptr(kvl), _lib.ptr(fixed), _lib.ptr(ws), nbytes,
                                     _lib.stream_ptr())
