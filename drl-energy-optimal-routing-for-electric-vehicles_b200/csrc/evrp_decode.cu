@@ -62,6 +62,14 @@ struct __align__(16) DecodeSmem {
   FFUnion u;
 };
 
+#ifdef EVRP_PHASE_TIMING
+// debug build only (tools/phase_timing.py): cycles spent by warp 0 of every CTA in [FF1, FF2, row phase, barrier wait]
+__device__ unsigned long long g_phase_cycles[4];
+#define PT_MARK(i) do { if (tid == 0) { const long long _n = clock64(); pt_acc[i] += _n - pt_t; pt_t = _n; } } while (0)
+#else
+#define PT_MARK(i) do { } while (0)
+#endif
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
@@ -133,6 +141,10 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
   }
   __syncthreads();
   int t = 0;
+#ifdef EVRP_PHASE_TIMING
+  long long pt_acc[4] = {0, 0, 0, 0};
+  long long pt_t = clock64();
+#endif
 
   // ---------------- step loop ----------------
   while (true) {
@@ -157,6 +169,7 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       }
     }
     __syncthreads();
+    PT_MARK(3);
 
     // ---- FF_tour layer 1: h1[r][n] = relu(b1[n] + W1veh^T veh_r + W1max^T m_r); 8 rows x 8 cols per thread,
     //      accumulators packed as float2 pairs and updated with FFMA2 (2 fp32 FMAs per issue slot) ----
@@ -204,6 +217,7 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       }
     }
     __syncthreads();
+    PT_MARK(0);
     // ---- FF_tour layer 2: ctx[r][d] = W2^T h1_r (b2 added in the query); 8 rows x 4 cols x K-half per thread ----
     {
       const int kh = tid & 1, cg = (tid >> 1) & 31, rg = tid >> 6;
@@ -243,6 +257,7 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       }
     }
     __syncthreads();
+    PT_MARK(1);
 
     // ---- per-row phase: each warp walks its rows ----
     WarpScratch& ws = sm.u.att.ws[wid];
@@ -563,8 +578,12 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       }
       __syncwarp();
     }
+    PT_MARK(2);
     ++t;
   }
+#ifdef EVRP_PHASE_TIMING
+  if (tid == 0) for (int i = 0; i < 4; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)pt_acc[i]);
+#endif
 }
 
 // sample_many reduction (nets/DRLModel.py:301-311): min / argmin cost over the R replicas of each instance
@@ -639,6 +658,14 @@ int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evr
   EVRP_LAUNCH_OK();
   return 0;
 }
+
+#ifdef EVRP_PHASE_TIMING
+int evrp_debug_phase_cycles(unsigned long long* out4, int reset) {
+  if (cudaMemcpyFromSymbol(out4, evrp::g_phase_cycles, sizeof(unsigned long long) * 4) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(evrp::g_phase_cycles, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 int evrp_sample_min(const float* reward, const int64_t* pi, int B, int R, int Tcap, float* mincost, int32_t* argmin,
                     int64_t* minpi, void* stream) {

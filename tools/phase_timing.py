@@ -1,0 +1,36 @@
+"""GPU helper: cycle split of the persistent rollout kernel by phase (debug build with -DEVRP_PHASE_TIMING).
+
+  bash tools/build_timing.sh && EVRP_B200_LIB=tools/_build/libevrp_b200_timing.so python tools/phase_timing.py [N] [B]
+"""
+import ctypes as C, os, sys, types
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import evrp_b200
+from evrp_b200 import policy_math as PM
+from oracle import evrp_oracle as O
+
+N, B = int(sys.argv[1]) if len(sys.argv) > 1 else 100, int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+L = evrp_b200.lib()
+L.evrp_debug_phase_cycles.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
+W = dict(np.load("tests/golden/weights_seed0.npz"))
+a = types.SimpleNamespace(CVRP_lib_test=False, Start_SOC=80., t_limit=10., num_nodes=N, charging_num=5)
+m = evrp_b200.AttentionModel(128, 128, a, n_encode_layers=3)
+m.load_state_dict({k: torch.from_numpy(v) for k, v in W.items()}); m = m.cuda().eval(); m.set_decode_type("greedy")
+s, d, e = O.generate_instances(B, N, seed=1000)
+st, dy = torch.from_numpy(s).cuda(), torch.from_numpy(d).cuda()
+D, G = PM.pairwise_matrices(st, torch.from_numpy(e).cuda())
+with torch.no_grad():
+    emb, kvl, fixed = m.encode(st, dy)
+    for _ in range(2):
+        o = m.rollout(emb, kvl, fixed, dy, D, G)
+    torch.cuda.synchronize()
+    buf = (C.c_ulonglong * 4)()
+    L.evrp_debug_phase_cycles(buf, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); o = m.rollout(emb, kvl, fixed, dy, D, G); e1.record(); torch.cuda.synchronize()
+    L.evrp_debug_phase_cycles(buf, 0)
+v = np.array(list(buf), dtype=np.float64)
+names = ["FF1", "FF2", "row phase (warp 0 busy)", "barrier wait + veh"]
+print(f"N={N} B={B} T={o['pi'].shape[1]} kernel {e0.elapsed_time(e1):.2f} ms")
+for n, x in zip(names, v):
+    print(f"  {n:28s} {100 * x / v.sum():5.1f} %")
