@@ -612,13 +612,23 @@ sample_min_kernel(const float* __restrict__ reward, const int64_t* __restrict__ 
   for (int t = lane; t < Tcap; t += 32) minpi[(size_t)b * Tcap + t] = src[t];
 }
 
+// evrp_decode_tc.cu
+int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, const evrp_rollout_cfg* cfg, const float* emb,
+                      const float* kvl, const float* fixed_ctx, const float* dynamic0, const float* distances,
+                      const float* slope, int B, int S, int F, const int64_t* forced_actions, const float* uniforms,
+                      int64_t* pi, float* ll, float* reward, float* energy, uint32_t* saved_mask, float* saved_veh,
+                      int32_t* steps_used, int32_t* t_max, int32_t* status, float* station_ws, float* dem_ws, float* m_ws,
+                      cudaStream_t st);
+
 }  // namespace evrp
 
 extern "C" {
 
-size_t evrp_rollout_workspace_bytes(int B, int S) {
+size_t evrp_rollout_workspace_bytes(int B, int S, int n_replicas) {
   (void)S;
-  return (size_t)B * 2 * EVRP_MAX_S * sizeof(float);
+  const size_t rows = (size_t)B * (n_replicas > 0 ? n_replicas : 1);
+  // station constants [B][2][128] | demand rows [rows][128] | exact running-max rows [rows][128]
+  return ((size_t)B * 2 * EVRP_MAX_S + rows * EVRP_MAX_S + rows * EVRP_D) * sizeof(float);
 }
 
 int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evrp_rollout_cfg* cfg,
@@ -633,10 +643,18 @@ int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evr
       cfg->max_steps < 1 || cfg->n_replicas < 1 || !(cfg->temp > 0.f))
     return -EVRP_E_BADARG;
   if (S > EVRP_MAX_S) return -EVRP_E_TOO_MANY_NODES;
-  if (workspace_bytes < evrp_rollout_workspace_bytes(B, S)) return -EVRP_E_WORKSPACE;
+  if (workspace_bytes < evrp_rollout_workspace_bytes(B, S, cfg->n_replicas)) return -EVRP_E_WORKSPACE;
   if (B == 0) return 0;
   const int rows = B * cfg->n_replicas;
   cudaStream_t st = (cudaStream_t)stream;
+  if (w->ff_mode == 0) {
+    float* station_ws = (float*)workspace;
+    float* dem_ws = station_ws + (size_t)B * 2 * EVRP_MAX_S;
+    float* m_ws = dem_ws + (size_t)rows * EVRP_MAX_S;
+    return launch_rollout_tc(phys, w, cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope, B, S, F, forced_actions,
+                             uniforms, pi, ll, reward, energy, saved_mask, saved_veh, steps_used, t_max, status,
+                             station_ws, dem_ws, m_ws, st);
+  }
   const size_t smem = sizeof(DecodeSmem);
   const int mode = forced_actions ? 2 : (cfg->decode_type == EVRP_DECODE_SAMPLE ? 1 : 0);
   auto kern = mode == 2 ? rollout_kernel<2> : mode == 1 ? rollout_kernel<1> : rollout_kernel<0>;

@@ -1,0 +1,701 @@
+// Persistent rollout kernel, tensor-core variant: ONE launch decodes whole tours and the
+// per-step route-context MLP (FF_tour, nets/DRLModel.py:203-237) runs on tcgen05 tensor cores inside it.
+//
+//   AttentionModel._inner            nets/DRLModel.py:240-280   (the step loop lives inside the kernel)
+//   route_feature                    nets/DRLModel.py:203-237   (running max + FF_tour)
+//   _get_log_p / _one_to_many_logits nets/DRLModel.py:379-452   (8-head masked glimpse, pointer logits)
+//   _select_node                     nets/DRLModel.py:316-342   (greedy first-index argmax / sampling)
+//   _calc_log_likelihood             nets/DRLModel.py:182-190
+//   update_dynamic / update_mask     problems/EVRP.py:105-280   (fused, bit-exact recipe of evrp_common.cuh)
+//
+// Layout: ONE CTA per SM (576 threads) owns up to RPC = 64 rollout rows for their whole life.
+//   warps 0-15   row warps: per-row decode phase; in the FF phase they are the TMEM epilogue / operand converters
+//   warp  16     TMA producer: streams the pre-split TF32 weight planes of FF_tour from L2 (2-stage ring, 32 KB stages)
+//   warp  17     MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = 64, K = 8)
+// Per step
+//   1. FF_tour, transposed so that the ROWS are the MMA N dimension (any row count <= 64 costs N/256 of a full tile):
+//        h1^T [512 x rows] = W1max [512 x 128] . m^T      4 M-tiles, A = weight tile (smem, TMA), B = running-max planes
+//        ctx^T [128 x rows] = W2 [128 x 512] . relu(h1 + b1 + W1veh veh)^T     B = hidden planes written by the epilogue
+//      every product is the error-compensated 3xTF32 split (Ah Bh + Al Bh + Ah Bl, fp32 accumulation in TMEM), the
+//      same fp32-faithful scheme as the encoder GEMMs (evrp_tc_gemm.cu); accumulators: 4 x 64 + 64 TMEM columns.
+//   2. per row (warp): glimpse attention / logits over the FEASIBLE nodes only, warp-level masked log-softmax,
+//      first-index argmax / inverse-CDF sample, state transition + look-ahead feasibility mask (bit-exact recipe).
+//      The running max of visited embeddings is kept exact in global memory (L2-resident) and as TF32 (hi, lo)
+//      planes in the 128B-swizzled K-major layout the MMA reads.
+// Rows retire individually; the host reads back only t_max and the status word.
+#include <math.h>
+#include "evrp_tc.cuh"
+
+namespace evrp {
+namespace dtc {
+
+using namespace tc;
+
+constexpr int RPC = 64;                      // rollout rows per CTA = MMA N
+constexpr int ROW_WARPS = 16;
+constexpr int NT = (ROW_WARPS + 2) * 32;     // 576
+constexpr int SP = EVRP_MAX_S;               // padded node count (128)
+constexpr int PSTR = SP + 4;                 // head stride of the compat buffer
+constexpr int KBLK = RPC * 128;              // 8 KB: [64 rows x 32 fp32], 128B-swizzled, one plane of one K block
+constexpr int ACT_BYTES = 4 * 2 * KBLK;      // 64 KB: 4 K blocks x (hi, lo)
+constexpr int WPLANE = 128 * 128;            // 16 KB: [128 x 32 fp32] weight tile plane
+constexpr int WSTAGE = 2 * WPLANE;           // hi + lo
+constexpr int WSTAGES = 2;
+constexpr uint32_t IDESC = make_idesc_tf32(128, RPC);
+constexpr int TM_D2 = 4 * RPC;               // TMEM column of the ctx accumulator (after the 4 hidden tiles)
+
+struct RowState {
+  float load, soc, tim, d4;
+  int now, done, inst, valid;
+  uint32_t mk[4];
+};
+
+struct WarpScratch {
+  float pc[H][PSTR];             // compat -> attention probabilities, by list position
+  float logit[SP];               // clipped logits / temp, by list position
+  float heads[D];                // glimpse heads (concat)
+  unsigned char list[SP];        // feasible node indices, ascending
+};
+
+constexpr int SCRATCH_BYTES = ROW_WARPS * (int)sizeof(WarpScratch);
+constexpr int RING_BYTES = WSTAGES * WSTAGE;
+constexpr int RS_BYTES = ((SCRATCH_BYTES > RING_BYTES ? SCRATCH_BYTES : RING_BYTES) + 1023) / 1024 * 1024;
+
+struct __align__(16) Ctl {
+  RowState rs[RPC];
+  float veh[RPC][4];             // load, soc/Start_SOC, time/t_limit          (:215-222)
+  uint64_t full[WSTAGES], empty[WSTAGES];
+  uint64_t d1_full[4];           // hidden tile j accumulated (tcgen05.commit)
+  uint64_t b2_full;              // hidden tile planes written by the 512 epilogue threads
+  uint64_t b2_empty;             // GEMM2 partial over that tile retired (tcgen05.commit)
+  uint64_t d2_full;              // ctx accumulated
+  uint32_t tmem_base;
+  int next_row;
+};
+
+constexpr size_t SMEM_BYTES = 2 * (size_t)ACT_BYTES + RS_BYTES + sizeof(Ctl) + 1024;
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ T sel4(const T (&a)[4], int i) { return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : a[3]; }
+
+struct Maps { CUtensorMap w1h, w1l, w2h, w2l; };
+
+// MODE: 0 greedy, 1 sample, 2 teacher-forced
+template <int MODE>
+__global__ void __launch_bounds__(NT, 1)
+rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
+                  const float* __restrict__ emb, const float* __restrict__ kvl, const float* __restrict__ fixed_ctx,
+                  const float* __restrict__ dynamic0, const float* __restrict__ Dm, const float* __restrict__ Gm,
+                  float* station_ws, float* dem_ws, float* m_ws, int B, int S, int F, int rows_total, int rows_per_cta,
+                  const int64_t* __restrict__ forced, const float* __restrict__ uniforms,
+                  int64_t* __restrict__ pi, float* __restrict__ ll, float* __restrict__ reward,
+                  float* __restrict__ energy, uint32_t* __restrict__ saved_mask, float* __restrict__ saved_veh,
+                  int32_t* __restrict__ steps_used, int32_t* __restrict__ t_max, int32_t* __restrict__ status) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* B1 = smem;                                  // running-max planes   [kb][plane][row][128 B]
+  unsigned char* B2 = smem + ACT_BYTES;                      // hidden tile planes   [kb][plane][row][128 B]
+  float (*ctx)[D] = reinterpret_cast<float (*)[D]>(B2);      // FF_tour output (aliases B2 once GEMM2 has retired)
+  unsigned char* ring = smem + 2 * ACT_BYTES;                // weight stages (FF phase) / row scratch (row phase)
+  Ctl& sm = *reinterpret_cast<Ctl*>(smem + 2 * ACT_BYTES + RS_BYTES);
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  const int Tcap = cfg.max_steps;
+  const int nblk = (S + 31) >> 5;
+  const float sqrt_d = sqrtf((float)D);
+
+  if (tid == 0) {
+    for (int s = 0; s < WSTAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    for (int j = 0; j < 4; ++j) mbar_init(&sm.d1_full[j], 1);
+    mbar_init(&sm.b2_full, ROW_WARPS * 32);
+    mbar_init(&sm.b2_empty, 1);
+    mbar_init(&sm.d2_full, 1);
+    sm.next_row = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (wid == ROW_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+
+  // ---------------- prologue: per-row state ----------------
+  if (wid < ROW_WARPS) {
+    for (int lr = wid; lr < RPC; lr += ROW_WARPS) {
+      const int row = blockIdx.x * rows_per_cta + lr;
+      const bool valid = (lr < rows_per_cta) && (row < rows_total);
+      const int inst = valid ? row % B : 0;
+      const float* Db = Dm + (size_t)inst * S * S;
+      const float* Gb = Gm + (size_t)inst * S * S;
+      const float* dy = dynamic0 + (size_t)inst * 4 * S;
+      const float load = dy[0], soc = dy[2 * S], tim = dy[3 * S];
+      bool nonuni = false;
+      float d4 = 0.f;
+      uint32_t mk[4];
+#pragma unroll
+      for (int jb = 0; jb < 4; ++jb) {
+        const int j = jb * 32 + lane;
+        float dmv = 0.f;
+        if (j < S) {
+          dmv = dy[S + j];
+          nonuni |= (dy[j] != load) || (dy[2 * S + j] != soc) || (dy[3 * S + j] != tim);
+          int k = 0; float best = Db[(size_t)1 * S + j];       // rule-7 constants (problems/EVRP.py:196-202)
+          for (int i = 1; i < F; ++i) { const float v = Db[(size_t)(1 + i) * S + j]; if (v < best) { best = v; k = i; } }
+          if (valid) {
+            station_ws[((size_t)inst * 2 + 0) * SP + j] = (j == 0) ? 0.f : best;
+            station_ws[((size_t)inst * 2 + 1) * SP + j] = Gb[(size_t)(1 + k) * S + j];
+          }
+          if (j == 0) d4 = Db[(size_t)(1 + k) * S + 0];
+        }
+        if (valid) __stcg(dem_ws + (size_t)row * SP + j, dmv);
+        mk[jb] = __ballot_sync(FULL, j < S);                     // mask = ones (:256)
+      }
+      d4 = __shfl_sync(FULL, d4, 0);
+      if (valid && __any_sync(FULL, nonuni) && lane == 0) atomicOr(status, EVRP_ST_NONUNIFORM_DYNAMIC);
+      // zeros before the first pick (:224): exact copy and both operand planes
+      if (valid) __stcg(reinterpret_cast<float4*>(m_ws + (size_t)row * D) + lane, make_float4(0.f, 0.f, 0.f, 0.f));
+      {
+        unsigned char* p = B1 + (lane >> 3) * (2 * KBLK) + lr * 128 + ((lane & 7) << 4);
+        *reinterpret_cast<uint4*>(p) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(p + KBLK) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      if (lane == 0) {
+        RowState& rs = sm.rs[lr];
+        rs.load = load; rs.soc = soc; rs.tim = tim; rs.d4 = d4;
+        rs.now = 0; rs.done = valid ? 0 : 1; rs.inst = inst; rs.valid = valid ? 1 : 0;
+        rs.mk[0] = mk[0]; rs.mk[1] = mk[1]; rs.mk[2] = mk[2]; rs.mk[3] = mk[3];
+        const float v1 = __fdiv_rn(soc, phys.start_soc), v2 = __fdiv_rn(tim, phys.t_limit);
+        sm.veh[lr][0] = valid ? load : 0.f; sm.veh[lr][1] = valid ? v1 : 0.f; sm.veh[lr][2] = valid ? v2 : 0.f; sm.veh[lr][3] = 0.f;
+        if (valid) {
+          if (saved_veh) { float* sv = saved_veh + ((size_t)row * Tcap) * 3; sv[0] = load; sv[1] = v1; sv[2] = v2; }
+          if (saved_mask) { uint32_t* smk = saved_mask + ((size_t)row * Tcap) * 4; smk[0] = mk[0]; smk[1] = mk[1]; smk[2] = mk[2]; smk[3] = mk[3]; }
+        }
+      }
+    }
+    fence_async_smem();                                          // plane writes -> visible to tcgen05.mma
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = sm.tmem_base;
+  int t = 0;
+  uint32_t it = 0;          // weight-ring counter (producer and MMA issuer keep their own copy in step)
+  uint32_t n_bf = 0;        // b2_full phases consumed (MMA issuer)
+  uint32_t n_be = 0;        // b2_empty phases consumed (epilogue threads)
+
+  // ---------------- step loop ----------------
+  while (true) {
+    int my_done = 1;
+    if (wid < ROW_WARPS) {
+#pragma unroll
+      for (int r = 0; r < RPC / ROW_WARPS; ++r) my_done &= sm.rs[r * ROW_WARPS + wid].done;
+    }
+    if (__syncthreads_and(my_done)) break;
+
+    // =========================== FF_tour on the tensor cores ===========================
+    if (wid == ROW_WARPS) {
+      // ---- TMA producer: 16 stages of W1max (tile j, K block kb), then 16 stages of W2 (K block) ----
+      if (lane == 0) {
+        if (t == 0) sm.next_row = 0;
+        for (int i = 0; i < 32; ++i, ++it) {
+          const int s = it % WSTAGES;
+          mbar_wait(&sm.empty[s], ((it / WSTAGES) & 1) ^ 1);
+          unsigned char* st = ring + s * WSTAGE;
+          mbar_expect_tx(&sm.full[s], WSTAGE);
+          if (i < 16) {
+            tma_load_2d(st, &maps.w1h, &sm.full[s], (i & 3) * 32, (i >> 2) * 128);
+            tma_load_2d(st + WPLANE, &maps.w1l, &sm.full[s], (i & 3) * 32, (i >> 2) * 128);
+          } else {
+            tma_load_2d(st, &maps.w2h, &sm.full[s], (i - 16) * 32, 0);
+            tma_load_2d(st + WPLANE, &maps.w2l, &sm.full[s], (i - 16) * 32, 0);
+          }
+        }
+      }
+    } else if (wid == ROW_WARPS + 1) {
+      // ---- MMA issuer ----
+      if (lane == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int j = 0; j < 4; ++j) {                        // GEMM1: hidden tile j (features 128j..128j+127)
+          const uint32_t d_tmem = tmem_base + j * RPC;
+          for (int kb = 0; kb < 4; ++kb, ++it) {
+            const int s = it % WSTAGES;
+            mbar_wait(&sm.full[s], (it / WSTAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = smem_u32(ring + s * WSTAGE), a_lo = a_hi + WPLANE;
+            const uint32_t b_hi = smem_u32(B1 + kb * (2 * KBLK)), b_lo = b_hi + KBLK;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t dah = umma_desc(a_hi + k * 32), dal = umma_desc(a_lo + k * 32);
+              const uint64_t dbh = umma_desc(b_hi + k * 32), dbl = umma_desc(b_lo + k * 32);
+              umma_tf32(d_tmem, dah, dbh, (kb | k) ? 1u : 0u, IDESC);
+              umma_tf32(d_tmem, dal, dbh, 1u, IDESC);
+              umma_tf32(d_tmem, dah, dbl, 1u, IDESC);
+            }
+            umma_commit(&sm.empty[s]);
+          }
+          umma_commit(&sm.d1_full[j]);
+        }
+        const uint32_t d2 = tmem_base + TM_D2;
+        for (int j = 0; j < 4; ++j, ++n_bf) {                // GEMM2: K blocks 4j..4j+3 = hidden tile j
+          mbar_wait(&sm.b2_full, n_bf & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int kb = 0; kb < 4; ++kb, ++it) {
+            const int s = it % WSTAGES;
+            mbar_wait(&sm.full[s], (it / WSTAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = smem_u32(ring + s * WSTAGE), a_lo = a_hi + WPLANE;
+            const uint32_t b_hi = smem_u32(B2 + kb * (2 * KBLK)), b_lo = b_hi + KBLK;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t dah = umma_desc(a_hi + k * 32), dal = umma_desc(a_lo + k * 32);
+              const uint64_t dbh = umma_desc(b_hi + k * 32), dbl = umma_desc(b_lo + k * 32);
+              umma_tf32(d2, dah, dbh, (j | kb | k) ? 1u : 0u, IDESC);
+              umma_tf32(d2, dal, dbh, 1u, IDESC);
+              umma_tf32(d2, dah, dbl, 1u, IDESC);
+            }
+            umma_commit(&sm.empty[s]);
+          }
+          if (j < 3) umma_commit(&sm.b2_empty);
+        }
+        umma_commit(&sm.d2_full);
+      }
+    } else {
+      // ---- epilogue / converters: thread = (TMEM lane = feature 32q + lane, 16 rows 16cg..16cg+15) ----
+      const int q = wid & 3, cg = wid >> 2;
+      const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+      for (int j = 0; j < 4; ++j) {
+        const int f = j * 128 + q * 32 + lane;
+        const float bb = __ldg(w.b1 + f), wv0 = __ldg(w.w1_veh + f), wv1 = __ldg(w.w1_veh + FF + f), wv2 = __ldg(w.w1_veh + 2 * FF + f);
+        mbar_wait(&sm.d1_full[j], t & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t v[16];
+        tmem_ld16(tmem_base + lane_base + j * RPC + cg * 16, v);
+        if (j > 0) { mbar_wait(&sm.b2_empty, n_be & 1); ++n_be; }
+        unsigned char* pb = B2 + q * (2 * KBLK) + ((lane & 3) << 2);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int r = cg * 16 + i;
+          const float4 vh = *reinterpret_cast<const float4*>(&sm.veh[r][0]);
+          float x = fmaf(wv2, vh.z, fmaf(wv1, vh.y, fmaf(wv0, vh.x, bb))) + __uint_as_float(v[i]);
+          x = fmaxf(x, 0.f);
+          const uint32_t hi = to_tf32(x);
+          const uint32_t lo = to_tf32(x - __uint_as_float(hi));
+          unsigned char* p = pb + r * 128 + (((lane >> 2) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint32_t*>(p) = hi;
+          *reinterpret_cast<uint32_t*>(p + KBLK) = lo;
+        }
+        fence_async_smem();
+        mbar_arrive(&sm.b2_full);
+      }
+      mbar_wait(&sm.d2_full, t & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + lane_base + TM_D2 + cg * 16, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ctx[cg * 16 + i][q * 32 + lane] = __uint_as_float(v[i]);
+      }
+      if (tid == 0) sm.next_row = 0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+
+    // =========================== per-row phase: each row warp walks rows ===========================
+    if (wid < ROW_WARPS) {
+      WarpScratch& ws = reinterpret_cast<WarpScratch*>(ring)[wid];
+      const int hd = lane >> 2, sub = lane & 3;
+#pragma unroll 1
+      while (true) {
+        int lr = 0;
+        if (lane == 0) lr = atomicAdd(&sm.next_row, 1);
+        lr = __shfl_sync(FULL, lr, 0);
+        if (lr >= rows_per_cta) break;
+        RowState& rs = sm.rs[lr];
+        if (rs.done) continue;                             // warp-uniform
+        const int row = blockIdx.x * rows_per_cta + lr;
+        const int inst = rs.inst;
+        const int now = rs.now;
+        const float* Db = Dm + (size_t)inst * S * S;
+        const float* Gb = Gm + (size_t)inst * S * S;
+        const float* embb = emb + (size_t)inst * S * D;
+        const float* kvlb = kvl + (size_t)inst * S * 384;
+        uint32_t mk[4] = {rs.mk[0], rs.mk[1], rs.mk[2], rs.mk[3]};
+        // demand row and exact running max of this row (L2; written by this CTA only): issued early
+        float dmj[4];
+#pragma unroll
+        for (int jb = 0; jb < 4; ++jb) dmj[jb] = __ldcg(dem_ws + (size_t)row * SP + jb * 32 + lane);
+        float4 mm = __ldcg(reinterpret_cast<const float4*>(m_ws + (size_t)row * D) + lane);
+        // ---- feasible list (ascending node index) ----
+        int nf = 0;
+#pragma unroll
+        for (int jb = 0; jb < 4; ++jb) {
+          const uint32_t bits = mk[jb];
+          if ((bits >> lane) & 1u) ws.list[nf + __popc(bits & ((1u << lane) - 1u))] = (unsigned char)(jb * 32 + lane);
+          nf += __popc(bits);
+        }
+        __syncwarp();
+        // V and logit-K rows of this step: warm L2 while the compat pass runs
+        for (int i = lane; i < nf; i += 32) {
+          const float* p = kvlb + (size_t)ws.list[i] * 384 + 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) prefetch_l2(p + c * 32);
+        }
+        // ---- query (:394): (fixed_ctx + ctx) + emb[now] ; lane holds 4 channels of head lane/4 ----
+        float q[4];
+        {
+          const float4 fc = ldg4(fixed_ctx + (size_t)inst * D + lane * 4);
+          const float4 en = ldg4(embb + (size_t)now * D + lane * 4);
+          const float4 cx = *reinterpret_cast<const float4*>(&ctx[lr][lane * 4]);
+          const float4 b2 = ldg4(w.b2 + lane * 4);
+          q[0] = (fc.x + (cx.x + b2.x)) + en.x;
+          q[1] = (fc.y + (cx.y + b2.y)) + en.y;
+          q[2] = (fc.z + (cx.z + b2.z)) + en.z;
+          q[3] = (fc.w + (cx.w + b2.w)) + en.w;
+        }
+        // ---- compat[h][i] = q_h . K[j_i, h] / 4 ; CH rows (CH x 512 B) in flight per warp ----
+        constexpr int CH = 8;
+        for (int i0 = 0; i0 < nf; i0 += CH) {
+          float4 kv[CH];
+#pragma unroll
+          for (int a = 0; a < CH; ++a) kv[a] = ldg4(kvlb + (size_t)ws.list[min(i0 + a, nf - 1)] * 384 + lane * 4);
+#pragma unroll
+          for (int a = 0; a < CH; ++a) {
+            float p = fmaf(q[3], kv[a].w, fmaf(q[2], kv[a].z, fmaf(q[1], kv[a].y, q[0] * kv[a].x)));
+            p += __shfl_xor_sync(FULL, p, 1);
+            p += __shfl_xor_sync(FULL, p, 2);
+            if (sub == 0 && i0 + a < nf) ws.pc[hd][i0 + a] = p * 0.25f;
+          }
+        }
+        __syncwarp();
+        // ---- per-head softmax over the list; lane (hd, sub) strides i = sub, sub+4, ... ----
+        {
+          float mx = -INFINITY;
+          for (int i = sub; i < nf; i += 4) mx = fmaxf(mx, ws.pc[hd][i]);
+          mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 2));
+          float sum = 0.f;
+          for (int i = sub; i < nf; i += 4) { const float e = expf(ws.pc[hd][i] - mx); ws.pc[hd][i] = e; sum += e; }
+          sum += __shfl_xor_sync(FULL, sum, 1);
+          sum += __shfl_xor_sync(FULL, sum, 2);
+          for (int i = sub; i < nf; i += 4) ws.pc[hd][i] = __fdiv_rn(ws.pc[hd][i], sum);
+        }
+        __syncwarp();
+        // ---- heads = attn @ V ; lane owns 4 channels ----
+        {
+          float hv[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int i0 = 0; i0 < nf; i0 += CH) {
+            float4 vv[CH]; float pr[CH];
+#pragma unroll
+            for (int a = 0; a < CH; ++a) {
+              const int ii = min(i0 + a, nf - 1);
+              vv[a] = ldg4(kvlb + (size_t)ws.list[ii] * 384 + 128 + lane * 4);
+              pr[a] = (i0 + a < nf) ? ws.pc[hd][ii] : 0.f;
+            }
+#pragma unroll
+            for (int a = 0; a < CH; ++a) {
+              hv[0] = fmaf(pr[a], vv[a].x, hv[0]); hv[1] = fmaf(pr[a], vv[a].y, hv[1]);
+              hv[2] = fmaf(pr[a], vv[a].z, hv[2]); hv[3] = fmaf(pr[a], vv[a].w, hv[3]);
+            }
+          }
+          *reinterpret_cast<float4*>(&ws.heads[lane * 4]) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        }
+        __syncwarp();
+        // ---- logits[i] = heads . lK[j_i] / sqrt(128) -> tanh clip -> / temp  (project_out folded into lK).
+        //      8 lanes per node: lane (grp, s8) covers channels 4*s8 + 32*c, c = 0..3; 4 nodes per pass ----
+        {
+          const int grp = lane >> 3, s8 = lane & 7;
+          float4 hq[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) hq[c] = *reinterpret_cast<const float4*>(&ws.heads[s8 * 4 + c * 32]);
+          for (int i0 = 0; i0 < nf; i0 += 16) {            // 4 nodes per sub-pass, 4 sub-passes in flight
+            float4 lv[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int ii = min(i0 + u * 4 + grp, nf - 1);
+              const float* p = kvlb + (size_t)ws.list[ii] * 384 + 256 + s8 * 4;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) lv[u][c] = ldg4(p + c * 32);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float acc = 0.f;
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                acc = fmaf(hq[c].w, lv[u][c].w, fmaf(hq[c].z, lv[u][c].z, fmaf(hq[c].y, lv[u][c].y, fmaf(hq[c].x, lv[u][c].x, acc))));
+              acc += __shfl_xor_sync(FULL, acc, 1);
+              acc += __shfl_xor_sync(FULL, acc, 2);
+              acc += __shfl_xor_sync(FULL, acc, 4);
+              const int i = i0 + u * 4 + grp;
+              if (s8 == 0 && i < nf) {
+                float z = __fdiv_rn(acc, sqrt_d);
+                if (cfg.tanh_clipping > 0.f) z = tanhf(z) * cfg.tanh_clipping;
+                ws.logit[i] = __fdiv_rn(z, cfg.temp);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        // ---- log_softmax over the list (:403) ----
+        float zl[4];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int i = rr * 32 + lane;
+          zl[rr] = (i < nf) ? ws.logit[i] : -INFINITY;
+          mx = fmaxf(mx, zl[rr]);
+        }
+        mx = warp_max(mx);
+        float se = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) if (rr * 32 + lane < nf) se += expf(zl[rr] - mx);
+        se = warp_sum(se);
+        const float lgs = logf(se);
+        const float lse = lgs + mx;
+        float lp[4], pr[4];
+        bool bad = false;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          lp[rr] = (zl[rr] - mx) - lgs;                          // x - max - log(sum(exp(x - max)))
+          pr[rr] = (rr * 32 + lane < nf) ? expf(lp[rr]) : -1.f;  // probs = log_p.exp() (:265)
+          bad |= (rr * 32 + lane < nf) && !(lp[rr] == lp[rr]);
+        }
+        if (__any_sync(FULL, bad) && lane == 0) atomicOr(status, EVRP_ST_NAN_LOGIT);
+        // ---- pick ----
+        int sel_i = 0;
+        if (MODE == 2) {
+          const int j = (int)forced[(size_t)row * Tcap + t];
+          const bool ok = (j >= 0 && j < S) && ((sel4(mk, j >> 5) >> (j & 31)) & 1u);
+          if (!ok) { if (lane == 0) atomicOr(status, EVRP_ST_INFEASIBLE_PICK); sel_i = -1 - max(0, min(j, S - 1)); }
+          else {
+            int pos = 0;
+#pragma unroll
+            for (int jb = 0; jb < 4; ++jb) {
+              if (jb < (j >> 5)) pos += __popc(mk[jb]);
+              else if (jb == (j >> 5)) pos += __popc(mk[jb] & ((1u << (j & 31)) - 1u));
+            }
+            sel_i = pos;
+          }
+        } else if (MODE == 0) {
+          // first-index argmax of probs (torch.max(1), :327)
+          float bv = pr[0]; int bi = lane;
+#pragma unroll
+          for (int rr = 1; rr < 4; ++rr) if (pr[rr] > bv) { bv = pr[rr]; bi = rr * 32 + lane; }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(FULL, bv, o);
+            const int oi = __shfl_xor_sync(FULL, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+          }
+          sel_i = bi;
+        } else {
+          // inverse-CDF sample of probs over the list (multinomial(1), :333); lane owns positions 4*lane..4*lane+3
+          const float u = uniforms ? uniforms[(size_t)row * Tcap + t] : uniform01(cfg.seed, (uint64_t)row, (uint32_t)t);
+          float c[4]; float s = 0.f;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            const int i = lane * 4 + a;
+            const float pv = (i < nf) ? expf(ws.logit[i] - lse) : 0.f;
+            s += pv; c[a] = s;
+          }
+          float incl = s;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+          const float total = __shfl_sync(FULL, incl, 31);
+          const float excl = incl - s;
+          const float target = u * total;
+          int cand = 1 << 30;
+#pragma unroll
+          for (int a = 3; a >= 0; --a) if (lane * 4 + a < nf && excl + c[a] > target) cand = lane * 4 + a;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(FULL, cand, o));
+          sel_i = (cand < nf) ? cand : nf - 1;
+        }
+        int c_node; float lp_sel;
+        if (sel_i >= 0) {
+          c_node = ws.list[sel_i];
+          lp_sel = __shfl_sync(FULL, sel4(lp, sel_i >> 5), sel_i & 31);
+        } else { c_node = -1 - sel_i; lp_sel = -INFINITY; }
+
+        // ---- loads for the transition and the new mask, issued together ----
+        const float dist = __ldg(Db + (size_t)now * S + c_node);
+        const float slp = __ldg(Gb + (size_t)now * S + c_node);
+        const float4 ec = ldg4(embb + (size_t)c_node * D + lane * 4);
+        float dcj[4], gcj[4], d0j[4], g0j[4], d3j[4], s3j[4];
+#pragma unroll
+        for (int jb = 0; jb < 4; ++jb) {
+          const int j = jb * 32 + lane;
+          const bool in = (jb < nblk) && (j < S);
+          dcj[jb] = in ? __ldg(Db + (size_t)c_node * S + j) : 0.f;
+          gcj[jb] = in ? __ldg(Gb + (size_t)c_node * S + j) : 0.f;
+          d0j[jb] = in ? __ldg(Db + j) : 0.f;
+          g0j[jb] = in ? __ldg(Gb + j) : 0.f;
+          d3j[jb] = in ? station_ws[((size_t)inst * 2 + 0) * SP + j] : 0.f;
+          s3j[jb] = in ? station_ws[((size_t)inst * 2 + 1) * SP + j] : 0.f;
+        }
+        // ---- state transition (problems/EVRP.py:226-280) on warp-uniform scalars ----
+        float load = rs.load, soc = rs.soc, tim = rs.tim;
+        const float d4 = rs.d4;
+        const float tc = travel_time(phys, dist);
+        const float e = leg_energy(phys, vehicle_mass(phys, load), slp, tc);
+        const bool is_depot = (c_node == 0), is_station = (c_node > 0 && c_node <= F), is_cust = (c_node > F);
+        tim = __fsub_rn(tim, tc);
+        if (is_depot) tim = phys.t_limit;
+        if (is_station) tim = __fsub_rn(tim, phys.charging_time);
+        if (is_cust) tim = __fsub_rn(tim, phys.serve_time);
+        soc = __fsub_rn(soc, e);
+        if (c_node <= F) soc = phys.start_soc;
+        if (is_cust) {
+          const float dmc = __shfl_sync(FULL, sel4(dmj, c_node >> 5), c_node & 31);
+          const float nl = fmaxf(__fsub_rn(load, dmc), 0.f);
+          const float nd = fmaxf(__fsub_rn(dmc, load), 0.f);
+          if (lane == (c_node & 31)) {
+            const int jb = c_node >> 5;
+            if (jb == 0) dmj[0] = nd; else if (jb == 1) dmj[1] = nd; else if (jb == 2) dmj[2] = nd; else dmj[3] = nd;
+            __stcg(dem_ws + (size_t)row * SP + c_node, nd);
+          }
+          if (lane == 0) { dmj[0] = __fadd_rn(-1.f, nl); __stcg(dem_ws + (size_t)row * SP, dmj[0]); }
+          load = nl;
+        }
+        if (is_depot) { load = 1.f; if (lane == 0) { dmj[0] = 0.f; __stcg(dem_ws + (size_t)row * SP, 0.f); } }
+        if (lane == 0) {
+          const size_t o = (size_t)row * Tcap + t;
+          pi[o] = c_node; ll[o] = lp_sel;
+          reward[o] = phys.objective ? dist : e;
+          if (energy) energy[o] = e;
+        }
+        // ---- running max of visited embeddings (route_feature :207-214): exact copy + TF32 (hi, lo) operand planes ----
+        {
+          if (t == 0) mm = ec;
+          else { mm.x = fmaxf(mm.x, ec.x); mm.y = fmaxf(mm.y, ec.y); mm.z = fmaxf(mm.z, ec.z); mm.w = fmaxf(mm.w, ec.w); }
+          __stcg(reinterpret_cast<float4*>(m_ws + (size_t)row * D) + lane, mm);
+          uint4 hi, lo;
+          hi.x = to_tf32(mm.x); hi.y = to_tf32(mm.y); hi.z = to_tf32(mm.z); hi.w = to_tf32(mm.w);
+          lo.x = to_tf32(mm.x - __uint_as_float(hi.x)); lo.y = to_tf32(mm.y - __uint_as_float(hi.y));
+          lo.z = to_tf32(mm.z - __uint_as_float(hi.z)); lo.w = to_tf32(mm.w - __uint_as_float(hi.w));
+          unsigned char* p = B1 + (lane >> 3) * (2 * KBLK) + lr * 128 + (((lane & 7) ^ (lr & 7)) << 4);
+          *reinterpret_cast<uint4*>(p) = hi;
+          *reinterpret_cast<uint4*>(p + KBLK) = lo;
+        }
+        // ---- new mask (problems/EVRP.py:105-223) ----
+        bool any_dem = false, cust_dem = false;
+#pragma unroll
+        for (int jb = 0; jb < 4; ++jb) {
+          const int j = jb * 32 + lane;
+          any_dem |= (j < S) && (dmj[jb] != 0.f);
+          cust_dem |= (j < S) && (j >= F) && (dmj[jb] != 0.f);
+        }
+        any_dem = __any_sync(FULL, any_dem);
+        cust_dem = __any_sync(FULL, cust_dem);
+        bool done = false;
+        if (!any_dem) {
+          done = true;                                     // this row's tour is complete (:127)
+        } else {
+          const bool combined = (load == 0.f) || !cust_dem;
+          bool cust_ok = false;
+          uint32_t nm[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+          for (int jb = 0; jb < nblk; ++jb) {              // rolled: one instance of the look-ahead code (i-cache)
+            const int j = jb * 32 + lane;
+            bool mbit = false;
+            const float dm = sel4(dmj, jb);
+            if (j < S) {
+              mbit = (dm != 0.f) && (dm < load);
+              if (j == c_node) mbit = false;
+              if (c_node <= F && j >= 1 && j <= F) mbit = false;
+              if (is_station && j == 0) mbit = true;
+              if (is_cust && j <= F) mbit = true;
+              if (is_depot && j == 0) mbit = false;
+              if (combined) mbit = (j == 0);
+            }
+            if (__any_sync(FULL, mbit)) {                  // look-ahead rules 5-7 only where something is still open
+              if (mbit && !reachable(phys, j, F, load, load, dm, soc, tim, sel4(dcj, jb), sel4(gcj, jb), sel4(d0j, jb),
+                                     sel4(g0j, jb), sel4(d3j, jb), sel4(s3j, jb), d4)) mbit = false;
+            }
+            if (j > F && mbit) cust_ok = true;
+            const uint32_t bal = __ballot_sync(FULL, mbit);
+            if (jb == 0) nm[0] = bal; else if (jb == 1) nm[1] = bal; else if (jb == 2) nm[2] = bal; else nm[3] = bal;
+          }
+          cust_ok = __any_sync(FULL, cust_ok);
+          if (!cust_ok) nm[0] |= 1u;                       // rule 8 (:220-221)
+          mk[0] = nm[0]; mk[1] = nm[1]; mk[2] = nm[2]; mk[3] = nm[3];
+          if ((mk[0] | mk[1] | mk[2] | mk[3]) == 0u) {
+            if (lane == 0) atomicOr(status, EVRP_ST_NO_FEASIBLE);
+            done = true;
+          } else if (t + 1 >= Tcap) {
+            if (lane == 0) atomicOr(status, EVRP_ST_STEP_CAP);
+            done = true;
+          }
+        }
+        if (lane == 0) {
+          rs.load = load; rs.soc = soc; rs.tim = tim; rs.now = c_node;
+          rs.mk[0] = mk[0]; rs.mk[1] = mk[1]; rs.mk[2] = mk[2]; rs.mk[3] = mk[3];
+          if (done) { rs.done = 1; steps_used[row] = t + 1; atomicMax(t_max, t + 1); }
+          else {
+            // vehicle scalars of the next step (:215-222) + trace
+            const float v1 = __fdiv_rn(soc, phys.start_soc), v2 = __fdiv_rn(tim, phys.t_limit);
+            sm.veh[lr][0] = load; sm.veh[lr][1] = v1; sm.veh[lr][2] = v2;
+            const size_t o = (size_t)row * Tcap + t + 1;
+            if (saved_veh) { float* sv = saved_veh + o * 3; sv[0] = load; sv[1] = v1; sv[2] = v2; }
+            if (saved_mask) { uint32_t* smk = saved_mask + o * 4; smk[0] = mk[0]; smk[1] = mk[1]; smk[2] = mk[2]; smk[3] = mk[3]; }
+          }
+        }
+        __syncwarp();
+      }
+      fence_async_smem();          // B1 plane writes (and the scratch the next TMA overwrites) -> async proxy
+    }
+    ++t;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (wid == ROW_WARPS + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+}  // namespace dtc
+
+// host launcher (called from evrp_rollout in evrp_decode.cu when the decoder weights carry ff_mode == 0)
+int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, const evrp_rollout_cfg* cfg, const float* emb,
+                      const float* kvl, const float* fixed_ctx, const float* dynamic0, const float* distances,
+                      const float* slope, int B, int S, int F, const int64_t* forced_actions, const float* uniforms,
+                      int64_t* pi, float* ll, float* reward, float* energy, uint32_t* saved_mask, float* saved_veh,
+                      int32_t* steps_used, int32_t* t_max, int32_t* status, float* station_ws, float* dem_ws, float* m_ws,
+                      cudaStream_t st) {
+  using namespace dtc;
+  if (!w->w1max_hi || !w->w1max_lo || !w->w2_hi || !w->w2_lo) return -EVRP_E_BADARG;
+  Maps maps;
+  int rc;
+  if ((rc = tc::make_weight_map(&maps.w1h, w->w1max_hi, FF, D, 0, 128))) return rc;
+  if ((rc = tc::make_weight_map(&maps.w1l, w->w1max_lo, FF, D, 0, 128))) return rc;
+  if ((rc = tc::make_weight_map(&maps.w2h, w->w2_hi, D, FF, 0, 128))) return rc;
+  if ((rc = tc::make_weight_map(&maps.w2l, w->w2_lo, D, FF, 0, 128))) return rc;
+  const int rows = B * cfg->n_replicas;
+  const int mode = forced_actions ? 2 : (cfg->decode_type == EVRP_DECODE_SAMPLE ? 1 : 0);
+  auto kern = mode == 2 ? rollout_tc_kernel<2> : mode == 1 ? rollout_tc_kernel<1> : rollout_tc_kernel<0>;
+  EVRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  int dev = 0, sms = 148;
+  EVRP_CUDA_OK(cudaGetDevice(&dev));
+  EVRP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // balance: whole waves of one CTA per SM, rows spread evenly (<= RPC rows per CTA)
+  const int min_ctas = (rows + RPC - 1) / RPC;
+  const int waves = (min_ctas + sms - 1) / sms;
+  int grid = waves * sms;
+  if (grid > rows) grid = rows;
+  const int rows_per_cta = (rows + grid - 1) / grid;
+  grid = (rows + rows_per_cta - 1) / rows_per_cta;
+  kern<<<grid, NT, SMEM_BYTES, st>>>(maps, *phys, *w, *cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope, station_ws,
+                                     dem_ws, m_ws, B, S, F, rows, rows_per_cta, forced_actions, uniforms, pi, ll, reward,
+                                     energy, saved_mask, saved_veh, steps_used, t_max, status);
+  EVRP_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace evrp

@@ -19,7 +19,7 @@
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
-#include "evrp_common.cuh"
+#include "evrp_tc.cuh"
 
 namespace evrp {
 namespace tc {
@@ -30,69 +30,7 @@ constexpr int PLANE = BM * BKB * 4;                  // 16 KB: one [128 x 32] fp
 constexpr int NTHREADS = 320;
 constexpr int EPI_BIAS = 1, EPI_RELU = 2, EPI_RESID = 4, EPI_AFFINE = 8;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  const uint32_t addr = smem_u32(bar);
-  while (!ok) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-  }
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14),
-// LBO=1 [16,30), SBO = 1024 B >> 4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2,
-// A,B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
-}
-// A operand taken from TMEM (lane = row, 32-bit column = k): no shared-memory read for A
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(IDESC), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+constexpr uint32_t IDESC = make_idesc_tf32(128, 128);
 
 struct Epilogue {
   const float* bias; const float* resid; int ldr; const float* scale; const float* shift;
@@ -211,14 +149,14 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
           for (int k = 0; k < BKB / 8; ++k) {            // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row
             const uint64_t dwh = umma_desc(w_hi + k * 32), dwl = umma_desc(w_lo + k * 32);
             if (A_TMEM) {
-              umma_tf32_ts(d_tmem, ta_hi + k * 8, dwh, (kb | k) ? 1u : 0u);
-              umma_tf32_ts(d_tmem, ta_hi + k * 8, dwl, 1u);
-              umma_tf32_ts(d_tmem, ta_lo + k * 8, dwh, 1u);
+              umma_tf32_ts(d_tmem, ta_hi + k * 8, dwh, (kb | k) ? 1u : 0u, IDESC);
+              umma_tf32_ts(d_tmem, ta_hi + k * 8, dwl, 1u, IDESC);
+              umma_tf32_ts(d_tmem, ta_lo + k * 8, dwh, 1u, IDESC);
             } else {
               const uint64_t dah = umma_desc(a_hi + k * 32), dal = umma_desc(a_lo + k * 32);
-              umma_tf32(d_tmem, dah, dwh, (kb | k) ? 1u : 0u);
-              umma_tf32(d_tmem, dah, dwl, 1u);
-              umma_tf32(d_tmem, dal, dwh, 1u);
+              umma_tf32(d_tmem, dah, dwh, (kb | k) ? 1u : 0u, IDESC);
+              umma_tf32(d_tmem, dah, dwl, 1u, IDESC);
+              umma_tf32(d_tmem, dal, dwh, 1u, IDESC);
             }
           }
           umma_commit(&bars->empty[s]);                  // frees the stage when these MMAs retire
@@ -390,14 +328,14 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// row-major fp32 matrix [rows][ld] (weights plane [N][K] or activations [M][lda]); box = 32 (K) x 128 (rows),
+// row-major fp32 matrix [rows][ld] (weights plane [N][K] or activations [M][lda]); box = 32 (K) x box_rows,
 // 128-byte swizzle; out-of-bounds rows are zero-filled (ragged last M tile)
-static int make_weight_map(CUtensorMap* map, const float* W, int N, int K, int ld = 0) {
+int make_weight_map(CUtensorMap* map, const float* W, int N, int K, int ld, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return -EVRP_E_BADARG;
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
   cuuint64_t strides[1] = {(cuuint64_t)(ld ? ld : K) * 4};
-  cuuint32_t box[2] = {BKB, BN};
+  cuuint32_t box[2] = {BKB, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)W, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -445,9 +383,9 @@ int tc_gemm(int epi, const float* A, int lda, const float* Wh, const float* Wl, 
   if (N % BN || (K != 128 && K != 512)) return -EVRP_E_BADARG;
   CUtensorMap mh, ml, ma;
   int rc;
-  if ((rc = make_weight_map(&mh, Wh, N, K))) return rc;
-  if ((rc = make_weight_map(&ml, Wl, N, K))) return rc;
-  if ((rc = make_weight_map(&ma, A, M, K, lda))) return rc;
+  if ((rc = make_weight_map(&mh, Wh, N, K, 0, BN))) return rc;
+  if ((rc = make_weight_map(&ml, Wl, N, K, 0, BN))) return rc;
+  if ((rc = make_weight_map(&ma, A, M, K, lda, BN))) return rc;
   Epilogue ep{bias, resid, ldr, scale, shift};
   if (K == 128) {
     switch (epi) {

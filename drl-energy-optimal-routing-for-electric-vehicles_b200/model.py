@@ -116,6 +116,7 @@ class AttentionModel(nn.Module):
         self._calls = 0
         self.last_energy = None                   # [B,T] energy of the last rollout (DM trainer's 3rd output)
         self.gemm_mode = 0                        # encoder GEMMs: 0 = tcgen05 3xTF32 (fp32-faithful), 1 = fp32 FFMA
+        self.ff_mode = 0                          # FF_tour inside the rollout kernel: 0 = tcgen05 3xTF32, 1 = fp32 FFMA
         self.profile_events = None                # list -> (start, end) CUDA events around each rollout kernel launch
 
     # ------------------------------------------------------------------------------------------
@@ -150,7 +151,7 @@ class AttentionModel(nn.Module):
         """Kernel-side weight layouts (k-major transposes, folded BatchNorm / project_out / tour), rebuilt only
         when a parameter or buffer changed (tensor version counters)."""
         sd = list(self.parameters()) + list(self.buffers())
-        key = (tuple(t._version for t in sd), tuple(t.data_ptr() for t in sd), self.training, self.gemm_mode)
+        key = (tuple(t._version for t in sd), tuple(t.data_ptr() for t in sd), self.training, self.gemm_mode, self.ff_mode)
         if self._pack_cache is None or self._pack_cache[0] != key:
             with torch.no_grad():
                 self._pack_cache = (key, policy_math.pack_weights(self))
@@ -211,7 +212,7 @@ class AttentionModel(nn.Module):
             tcap = forced.shape[1]
         else:
             tcap = int(max_steps or min(self.max_steps, 8 * S))
-        wsp = torch.empty(L.evrp_rollout_workspace_bytes(B, S), dtype=torch.uint8, device=dev)
+        wsp = torch.empty(L.evrp_rollout_workspace_bytes(B, S, n_replicas), dtype=torch.uint8, device=dev)
         while True:
             cfg = _lib.RolloutCfg(_lib.DECODE_SAMPLE if decode_type == "sample" else _lib.DECODE_GREEDY,
                                   float(self.temp), float(self.tanh_clipping), tcap,

@@ -99,6 +99,11 @@ def pack_weights(model):
     dw.b1 = dev("b1", model.FF_tour[0].bias)
     dw.w2 = dev("w2", model.FF_tour[2].weight.t())
     dw.b2 = dev("b2", model.FF_tour[2].bias)
+    hi, lo = split_tf32(model.FF_tour[0].weight[:, 128:])
+    dw.w1max_hi, dw.w1max_lo = dev("w1max_hi", hi), dev("w1max_lo", lo)
+    hi, lo = split_tf32(model.FF_tour[2].weight)
+    dw.w2_hi, dw.w2_lo = dev("w2_hi", hi), dev("w2_lo", lo)
+    dw.ff_mode = int(getattr(model, "ff_mode", 0))
     keep["enc_struct"], keep["dec_struct"] = ew, dw
     return keep
 

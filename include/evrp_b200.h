@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 6
+#define EVRP_ABI_VERSION 7
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -148,6 +148,12 @@ typedef struct {
   const float *b1;       /* [512]      FF_tour.0.bias                                                   */
   const float *w2;       /* [512,128]  FF_tour.2.weight^T                                               */
   const float *b2;       /* [128]      FF_tour.2.bias                                                   */
+  /* tcgen05 path (ff_mode 0): the two FF_tour matrices in nn.Linear layout [out][in], split into TF32 planes
+     (round-to-nearest, w = hi + lo; evrp_b200/policy_math.py::split_tf32), streamed by TMA every decode step   */
+  const float *w1max_hi, *w1max_lo;   /* [512,128]  FF_tour.0.weight[:, 128:]                                   */
+  const float *w2_hi, *w2_lo;         /* [128,512]  FF_tour.2.weight                                            */
+  int32_t ff_mode;       /* 0: FF_tour on tcgen05 tensor cores, 3xTF32 (fp32-faithful), one 576-thread CTA per SM;
+                            1: fp32 FFMA inside a 256-thread CTA (2 per SM)                                     */
 } evrp_decoder_weights;
 
 #define EVRP_DECODE_GREEDY 0
@@ -172,9 +178,10 @@ int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evr
                  float* energy /*[B*R,Tcap] or NULL*/,
                  uint32_t* saved_mask /*[B*R,Tcap,4] or NULL*/, float* saved_veh /*[B*R,Tcap,3] or NULL*/,
                  int32_t* steps_used /*[B*R]*/, int32_t* t_max /*[1] atomicMax*/, int32_t* status /*[1]*/,
-                 void* workspace /* evrp_rollout_workspace_bytes(B,S): rule-7 station constants per instance */,
+                 void* workspace /* evrp_rollout_workspace_bytes(B,S,R): rule-7 station constants per instance,
+                                    demand row and exact running-max row per rollout row (L2-resident state) */,
                  size_t workspace_bytes, void* stream);
-size_t evrp_rollout_workspace_bytes(int B, int S);
+size_t evrp_rollout_workspace_bytes(int B, int S, int n_replicas);
 
 /* sample_many reduction (nets/DRLModel.py:301-311): per instance min cost over replicas + its tour. */
 int evrp_sample_min(const float* reward /*[B*R,Tcap]*/, const int64_t* pi, int B, int R, int Tcap,
