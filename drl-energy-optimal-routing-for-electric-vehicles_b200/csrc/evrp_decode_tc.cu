@@ -75,6 +75,14 @@ struct __align__(16) Ctl {
 
 constexpr size_t SMEM_BYTES = 2 * (size_t)ACT_BYTES + RS_BYTES + sizeof(Ctl) + 1024;
 
+#ifdef EVRP_PHASE_TIMING
+// debug build only (tools/phase_timing.py): cycles of warp 0 in [FF hidden tiles, FF ctx + sync, row phase busy, barrier wait]
+__device__ unsigned long long g_phase_cycles_tc[4];
+#define PT_MARK(i) do { if (tid == 0) { const long long _n = clock64(); pt_acc[i] += _n - pt_t; pt_t = _n; } } while (0)
+#else
+#define PT_MARK(i) do { } while (0)
+#endif
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -192,6 +200,10 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
   uint32_t it = 0;          // weight-ring counter (producer and MMA issuer keep their own copy in step)
   uint32_t n_bf = 0;        // b2_full phases consumed (MMA issuer)
   uint32_t n_be = 0;        // b2_empty phases consumed (epilogue threads)
+#ifdef EVRP_PHASE_TIMING
+  long long pt_acc[4] = {0, 0, 0, 0};
+  long long pt_t = clock64();
+#endif
 
   // ---------------- step loop ----------------
   while (true) {
@@ -201,6 +213,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
       for (int r = 0; r < RPC / ROW_WARPS; ++r) my_done &= sm.rs[r * ROW_WARPS + wid].done;
     }
     if (__syncthreads_and(my_done)) break;
+    PT_MARK(3);
 
     // =========================== FF_tour on the tensor cores ===========================
     if (wid == ROW_WARPS) {
@@ -297,6 +310,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         fence_async_smem();
         mbar_arrive(&sm.b2_full);
       }
+      PT_MARK(0);
       mbar_wait(&sm.d2_full, t & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       {
@@ -309,6 +323,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    PT_MARK(1);
 
     // =========================== per-row phase: each row warp walks rows ===========================
     if (wid < ROW_WARPS) {
@@ -651,16 +666,28 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         }
         __syncwarp();
       }
+      PT_MARK(2);
       fence_async_smem();          // B1 plane writes (and the scratch the next TMA overwrites) -> async proxy
     }
     ++t;
   }
+#ifdef EVRP_PHASE_TIMING
+  if (tid == 0) for (int i = 0; i < 4; ++i) atomicAdd(&g_phase_cycles_tc[i], (unsigned long long)pt_acc[i]);
+#endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (wid == ROW_WARPS + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
 }  // namespace dtc
+
+#ifdef EVRP_PHASE_TIMING
+int debug_phase_cycles_tc(unsigned long long* out4, int reset) {
+  if (cudaMemcpyFromSymbol(out4, dtc::g_phase_cycles_tc, sizeof(unsigned long long) * 4) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(dtc::g_phase_cycles_tc, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 // host launcher (called from evrp_rollout in evrp_decode.cu when the decoder weights carry ff_mode == 0)
 int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, const evrp_rollout_cfg* cfg, const float* emb,

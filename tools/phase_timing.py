@@ -11,11 +11,13 @@ from oracle import evrp_oracle as O
 
 N, B = int(sys.argv[1]) if len(sys.argv) > 1 else 100, int(sys.argv[2]) if len(sys.argv) > 2 else 8192
 L = evrp_b200.lib()
-L.evrp_debug_phase_cycles.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
+FFM = int(os.environ.get("FF_MODE", "0"))
+dbg = L.evrp_debug_phase_cycles if FFM else L.evrp_debug_phase_cycles_tc
+dbg.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
 W = dict(np.load("tests/golden/weights_seed0.npz"))
 a = types.SimpleNamespace(CVRP_lib_test=False, Start_SOC=80., t_limit=10., num_nodes=N, charging_num=5)
 m = evrp_b200.AttentionModel(128, 128, a, n_encode_layers=3)
-m.load_state_dict({k: torch.from_numpy(v) for k, v in W.items()}); m = m.cuda().eval(); m.set_decode_type("greedy")
+m.load_state_dict({k: torch.from_numpy(v) for k, v in W.items()}); m = m.cuda().eval(); m.set_decode_type("greedy"); m.ff_mode = FFM
 s, d, e = O.generate_instances(B, N, seed=1000)
 st, dy = torch.from_numpy(s).cuda(), torch.from_numpy(d).cuda()
 D, G = PM.pairwise_matrices(st, torch.from_numpy(e).cuda())
@@ -25,12 +27,12 @@ with torch.no_grad():
         o = m.rollout(emb, kvl, fixed, dy, D, G)
     torch.cuda.synchronize()
     buf = (C.c_ulonglong * 4)()
-    L.evrp_debug_phase_cycles(buf, 1)
+    dbg(buf, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); o = m.rollout(emb, kvl, fixed, dy, D, G); e1.record(); torch.cuda.synchronize()
-    L.evrp_debug_phase_cycles(buf, 0)
+    dbg(buf, 0)
 v = np.array(list(buf), dtype=np.float64)
-names = ["FF1", "FF2", "row phase (warp 0 busy)", "barrier wait + veh"]
+names = ["FF1", "FF2", "row phase (warp 0 busy)", "barrier wait + veh"] if FFM else ["FF: hidden tiles (wait + convert)", "FF: ctx wait + store + sync", "row phase (warp 0 busy)", "barrier wait (other warps' rows)"]
 print(f"N={N} B={B} T={o['pi'].shape[1]} kernel {e0.elapsed_time(e1):.2f} ms")
 for n, x in zip(names, v):
     print(f"  {n:28s} {100 * x / v.sum():5.1f} %")
