@@ -24,6 +24,7 @@
 //      planes in the 128B-swizzled K-major layout the MMA reads.
 // Rows retire individually; the host reads back only t_max and the status word.
 #include <math.h>
+#include <stdlib.h>
 #include "evrp_tc.cuh"
 
 namespace evrp {
@@ -107,7 +108,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
                   const float* __restrict__ emb, const float* __restrict__ kvl, const float* __restrict__ fixed_ctx,
                   const float* __restrict__ dynamic0, const float* __restrict__ Dm, const float* __restrict__ Gm,
                   float* station_ws, float* dem_ws, float* m_ws, int B, int S, int F, int rows_total, int rows_per_cta,
-                  const int64_t* __restrict__ forced, const float* __restrict__ uniforms,
+                  int pf_lines, const int64_t* __restrict__ forced, const float* __restrict__ uniforms,
                   int64_t* __restrict__ pi, float* __restrict__ ll, float* __restrict__ reward,
                   float* __restrict__ energy, uint32_t* __restrict__ saved_mask, float* __restrict__ saved_veh,
                   int32_t* __restrict__ steps_used, int32_t* __restrict__ t_max, int32_t* __restrict__ status) {
@@ -359,11 +360,16 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           nf += __popc(bits);
         }
         __syncwarp();
-        // V and logit-K rows of this step: warm L2 while the compat pass runs
-        for (int i = lane; i < nf; i += 32) {
-          const float* p = kvlb + (size_t)ws.list[i] * 384 + 128;
+        // Just-in-time L2 prefetch (fire-and-forget, no registers): every pass requests ALL of its records one pass
+        // ahead of the demand loads - K here, V when the softmax starts, logit-K when the V pass starts - so the 8-deep
+        // demand batches find their lines in L2.  Requesting everything up front, or the next row's records, measured
+        // slower (the requests queue ahead of the critical demand loads): profiles/r1_prefetch_sweep.md.
+        if (pf_lines & 1) {
+          for (int i = lane; i < nf; i += 32) {
+            const float* p = kvlb + (size_t)ws.list[i] * 384;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) prefetch_l2(p + c * 32);
+            for (int c = 0; c < 4; ++c) prefetch_l2(p + c * 32);
+          }
         }
         // ---- query (:394): (fixed_ctx + ctx) + emb[now] ; lane holds 4 channels of head lane/4 ----
         float q[4];
@@ -394,6 +400,13 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         __syncwarp();
         // ---- per-head softmax over the list; lane (hd, sub) strides i = sub, sub+4, ... ----
         {
+          if (pf_lines & 4) {
+            for (int i = lane; i < nf; i += 32) {
+              const float* p = kvlb + (size_t)ws.list[i] * 384 + 128;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) prefetch_l2(p + c * 32);
+            }
+          }
           float mx = -INFINITY;
           for (int i = sub; i < nf; i += 4) mx = fmaxf(mx, ws.pc[hd][i]);
           mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 1));
@@ -407,6 +420,13 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         __syncwarp();
         // ---- heads = attn @ V ; lane owns 4 channels ----
         {
+          if (pf_lines & 8) {
+            for (int i = lane; i < nf; i += 32) {
+              const float* p = kvlb + (size_t)ws.list[i] * 384 + 256;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) prefetch_l2(p + c * 32);
+            }
+          }
           float hv[4] = {0.f, 0.f, 0.f, 0.f};
           for (int i0 = 0; i0 < nf; i0 += CH) {
             float4 vv[CH]; float pr[CH];
@@ -718,8 +738,10 @@ int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, cons
   if (grid > rows) grid = rows;
   const int rows_per_cta = (rows + grid - 1) / grid;
   grid = (rows + rows_per_cta - 1) / rows_per_cta;
+  static int pf_lines = -1;              // tuning knob: bit 0 K, bit 2 V, bit 3 logit-K just-in-time prefetch
+  if (pf_lines < 0) { const char* l = getenv("EVRP_PF_LINES"); pf_lines = l ? atoi(l) : 13; }
   kern<<<grid, NT, SMEM_BYTES, st>>>(maps, *phys, *w, *cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope, station_ws,
-                                     dem_ws, m_ws, B, S, F, rows, rows_per_cta, forced_actions, uniforms, pi, ll, reward,
+                                     dem_ws, m_ws, B, S, F, rows, rows_per_cta, pf_lines, forced_actions, uniforms, pi, ll, reward,
                                      energy, saved_mask, saved_veh, steps_used, t_max, status);
   EVRP_LAUNCH_OK();
   return 0;
