@@ -73,7 +73,7 @@ class ClockSampler:
         self.rows, self.p = [], None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -181,12 +181,11 @@ def main():
             pi, ll, R = model((st_h, dy_h, D, G))
             return R.sum(1).cpu(), pi.cpu()
 
+    sampler = ClockSampler(local)                     # nvidia-smi takes a moment to start: launched before the warm-up
     for _ in range(max(a.warmup, 3)):
         o = step_resident()
     # ---------------- device-resident timing ----------------
     model.profile_events = []
-    enc_ev = []
-    sampler = ClockSampler(local)
     barrier()
     t0 = time.perf_counter()
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -273,9 +272,10 @@ def main():
                         "d2h_bytes_per_step": d2h},
                 "gpu_launches": a.steps * (1 + 5 * 3 + 2 + 1),
                 "clocks": clocks,
-                "roofline": {"bound": "hbm", "kernel": "evrp::rollout_kernel", "achieved": achieved,
+                "roofline": {"bound": "hbm", "kernel": "evrp::dtc::rollout_tc_kernel", "achieved": achieved,
                              "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s",
                              "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
+                             "dram_achieved": (traffic / (roll_avg_ms * 1e-3) / 1e9) if traffic else None,
                              "kernel_ms": roll_avg_ms, "kernel_share_of_step": roll_avg_ms / (ms_total / a.steps),
                              "algorithmic_bytes_per_launch": alg_bytes_per_launch}}
         if train is not None:

@@ -36,3 +36,13 @@ names = ["FF1", "FF2", "row phase (warp 0 busy)", "barrier wait + veh"] if FFM e
 print(f"N={N} B={B} T={o['pi'].shape[1]} kernel {e0.elapsed_time(e1):.2f} ms")
 for n, x in zip(names, v):
     print(f"  {n:28s} {100 * x / v.sum():5.1f} %")
+if not FFM:
+    rb = (C.c_ulonglong * 8)()
+    L.evrp_debug_row_cycles_tc.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
+    L.evrp_debug_row_cycles_tc(rb, 0)
+    r = np.array(list(rb), dtype=np.float64)
+    rn = ["list + K prefetch + query", "compat pass (K)", "softmax (+V prefetch)", "heads pass (V, + logit-K prefetch)",
+          "logits pass (logit-K)", "log-softmax + pick", "transition loads + state + running max", "look-ahead mask + bookkeeping"]
+    print("  row phase of warp 0 by pass:")
+    for n, x in zip(rn, r):
+        print(f"    {n:40s} {100 * x / r.sum():5.1f} %")
