@@ -79,9 +79,12 @@ constexpr size_t SMEM_BYTES = 2 * (size_t)ACT_BYTES + RS_BYTES + sizeof(Ctl) + 1
 #ifdef EVRP_PHASE_TIMING
 // debug build only (tools/phase_timing.py): cycles of warp 0 in [FF hidden tiles, FF ctx + sync, row phase busy, barrier wait]
 __device__ unsigned long long g_phase_cycles_tc[4];
+__device__ unsigned long long g_row_cycles_tc[8];   // per-pass cycles of warp 0 inside the row phase
+#define RT_MARK(i) do { if (tid == 0) { const long long _n = clock64(); rt_acc[i] += _n - rt_t; rt_t = _n; } } while (0)
 #define PT_MARK(i) do { if (tid == 0) { const long long _n = clock64(); pt_acc[i] += _n - pt_t; pt_t = _n; } } while (0)
 #else
 #define PT_MARK(i) do { } while (0)
+#define RT_MARK(i) do { } while (0)
 #endif
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -204,6 +207,8 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
 #ifdef EVRP_PHASE_TIMING
   long long pt_acc[4] = {0, 0, 0, 0};
   long long pt_t = clock64();
+  long long rt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long rt_t = 0;
 #endif
 
   // ---------------- step loop ----------------
@@ -338,6 +343,9 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         if (lr >= rows_per_cta) break;
         RowState& rs = sm.rs[lr];
         if (rs.done) continue;                             // warp-uniform
+#ifdef EVRP_PHASE_TIMING
+        if (tid == 0) rt_t = clock64();
+#endif
         const int row = blockIdx.x * rows_per_cta + lr;
         const int inst = rs.inst;
         const int now = rs.now;
@@ -383,6 +391,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           q[2] = (fc.z + (cx.z + b2.z)) + en.z;
           q[3] = (fc.w + (cx.w + b2.w)) + en.w;
         }
+        RT_MARK(0);
         // ---- compat[h][i] = q_h . K[j_i, h] / 4 ; CH rows (CH x 512 B) in flight per warp ----
         constexpr int CH = 8;
         for (int i0 = 0; i0 < nf; i0 += CH) {
@@ -398,6 +407,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           }
         }
         __syncwarp();
+        RT_MARK(1);
         // ---- per-head softmax over the list; lane (hd, sub) strides i = sub, sub+4, ... ----
         {
           if (pf_lines & 4) {
@@ -418,6 +428,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           for (int i = sub; i < nf; i += 4) ws.pc[hd][i] = __fdiv_rn(ws.pc[hd][i], sum);
         }
         __syncwarp();
+        RT_MARK(2);
         // ---- heads = attn @ V ; lane owns 4 channels ----
         {
           if (pf_lines & 8) {
@@ -445,6 +456,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           *reinterpret_cast<float4*>(&ws.heads[lane * 4]) = make_float4(hv[0], hv[1], hv[2], hv[3]);
         }
         __syncwarp();
+        RT_MARK(3);
         // ---- logits[i] = heads . lK[j_i] / sqrt(128) -> tanh clip -> / temp  (project_out folded into lK).
         //      8 lanes per node: lane (grp, s8) covers channels 4*s8 + 32*c, c = 0..3; 4 nodes per pass ----
         {
@@ -480,6 +492,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           }
         }
         __syncwarp();
+        RT_MARK(4);
         // ---- log_softmax over the list (:403) ----
         float zl[4];
         float mx = -INFINITY;
@@ -561,6 +574,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           lp_sel = __shfl_sync(FULL, sel4(lp, sel_i >> 5), sel_i & 31);
         } else { c_node = -1 - sel_i; lp_sel = -INFINITY; }
 
+        RT_MARK(5);
         // ---- loads for the transition and the new mask, issued together ----
         const float dist = __ldg(Db + (size_t)now * S + c_node);
         const float slp = __ldg(Gb + (size_t)now * S + c_node);
@@ -621,6 +635,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           *reinterpret_cast<uint4*>(p) = hi;
           *reinterpret_cast<uint4*>(p + KBLK) = lo;
         }
+        RT_MARK(6);
         // ---- new mask (problems/EVRP.py:105-223) ----
         bool any_dem = false, cust_dem = false;
 #pragma unroll
@@ -685,6 +700,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           }
         }
         __syncwarp();
+        RT_MARK(7);
       }
       PT_MARK(2);
       fence_async_smem();          // B1 plane writes (and the scratch the next TMA overwrites) -> async proxy
@@ -693,6 +709,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
   }
 #ifdef EVRP_PHASE_TIMING
   if (tid == 0) for (int i = 0; i < 4; ++i) atomicAdd(&g_phase_cycles_tc[i], (unsigned long long)pt_acc[i]);
+  if (tid == 0) for (int i = 0; i < 8; ++i) atomicAdd(&g_row_cycles_tc[i], (unsigned long long)rt_acc[i]);
 #endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -705,6 +722,11 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
 int debug_phase_cycles_tc(unsigned long long* out4, int reset) {
   if (cudaMemcpyFromSymbol(out4, dtc::g_phase_cycles_tc, sizeof(unsigned long long) * 4) != cudaSuccess) return -1;
   if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(dtc::g_phase_cycles_tc, z, sizeof(z)); }
+  return 0;
+}
+int debug_row_cycles_tc(unsigned long long* out8, int reset) {
+  if (cudaMemcpyFromSymbol(out8, dtc::g_row_cycles_tc, sizeof(unsigned long long) * 8) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(dtc::g_row_cycles_tc, z, sizeof(z)); }
   return 0;
 }
 #endif
