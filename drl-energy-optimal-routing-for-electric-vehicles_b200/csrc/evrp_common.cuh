@@ -32,23 +32,27 @@ constexpr unsigned FULL = 0xffffffffu;
 // obtained with one FMA refinement of x * fl(1/d) (Markstein): q0 = x*r; q = fma(fma(-d, q0, x), r, q0).  This was
 // checked EXHAUSTIVELY against x / d for every finite fp32 x (tools/divcheck.c): identical for all |x| >= 2e-37;
 // smaller non-zero magnitudes (never produced by this model) take the generic division.
+// generic IEEE division, kept out of line: it is the rare path of div_scalar, and one shared copy keeps the
+// instruction footprint of the rollout kernels' row loop small (the loop is instruction-cache sensitive)
+static __device__ __noinline__ float div_generic(float x, float d) { return __fdiv_rn(x, d); }
+
 __device__ __forceinline__ float div_scalar(float x, float d, float inv_d, int mode) {
   if (mode) return __fmul_rn(x, inv_d);
   if ((d == 50.f || d == 3600.f) && (x == 0.f || fabsf(x) >= 1e-30f)) {
     const float q0 = __fmul_rn(x, inv_d);
     return __fmaf_rn(__fmaf_rn(-d, q0, x), inv_d, q0);
   }
-  return __fdiv_rn(x, d);
+  return div_generic(x, d);
 }
 
 // soc consumption of one leg (problems/EVRP.py:246-252 and the four copies inside update_mask :155-211)
 __device__ __forceinline__ float leg_energy(const evrp_phys& p, float mass, float slope, float tc) {
   const float mg = __fmul_rn(mass, p.g);
   const float Pm = __fmul_rn(__fadd_rn(__fadd_rn(p.aero, __fmul_rn(mg, slope)), __fmul_rn(mg, p.Cr)), p.velocity);
-  float e = 0.f;
-  if (Pm > 0.f) e = div_scalar(__fmul_rn(__fmul_rn(p.kd, Pm), tc), 3600.f, p.inv_3600, p.div_mode);
-  else if (Pm < 0.f) e = div_scalar(__fmul_rn(__fmul_rn(p.kr, Pm), tc), 3600.f, p.inv_3600, p.div_mode);
-  return e;
+  // drive (Pm > 0) and recuperation (Pm < 0) differ only in the efficiency factor: one division site (same ops, same bits)
+  const float k = (Pm > 0.f) ? p.kd : p.kr;
+  const float e = div_scalar(__fmul_rn(__fmul_rn(k, Pm), tc), 3600.f, p.inv_3600, p.div_mode);
+  return (Pm > 0.f || Pm < 0.f) ? e : 0.f;           // Pm == 0 (and NaN) contribute nothing, as in the reference
 }
 
 __device__ __forceinline__ float vehicle_mass(const evrp_phys& p, float load) {

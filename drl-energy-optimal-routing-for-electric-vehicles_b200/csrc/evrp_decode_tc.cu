@@ -473,6 +473,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
 #pragma unroll
               for (int c = 0; c < 4; ++c) lv[u][c] = ldg4(p + c * 32);
             }
+            float au[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               float acc = 0.f;
@@ -482,12 +483,14 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
               acc += __shfl_xor_sync(FULL, acc, 1);
               acc += __shfl_xor_sync(FULL, acc, 2);
               acc += __shfl_xor_sync(FULL, acc, 4);
-              const int i = i0 + u * 4 + grp;
-              if (s8 == 0 && i < nf) {
-                float z = __fdiv_rn(acc, sqrt_d);
-                if (cfg.tanh_clipping > 0.f) z = tanhf(z) * cfg.tanh_clipping;
-                ws.logit[i] = __fdiv_rn(z, cfg.temp);
-              }
+              au[u] = acc;                                   // every lane of the group holds the node's full dot product
+            }
+            // one copy of the divide / tanh / divide tail: lane (grp, s8 < 4) finishes node i0 + 4*s8 + grp
+            const int i = i0 + s8 * 4 + grp;
+            if (s8 < 4 && i < nf) {
+              float z = __fdiv_rn(sel4(au, s8), sqrt_d);
+              if (cfg.tanh_clipping > 0.f) z = tanhf(z) * cfg.tanh_clipping;
+              ws.logit[i] = __fdiv_rn(z, cfg.temp);
             }
           }
         }
