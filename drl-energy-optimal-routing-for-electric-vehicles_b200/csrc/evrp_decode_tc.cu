@@ -394,6 +394,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         RT_MARK(0);
         // ---- compat[h][i] = q_h . K[j_i, h] / 4 ; CH rows (CH x 512 B) in flight per warp ----
         constexpr int CH = 8;
+        float cmx = -INFINITY;                             // per-head maximum, tracked by all four lanes of the head
         for (int i0 = 0; i0 < nf; i0 += CH) {
           float4 kv[CH];
 #pragma unroll
@@ -403,12 +404,14 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
             float p = fmaf(q[3], kv[a].w, fmaf(q[2], kv[a].z, fmaf(q[1], kv[a].y, q[0] * kv[a].x)));
             p += __shfl_xor_sync(FULL, p, 1);
             p += __shfl_xor_sync(FULL, p, 2);
-            if (sub == 0 && i0 + a < nf) ws.pc[hd][i0 + a] = p * 0.25f;
+            p *= 0.25f;
+            if (i0 + a < nf) { cmx = fmaxf(cmx, p); if (sub == 0) ws.pc[hd][i0 + a] = p; }
           }
         }
         __syncwarp();
         RT_MARK(1);
         // ---- per-head softmax over the list; lane (hd, sub) strides i = sub, sub+4, ... ----
+        float sum = 0.f;
         {
           if (pf_lines & 4) {
             for (int i = lane; i < nf; i += 32) {
@@ -417,15 +420,9 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
               for (int c = 0; c < 4; ++c) prefetch_l2(p + c * 32);
             }
           }
-          float mx = -INFINITY;
-          for (int i = sub; i < nf; i += 4) mx = fmaxf(mx, ws.pc[hd][i]);
-          mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 1));
-          mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 2));
-          float sum = 0.f;
-          for (int i = sub; i < nf; i += 4) { const float e = expf(ws.pc[hd][i] - mx); ws.pc[hd][i] = e; sum += e; }
+          for (int i = sub; i < nf; i += 4) { const float e = expf(ws.pc[hd][i] - cmx); ws.pc[hd][i] = e; sum += e; }
           sum += __shfl_xor_sync(FULL, sum, 1);
-          sum += __shfl_xor_sync(FULL, sum, 2);
-          for (int i = sub; i < nf; i += 4) ws.pc[hd][i] = __fdiv_rn(ws.pc[hd][i], sum);
+          sum += __shfl_xor_sync(FULL, sum, 2);               // the division by `sum` is applied to the 4 head outputs below
         }
         __syncwarp();
         RT_MARK(2);
@@ -453,7 +450,8 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
               hv[2] = fmaf(pr[a], vv[a].z, hv[2]); hv[3] = fmaf(pr[a], vv[a].w, hv[3]);
             }
           }
-          *reinterpret_cast<float4*>(&ws.heads[lane * 4]) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+          *reinterpret_cast<float4*>(&ws.heads[lane * 4]) =
+              make_float4(__fdiv_rn(hv[0], sum), __fdiv_rn(hv[1], sum), __fdiv_rn(hv[2], sum), __fdiv_rn(hv[3], sum));
         }
         __syncwarp();
         RT_MARK(3);
