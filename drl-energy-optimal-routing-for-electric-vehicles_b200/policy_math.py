@@ -125,9 +125,54 @@ def init_embed_torch(model, static, dynamic):
                       model.init_embed(torch.cat((xy[:, F + 1:], dem[:, F + 1:]), 2))), 1)
 
 
+class _GlobalBatchNorm(torch.autograd.Function):
+    """Train-mode BatchNorm1d over the GLOBAL batch when instances are sharded over ranks: the batch statistics of
+    nets/GraphEncoder.py:144-145 couple every instance of the batch, so each rank contributes [sum x, sum x^2, n]
+    (and, backward, [sum g, sum g*xhat]) through one all-reduce of 2*C+1 floats.  Same outputs / gradients /
+    running-statistics update (momentum, unbiased variance) as nn.BatchNorm1d on the concatenated batch."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, bn):
+        import torch.distributed as dist
+        C = x.shape[1]
+        st = torch.cat([x.sum(0), (x * x).sum(0), x.new_tensor([float(x.shape[0])])])
+        dist.all_reduce(st, op=dist.ReduceOp.SUM)
+        n = st[2 * C]
+        mean = st[:C] / n
+        var = st[C:2 * C] / n - mean * mean                      # biased (normalisation)
+        with torch.no_grad():
+            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
+            bn.running_mean.mul_(1 - m).add_(m * mean)
+            bn.running_var.mul_(1 - m).add_(m * var * (n / (n - 1)))   # unbiased, like F.batch_norm
+            bn.num_batches_tracked += 1
+        inv = torch.rsqrt(var + bn.eps)
+        xhat = (x - mean) * inv
+        ctx.save_for_backward(xhat, weight, inv, n)
+        return xhat * weight + bias
+
+    @staticmethod
+    def backward(ctx, g):
+        import torch.distributed as dist
+        xhat, weight, inv, n = ctx.saved_tensors
+        C = g.shape[1]
+        st = torch.cat([g.sum(0), (g * xhat).sum(0)])
+        gw, gb = st[C:].clone(), st[:C].clone()                  # this rank's share; summed with the other gradients
+        dist.all_reduce(st, op=dist.ReduceOp.SUM)
+        gx = (weight * inv) * (g - st[:C] / n - xhat * (st[C:] / n))
+        return gx, gw, gb, None
+
+
+def _batch_norm(bn, x, training):
+    import torch.distributed as dist
+    if training and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return _GlobalBatchNorm.apply(x, bn.weight, bn.bias, bn)
+    return bn(x)
+
+
 def encode_torch(model, static, dynamic):
     """Differentiable restatement of the encoder kernels' math (nets/GraphEncoder.py:55-118,142-179).
-    BatchNorm follows ``model.training`` (batch statistics + running-stat update in train mode)."""
+    BatchNorm follows ``model.training`` (batch statistics + running-stat update in train mode; with instances
+    sharded over ranks the statistics are those of the global batch, see _GlobalBatchNorm)."""
     h = init_embed_torch(model, static, dynamic)
     B, S, d = h.shape
     for layer in model.embedder.layers:
@@ -139,8 +184,8 @@ def encode_torch(model, static, dynamic):
         attn = torch.softmax(torch.matmul(Q, K.transpose(2, 3)) / math.sqrt(Q.shape[-1]), -1)
         heads = torch.matmul(attn, V)
         out = torch.mm(heads.permute(1, 2, 0, 3).reshape(B * S, -1), att.W_out.reshape(-1, d)).view(B, S, d)
-        h = bn1((h + out).view(-1, d)).view(B, S, d)
-        h = bn2((h + ff(h)).view(-1, d)).view(B, S, d)
+        h = _batch_norm(bn1, (h + out).view(-1, d), model.training).view(B, S, d)
+        h = _batch_norm(bn2, (h + ff(h)).view(-1, d), model.training).view(B, S, d)
     kvl = Fn.linear(h, folded_node_projection(model))
     fixed = model.project_fixed_context(h.mean(1))
     return h, kvl, fixed

@@ -38,6 +38,22 @@ def _worker(rank, world, port, q):
     bl = T.ExponentialBaseline(0.8)
     v, _ = bl.eval(None, torch.from_numpy(cand[lo:hi]).float())
     out["ema"] = float(v)
+    # train-mode BatchNorm over the global batch (nets/GraphEncoder.py:144-145) with rows sharded over ranks
+    from evrp_b200 import policy_math as PM
+    torch.manual_seed(1)
+    bn = torch.nn.BatchNorm1d(6)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.5, 0.5)
+    xb = torch.randn(14, 6) * 2 + 1
+    gy = torch.randn(14, 6)
+    a, b = (0, 9) if rank == 0 else (9, 14)                    # ragged shards
+    xs = xb[a:b].clone().requires_grad_(True)
+    y = PM._batch_norm(bn, xs, True)
+    (y * gy[a:b]).sum().backward()
+    T.allreduce_gradients([bn.weight, bn.bias])
+    out["bn"] = dict(y=y.detach().numpy(), gx=xs.grad.numpy(), gw=bn.weight.grad.numpy(), gb=bn.bias.grad.numpy(),
+                     rm=bn.running_mean.numpy().copy(), rv=bn.running_var.numpy().copy(),
+                     nbt=int(bn.num_batches_tracked))
     q.put((rank, out))
     dist.destroy_process_group()
 
@@ -69,6 +85,22 @@ def test_world_size_2_gloo():
     (lin(x).pow(2).sum() / 10).backward()
     assert np.allclose(res[0]["grad"], lin.weight.grad.numpy(), atol=1e-6)
     assert np.allclose(res[1]["grad"], res[0]["grad"])
+    # sharded BatchNorm == nn.BatchNorm1d on the concatenated batch (outputs, input / affine gradients, running stats)
+    torch.manual_seed(1)
+    bn = torch.nn.BatchNorm1d(6)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.5, 0.5)
+    xb = (torch.randn(14, 6) * 2 + 1).requires_grad_(True)
+    gy = torch.randn(14, 6)
+    y = bn(xb)
+    (y * gy).sum().backward()
+    for r, (a, b) in ((0, (0, 9)), (1, (9, 14))):
+        o = res[r]["bn"]
+        assert np.allclose(o["y"], y.detach().numpy()[a:b], atol=1e-5)
+        assert np.allclose(o["gx"], xb.grad.numpy()[a:b], atol=1e-5)
+        assert np.allclose(o["gw"], bn.weight.grad.numpy(), atol=1e-5) and np.allclose(o["gb"], bn.bias.grad.numpy(), atol=1e-5)
+        assert np.allclose(o["rm"], bn.running_mean.numpy(), atol=1e-6) and np.allclose(o["rv"], bn.running_var.numpy(), atol=1e-5)
+        assert o["nbt"] == 1
 
 
 def test_shard_bounds_cover_everything():
