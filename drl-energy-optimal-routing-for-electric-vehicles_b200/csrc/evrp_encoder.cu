@@ -12,30 +12,44 @@
 namespace evrp {
 
 // ------------------------------------------------------------------------------------------------
-// init embedding: one thread per (row, 4 channels)
+// init embedding: one warp per node row, one lane per 4 channels (512-byte coalesced store per row)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 init_embed_kernel(const float* __restrict__ xy, const float* __restrict__ dyn, int B, int S, int F,
                   const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w1,
                   const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                   float* __restrict__ h) {
-  const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;   // over rows*128
-  const size_t total = (size_t)B * S * D;
-  if (idx >= total) return;
-  const int d = (int)(idx % D);
-  const size_t row = idx / D;
-  const int j = (int)(row % S);
-  const size_t b = row / S;
-  const float x = __fdiv_rn(xy[(b * 2 + 0) * S + j], 100.f);
-  const float y = __fdiv_rn(xy[(b * 2 + 1) * S + j], 100.f);
-  float v;
-  if (j == 0) v = fmaf(w0[d * 2 + 1], y, fmaf(w0[d * 2], x, 0.f)) + b0[d];
-  else if (j <= F) v = fmaf(w1[d * 2 + 1], y, fmaf(w1[d * 2], x, 0.f)) + b1[d];
-  else {
-    const float dem = dyn[(b * 4 + 1) * S + j];
-    v = fmaf(w2[d * 3 + 2], dem, fmaf(w2[d * 3 + 1], y, fmaf(w2[d * 3], x, 0.f))) + b2[d];
+  const int lane = threadIdx.x & 31;
+  const size_t rows = (size_t)B * S;
+  const size_t warp0 = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * (size_t)blockDim.x) >> 5;
+  // this lane's 4 channels of the three embedding layers (nets/DRLModel.py:78-80), kept in registers
+  float wd[4][2], ws[4][2], wc[4][3], bd[4], bs[4], bc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane * 4 + i;
+    wd[i][0] = w0[d * 2]; wd[i][1] = w0[d * 2 + 1]; bd[i] = b0[d];
+    ws[i][0] = w1[d * 2]; ws[i][1] = w1[d * 2 + 1]; bs[i] = b1[d];
+    wc[i][0] = w2[d * 3]; wc[i][1] = w2[d * 3 + 1]; wc[i][2] = w2[d * 3 + 2]; bc[i] = b2[d];
   }
-  h[idx] = v;
+  for (size_t row = warp0; row < rows; row += nwarps) {
+    const int j = (int)(row % S);
+    const size_t b = row / S;
+    const float x = __fdiv_rn(xy[(b * 2 + 0) * S + j], 100.f);
+    const float y = __fdiv_rn(xy[(b * 2 + 1) * S + j], 100.f);
+    float v[4];
+    if (j == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = fmaf(wd[i][1], y, fmaf(wd[i][0], x, 0.f)) + bd[i];
+    } else if (j <= F) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = fmaf(ws[i][1], y, fmaf(ws[i][0], x, 0.f)) + bs[i];
+    } else {
+      const float dem = dyn[(b * 4 + 1) * S + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = fmaf(wc[i][2], dem, fmaf(wc[i][1], y, fmaf(wc[i][0], x, 0.f))) + bc[i];
+    }
+    *reinterpret_cast<float4*>(h + row * D + lane * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -163,66 +177,70 @@ self_attention_kernel(const float* __restrict__ qkv, int S, float* __restrict__ 
   for (int i0 = 0; i0 < S; i0 += 64) {          // two query rows per lane per pass
     const int ia = i0 + lane, ib = i0 + 32 + lane;
     const bool va = ia < S, vb = ib < S;
-    // the two query rows of a lane are packed into float2 lanes so that every FMA is an FFMA2
-    float2 q2[DK], o2[DK];
+    // every FMA is an FFMA2 packed along the head dimension: (d, d+1) pairs of q, K and V sit in adjacent
+    // registers exactly as the 16-byte loads deliver them, so no operand has to be duplicated
+    float2 qa[DK / 2], qb[DK / 2], oa[DK / 2], ob[DK / 2];
 #pragma unroll
     for (int c4 = 0; c4 < DK; c4 += 4) {
       const float4 t = va ? *reinterpret_cast<const float4*>(base + (size_t)ia * 384 + h * DK + c4) : make_float4(0, 0, 0, 0);
       const float4 u = vb ? *reinterpret_cast<const float4*>(base + (size_t)ib * 384 + h * DK + c4) : make_float4(0, 0, 0, 0);
-      q2[c4] = make_float2(t.x, u.x); q2[c4 + 1] = make_float2(t.y, u.y);
-      q2[c4 + 2] = make_float2(t.z, u.z); q2[c4 + 3] = make_float2(t.w, u.w);
+      qa[c4 / 2] = make_float2(t.x, t.y); qa[c4 / 2 + 1] = make_float2(t.z, t.w);
+      qb[c4 / 2] = make_float2(u.x, u.y); qb[c4 / 2 + 1] = make_float2(u.z, u.w);
     }
 #pragma unroll
-    for (int c = 0; c < DK; ++c) o2[c] = make_float2(0.f, 0.f);
+    for (int c = 0; c < DK / 2; ++c) { oa[c] = make_float2(0.f, 0.f); ob[c] = make_float2(0.f, 0.f); }
     float ma = -INFINITY, mb = -INFINITY, la = 0.f, lb = 0.f;
     for (int j = 0; j < S; ++j) {
-      float kk[DK], vv[DK];
+      float2 kk[DK / 2], vv[DK / 2];
 #pragma unroll
       for (int c4 = 0; c4 < DK; c4 += 4) {
         const float4 t = *reinterpret_cast<const float4*>(Ks + j * DK + c4);
         const float4 u = *reinterpret_cast<const float4*>(Vs + j * DK + c4);
-        kk[c4] = t.x; kk[c4 + 1] = t.y; kk[c4 + 2] = t.z; kk[c4 + 3] = t.w;
-        vv[c4] = u.x; vv[c4 + 1] = u.y; vv[c4 + 2] = u.z; vv[c4 + 3] = u.w;
+        kk[c4 / 2] = make_float2(t.x, t.y); kk[c4 / 2 + 1] = make_float2(t.z, t.w);
+        vv[c4 / 2] = make_float2(u.x, u.y); vv[c4 / 2 + 1] = make_float2(u.z, u.w);
       }
-      float2 s2 = make_float2(0.f, 0.f);
+      // two partial sums per row keep the FMA chains short (4 deep)
+      float2 sa0 = make_float2(0.f, 0.f), sa1 = sa0, sb0 = sa0, sb1 = sa0;
 #pragma unroll
-      for (int c = 0; c < DK; ++c) ffma2s(s2, q2[c], kk[c]);
-      const float sa = s2.x * 0.25f, sb = s2.y * 0.25f;       // norm_factor = 1/sqrt(16), exact
+      for (int c = 0; c < DK / 2; c += 2) {
+        ffma2(sa0, qa[c], kk[c]); ffma2(sa1, qa[c + 1], kk[c + 1]);
+        ffma2(sb0, qb[c], kk[c]); ffma2(sb1, qb[c + 1], kk[c + 1]);
+      }
+      const float sa = ((sa0.x + sa1.x) + (sa0.y + sa1.y)) * 0.25f;    // norm_factor = 1/sqrt(16), exact
+      const float sb = ((sb0.x + sb1.x) + (sb0.y + sb1.y)) * 0.25f;
       if (sa > ma) {                                          // online softmax: rescale on a new maximum
         const float r = expf(ma - sa);                        // exp(-inf) = 0 on the first hit
         la *= r;
 #pragma unroll
-        for (int c = 0; c < DK; ++c) o2[c].x *= r;
+        for (int c = 0; c < DK / 2; ++c) { oa[c].x *= r; oa[c].y *= r; }
         ma = sa;
       }
       if (sb > mb) {
         const float r = expf(mb - sb);
         lb *= r;
 #pragma unroll
-        for (int c = 0; c < DK; ++c) o2[c].y *= r;
+        for (int c = 0; c < DK / 2; ++c) { ob[c].x *= r; ob[c].y *= r; }
         mb = sb;
       }
-      const float2 p2 = make_float2(expf(sa - ma), expf(sb - mb));
-      la += p2.x; lb += p2.y;
+      const float pa = expf(sa - ma), pb = expf(sb - mb);
+      la += pa; lb += pb;
+      const float2 pa2 = make_float2(pa, pa), pb2 = make_float2(pb, pb);
 #pragma unroll
-      for (int c = 0; c < DK; ++c) ffma2(o2[c], p2, make_float2(vv[c], vv[c]));
+      for (int c = 0; c < DK / 2; ++c) { ffma2(oa[c], pa2, vv[c]); ffma2(ob[c], pb2, vv[c]); }
     }
-    float oa[DK], ob[DK];
-#pragma unroll
-    for (int c = 0; c < DK; ++c) { oa[c] = o2[c].x; ob[c] = o2[c].y; }
     if (va) {
       const float inv = 1.f / la;
       float* o = heads + ((size_t)b * S + ia) * D + h * DK;
 #pragma unroll
-      for (int c4 = 0; c4 < DK; c4 += 4)
-        *reinterpret_cast<float4*>(o + c4) = make_float4(oa[c4] * inv, oa[c4 + 1] * inv, oa[c4 + 2] * inv, oa[c4 + 3] * inv);
+      for (int c = 0; c < DK / 2; c += 2)
+        *reinterpret_cast<float4*>(o + 2 * c) = make_float4(oa[c].x * inv, oa[c].y * inv, oa[c + 1].x * inv, oa[c + 1].y * inv);
     }
     if (vb) {
       const float inv = 1.f / lb;
       float* o = heads + ((size_t)b * S + ib) * D + h * DK;
 #pragma unroll
-      for (int c4 = 0; c4 < DK; c4 += 4)
-        *reinterpret_cast<float4*>(o + c4) = make_float4(ob[c4] * inv, ob[c4 + 1] * inv, ob[c4 + 2] * inv, ob[c4 + 3] * inv);
+      for (int c = 0; c < DK / 2; c += 2)
+        *reinterpret_cast<float4*>(o + 2 * c) = make_float4(ob[c].x * inv, ob[c].y * inv, ob[c + 1].x * inv, ob[c + 1].y * inv);
     }
   }
 }
@@ -282,10 +300,13 @@ int evrp_encoder_forward(const evrp_encoder_weights* w, const float* static_xy, 
   float* wide = (float*)((char*)workspace + 3 * slab);
 
   {
-    const size_t total = (size_t)M * D;
-    init_embed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(static_xy, dynamic, B, S, F, w->depot_w,
-                                                                       w->depot_b, w->station_w, w->station_b,
-                                                                       w->cust_w, w->cust_b, ha);
+    int dev = 0, sms = 148;
+    EVRP_CUDA_OK(cudaGetDevice(&dev));
+    EVRP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long want = ((long long)M + 7) / 8;                       // 8 warps (rows) per CTA per sweep
+    const unsigned grid = (unsigned)(want < (long long)sms * 16 ? want : (long long)sms * 16);
+    init_embed_kernel<<<grid, 256, 0, st>>>(static_xy, dynamic, B, S, F, w->depot_w, w->depot_b, w->station_w,
+                                            w->station_b, w->cust_w, w->cust_b, ha);
     EVRP_LAUNCH_OK();
   }
   const size_t attn_smem = (size_t)H * 2 * S * DK * sizeof(float);
