@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EVRP_B200_LIB") or os.path.join(_HERE, "libevrp_b200.so")   # override: instrumented debug builds (tools/)
 
 EVRP_MAX_S = 128
-ABI_VERSION = 7
+ABI_VERSION = 8
 EVRP_MAX_LAYERS = 8
 ST_NAN_LOGIT, ST_INFEASIBLE_PICK, ST_STEP_CAP, ST_NONUNIFORM_DYNAMIC, ST_NO_FEASIBLE = 1, 2, 4, 8, 16
 DECODE_GREEDY, DECODE_SAMPLE = 0, 1
@@ -42,7 +42,7 @@ class EncoderWeights(C.Structure):
 
 class DecoderWeights(C.Structure):
     _fields_ = [(n, _FP) for n in ("w1_veh", "w1_max", "b1", "w2", "b2", "w1max_hi", "w1max_lo", "w2_hi", "w2_lo")] + \
-        [("ff_mode", C.c_int32)]
+        [("w1_inv_scale", C.c_float), ("w2_inv_scale", C.c_float), ("ff_mode", C.c_int32)]
 
 
 class RolloutCfg(C.Structure):

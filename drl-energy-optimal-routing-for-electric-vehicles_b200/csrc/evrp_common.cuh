@@ -89,6 +89,51 @@ __device__ __forceinline__ bool reachable(const evrp_phys& p, int j, int F, floa
   return !(via_depot_bad && via_station_bad);                                       // :218
 }
 
+// ---- call-free variant for the rollout kernels' row loop (instruction-cache footprint) ----
+// div_fast is the FMA-refined quotient of div_scalar WITHOUT the range guard: it equals IEEE x / d for d in {50, 3600}
+// and every x with |x| >= 2e-37 or x == 0 (tools/divcheck.c); `bad` collects the (never observed) inputs outside that
+// range, for which the caller re-evaluates with the generic out-of-line version below.
+__device__ __forceinline__ float div_fast(float x, float d, float inv_d, bool& bad) {
+  bad |= (x != 0.f) && (fabsf(x) < 1e-30f);
+  const float q0 = __fmul_rn(x, inv_d);
+  return __fmaf_rn(__fmaf_rn(-d, q0, x), inv_d, q0);
+}
+__device__ __forceinline__ float leg_energy_fast(const evrp_phys& p, float mass, float slope, float tc, bool& bad) {
+  const float mg = __fmul_rn(mass, p.g);
+  const float Pm = __fmul_rn(__fadd_rn(__fadd_rn(p.aero, __fmul_rn(mg, slope)), __fmul_rn(mg, p.Cr)), p.velocity);
+  const float k = (Pm > 0.f) ? p.kd : p.kr;
+  const float e = div_fast(__fmul_rn(__fmul_rn(k, Pm), tc), 3600.f, p.inv_3600, bad);
+  return (Pm > 0.f || Pm < 0.f) ? e : 0.f;
+}
+// same statements as reachable(); legal when div_mode == 0 and velocity == 50 (the caller checks once per kernel)
+__device__ __forceinline__ bool reachable_fast(const evrp_phys& p, int j, int F, float load0, float load_j, float dem_j,
+                                               float soc_j, float time_j, float d0, float g0, float D0j, float G0j,
+                                               float d3, float s3, float d4, bool& bad) {
+  const float v = p.velocity, iv = p.inv_velocity;
+  const float tc0 = div_fast(d0, v, iv, bad);
+  const float soc0 = leg_energy_fast(p, vehicle_mass(p, load0), g0, tc0, bad);
+  const float mass2 = vehicle_mass(p, __fsub_rn(load_j, dem_j));
+  const float soc2 = leg_energy_fast(p, mass2, G0j, div_fast(D0j, v, iv, bad), bad);
+  float soc3 = __fadd_rn(soc0, soc2);
+  if (j <= F) soc3 = 0.f;
+  float tc3 = div_fast(__fadd_rn(d0, D0j), v, iv, bad);
+  if (j >= 1 && j <= F) tc3 = __fadd_rn(tc3, p.charging_time);
+  else if (j > F) tc3 = __fadd_rn(tc3, p.serve_time);
+  const float soc4 = leg_energy_fast(p, mass2, s3, div_fast(d3, v, iv, bad), bad);
+  const float soc5 = __fadd_rn(soc0, soc4);
+  float tc5 = div_fast(__fadd_rn(__fadd_rn(d0, d3), d4), v, iv, bad);
+  if (j > F) tc5 = __fadd_rn(tc5, p.charge_plus_serve);
+  const bool direct_bad = (soc_j < soc0) || (time_j < tc0);
+  const bool via_depot_bad = (soc_j < soc3) || (time_j < tc3);
+  const bool via_station_bad = (soc_j < soc5) || (time_j < tc5);
+  return !direct_bad && !(via_depot_bad && via_station_bad);
+}
+static __device__ __noinline__ bool reachable_generic(const evrp_phys& p, int j, int F, float load0, float load_j,
+                                                      float dem_j, float soc_j, float time_j, float d0, float g0,
+                                                      float D0j, float G0j, float d3, float s3, float d4) {
+  return reachable(p, j, F, load0, load_j, dem_j, soc_j, time_j, d0, g0, D0j, G0j, d3, s3, d4);
+}
+
 // Counter-based RNG for sampling: splitmix64 finaliser over (seed, row, step) -> uniform in [0,1).
 __device__ __forceinline__ float uniform01(uint64_t seed, uint64_t row, uint32_t step) {
   uint64_t z = seed + 0x9E3779B97F4A7C15ull * (row * 1024ull + step + 1ull);

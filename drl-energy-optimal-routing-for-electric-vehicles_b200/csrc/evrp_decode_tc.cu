@@ -10,21 +10,24 @@
 //
 // Layout: ONE CTA per SM (576 threads) owns up to RPC = 64 rollout rows for their whole life.
 //   warps 0-15   row warps: per-row decode phase; in the FF phase they are the TMEM epilogue / operand converters
-//   warp  16     TMA producer: streams the pre-split TF32 weight planes of FF_tour from L2 (2-stage ring, 32 KB stages)
-//   warp  17     MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::tf32 (M = 128, N = 64, K = 8)
+//   warp  16     TMA producer: streams the pre-split fp16 weight planes of FF_tour from L2 (4-stage ring, 32 KB stages)
+//   warp  17     MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = 64, K = 16)
 // Per step
 //   1. FF_tour, transposed so that the ROWS are the MMA N dimension (any row count <= 64 costs N/256 of a full tile):
 //        h1^T [512 x rows] = W1max [512 x 128] . m^T      4 M-tiles, A = weight tile (smem, TMA), B = running-max planes
 //        ctx^T [128 x rows] = W2 [128 x 512] . relu(h1 + b1 + W1veh veh)^T     B = hidden planes written by the epilogue
-//      every product is the error-compensated 3xTF32 split (Ah Bh + Al Bh + Ah Bl, fp32 accumulation in TMEM), the
-//      same fp32-faithful scheme as the encoder GEMMs (evrp_tc_gemm.cu); accumulators: 4 x 64 + 64 TMEM columns.
+//      every operand is split into two fp16 planes, x = hi + lo (22 significant bits, like a TF32 pair at half the
+//      bytes; weights pre-scaled by a power of two so that lo stays normal) and every product is the compensated sum
+//      Ah Bh + Al Bh + Ah Bl with fp32 accumulation in TMEM - the fp32-faithful scheme of the encoder GEMMs
+//      (evrp_tc_gemm.cu) at half the weight stream and half the MMA count; accumulators: 4 x 64 + 64 TMEM columns.
 //   2. per row (warp): glimpse attention / logits over the FEASIBLE nodes only, warp-level masked log-softmax,
 //      first-index argmax / inverse-CDF sample, state transition + look-ahead feasibility mask (bit-exact recipe).
-//      The running max of visited embeddings is kept exact in global memory (L2-resident) and as TF32 (hi, lo)
+//      The running max of visited embeddings is kept exact in global memory (L2-resident) and as fp16 (hi, lo)
 //      planes in the 128B-swizzled K-major layout the MMA reads.
 // Rows retire individually; the host reads back only t_max and the status word.
 #include <math.h>
 #include <stdlib.h>
+#include <cuda_fp16.h>
 #include "evrp_tc.cuh"
 
 namespace evrp {
@@ -37,12 +40,16 @@ constexpr int ROW_WARPS = 16;
 constexpr int NT = (ROW_WARPS + 2) * 32;     // 576
 constexpr int SP = EVRP_MAX_S;               // padded node count (128)
 constexpr int PSTR = SP + 4;                 // head stride of the compat buffer
-constexpr int KBLK = RPC * 128;              // 8 KB: [64 rows x 32 fp32], 128B-swizzled, one plane of one K block
-constexpr int ACT_BYTES = 4 * 2 * KBLK;      // 64 KB: 4 K blocks x (hi, lo)
-constexpr int WPLANE = 128 * 128;            // 16 KB: [128 x 32 fp32] weight tile plane
+constexpr int KBLK = RPC * 128;              // 8 KB: [64 rows x 64 fp16], 128B-swizzled, one plane of one K block
+constexpr int ACT_BYTES = 2 * 2 * KBLK;      // 32 KB: 2 K blocks (128 channels) x (hi, lo)
+constexpr int WPLANE = 128 * 128;            // 16 KB: [128 x 64 fp16] weight tile plane
 constexpr int WSTAGE = 2 * WPLANE;           // hi + lo
-constexpr int WSTAGES = 2;
-constexpr uint32_t IDESC = make_idesc_tf32(128, RPC);
+#ifndef EVRP_WSTAGES
+#define EVRP_WSTAGES 4
+#endif
+constexpr int WSTAGES = EVRP_WSTAGES;
+constexpr int NSTAGE_STEP = 16;              // stages per decode step: 8 of W1max (4 tiles x 2 K blocks), 8 of W2
+constexpr uint32_t IDESC = make_idesc_f16(128, RPC);
 constexpr int TM_D2 = 4 * RPC;               // TMEM column of the ctx accumulator (after the 4 hidden tiles)
 
 struct RowState {
@@ -116,7 +123,9 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
                   float* __restrict__ energy, uint32_t* __restrict__ saved_mask, float* __restrict__ saved_veh,
                   int32_t* __restrict__ steps_used, int32_t* __restrict__ t_max, int32_t* __restrict__ status) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment (swizzle atoms) by pointer arithmetic on the __shared__ array itself: the compiler keeps the
+  // address space, so every access below is an LDS/STS (an integer round trip degrades them to generic LD/ST)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* B1 = smem;                                  // running-max planes   [kb][plane][row][128 B]
   unsigned char* B2 = smem + ACT_BYTES;                      // hidden tile planes   [kb][plane][row][128 B]
   float (*ctx)[D] = reinterpret_cast<float (*)[D]>(B2);      // FF_tour output (aliases B2 once GEMM2 has retired)
@@ -126,6 +135,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
   const int Tcap = cfg.max_steps;
   const int nblk = (S + 31) >> 5;
   const float sqrt_d = sqrtf((float)D);
+  const bool fastdiv = (phys.div_mode == 0) && (phys.velocity == 50.f);   // call-free look-ahead arithmetic is exact
 
   if (tid == 0) {
     for (int s = 0; s < WSTAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
@@ -177,9 +187,9 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
       // zeros before the first pick (:224): exact copy and both operand planes
       if (valid) __stcg(reinterpret_cast<float4*>(m_ws + (size_t)row * D) + lane, make_float4(0.f, 0.f, 0.f, 0.f));
       {
-        unsigned char* p = B1 + (lane >> 3) * (2 * KBLK) + lr * 128 + ((lane & 7) << 4);
-        *reinterpret_cast<uint4*>(p) = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(p + KBLK) = make_uint4(0u, 0u, 0u, 0u);
+        unsigned char* p = B1 + (lane >> 4) * (2 * KBLK) + lr * 128 + ((lane & 15) << 3);
+        *reinterpret_cast<uint2*>(p) = make_uint2(0u, 0u);
+        *reinterpret_cast<uint2*>(p + KBLK) = make_uint2(0u, 0u);
       }
       if (lane == 0) {
         RowState& rs = sm.rs[lr];
@@ -223,20 +233,21 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
 
     // =========================== FF_tour on the tensor cores ===========================
     if (wid == ROW_WARPS) {
-      // ---- TMA producer: 16 stages of W1max (tile j, K block kb), then 16 stages of W2 (K block) ----
+      // ---- TMA producer: 8 stages of W1max (tile j, K block kb of 64), then 8 stages of W2 (K block of 64) ----
       if (lane == 0) {
         if (t == 0) sm.next_row = 0;
-        for (int i = 0; i < 32; ++i, ++it) {
+#pragma unroll 1
+        for (int i = 0; i < NSTAGE_STEP; ++i, ++it) {
           const int s = it % WSTAGES;
           mbar_wait(&sm.empty[s], ((it / WSTAGES) & 1) ^ 1);
           unsigned char* st = ring + s * WSTAGE;
           mbar_expect_tx(&sm.full[s], WSTAGE);
-          if (i < 16) {
-            tma_load_2d(st, &maps.w1h, &sm.full[s], (i & 3) * 32, (i >> 2) * 128);
-            tma_load_2d(st + WPLANE, &maps.w1l, &sm.full[s], (i & 3) * 32, (i >> 2) * 128);
+          if (i < 8) {
+            tma_load_2d(st, &maps.w1h, &sm.full[s], (i & 1) * 64, (i >> 1) * 128);
+            tma_load_2d(st + WPLANE, &maps.w1l, &sm.full[s], (i & 1) * 64, (i >> 1) * 128);
           } else {
-            tma_load_2d(st, &maps.w2h, &sm.full[s], (i - 16) * 32, 0);
-            tma_load_2d(st + WPLANE, &maps.w2l, &sm.full[s], (i - 16) * 32, 0);
+            tma_load_2d(st, &maps.w2h, &sm.full[s], (i - 8) * 64, 0);
+            tma_load_2d(st + WPLANE, &maps.w2l, &sm.full[s], (i - 8) * 64, 0);
           }
         }
       }
@@ -244,9 +255,11 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
       // ---- MMA issuer ----
       if (lane == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
         for (int j = 0; j < 4; ++j) {                        // GEMM1: hidden tile j (features 128j..128j+127)
           const uint32_t d_tmem = tmem_base + j * RPC;
-          for (int kb = 0; kb < 4; ++kb, ++it) {
+#pragma unroll 1
+          for (int kb = 0; kb < 2; ++kb, ++it) {
             const int s = it % WSTAGES;
             mbar_wait(&sm.full[s], (it / WSTAGES) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -256,19 +269,21 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
             for (int k = 0; k < 4; ++k) {
               const uint64_t dah = umma_desc(a_hi + k * 32), dal = umma_desc(a_lo + k * 32);
               const uint64_t dbh = umma_desc(b_hi + k * 32), dbl = umma_desc(b_lo + k * 32);
-              umma_tf32(d_tmem, dah, dbh, (kb | k) ? 1u : 0u, IDESC);
-              umma_tf32(d_tmem, dal, dbh, 1u, IDESC);
-              umma_tf32(d_tmem, dah, dbl, 1u, IDESC);
+              umma_f16(d_tmem, dah, dbh, (kb | k) ? 1u : 0u, IDESC);
+              umma_f16(d_tmem, dal, dbh, 1u, IDESC);
+              umma_f16(d_tmem, dah, dbl, 1u, IDESC);
             }
             umma_commit(&sm.empty[s]);
           }
           umma_commit(&sm.d1_full[j]);
         }
         const uint32_t d2 = tmem_base + TM_D2;
-        for (int j = 0; j < 4; ++j, ++n_bf) {                // GEMM2: K blocks 4j..4j+3 = hidden tile j
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j, ++n_bf) {                // GEMM2: K blocks 2j, 2j+1 (of 64) = hidden tile j
           mbar_wait(&sm.b2_full, n_bf & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int kb = 0; kb < 4; ++kb, ++it) {
+#pragma unroll 1
+          for (int kb = 0; kb < 2; ++kb, ++it) {
             const int s = it % WSTAGES;
             mbar_wait(&sm.full[s], (it / WSTAGES) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -278,9 +293,9 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
             for (int k = 0; k < 4; ++k) {
               const uint64_t dah = umma_desc(a_hi + k * 32), dal = umma_desc(a_lo + k * 32);
               const uint64_t dbh = umma_desc(b_hi + k * 32), dbl = umma_desc(b_lo + k * 32);
-              umma_tf32(d2, dah, dbh, (j | kb | k) ? 1u : 0u, IDESC);
-              umma_tf32(d2, dal, dbh, 1u, IDESC);
-              umma_tf32(d2, dah, dbl, 1u, IDESC);
+              umma_f16(d2, dah, dbh, (j | kb | k) ? 1u : 0u, IDESC);
+              umma_f16(d2, dal, dbh, 1u, IDESC);
+              umma_f16(d2, dah, dbl, 1u, IDESC);
             }
             umma_commit(&sm.empty[s]);
           }
@@ -292,6 +307,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
       // ---- epilogue / converters: thread = (TMEM lane = feature 32q + lane, 16 rows 16cg..16cg+15) ----
       const int q = wid & 3, cg = wid >> 2;
       const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+#pragma unroll 1
       for (int j = 0; j < 4; ++j) {
         const int f = j * 128 + q * 32 + lane;
         const float bb = __ldg(w.b1 + f), wv0 = __ldg(w.w1_veh + f), wv1 = __ldg(w.w1_veh + FF + f), wv2 = __ldg(w.w1_veh + 2 * FF + f);
@@ -300,18 +316,20 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         uint32_t v[16];
         tmem_ld16(tmem_base + lane_base + j * RPC + cg * 16, v);
         if (j > 0) { mbar_wait(&sm.b2_empty, n_be & 1); ++n_be; }
-        unsigned char* pb = B2 + q * (2 * KBLK) + ((lane & 3) << 2);
+        // feature 32q + lane of the tile = element (q & 1) * 32 + lane of K block q >> 1: 2 bytes at k * 2
+        unsigned char* pb = B2 + (q >> 1) * (2 * KBLK) + ((lane & 7) << 1);
+        const int chunk = (q & 1) * 4 + (lane >> 3);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int r = cg * 16 + i;
           const float4 vh = *reinterpret_cast<const float4*>(&sm.veh[r][0]);
-          float x = fmaf(wv2, vh.z, fmaf(wv1, vh.y, fmaf(wv0, vh.x, bb))) + __uint_as_float(v[i]);
+          float x = fmaf(__uint_as_float(v[i]), w.w1_inv_scale, fmaf(wv2, vh.z, fmaf(wv1, vh.y, fmaf(wv0, vh.x, bb))));
           x = fmaxf(x, 0.f);
-          const uint32_t hi = to_tf32(x);
-          const uint32_t lo = to_tf32(x - __uint_as_float(hi));
-          unsigned char* p = pb + r * 128 + (((lane >> 2) ^ (r & 7)) << 4);
-          *reinterpret_cast<uint32_t*>(p) = hi;
-          *reinterpret_cast<uint32_t*>(p + KBLK) = lo;
+          const __half hi = __float2half_rn(x);
+          const __half lo = __float2half_rn(x - __half2float(hi));
+          unsigned char* p = pb + r * 128 + ((chunk ^ (r & 7)) << 4);
+          *reinterpret_cast<__half*>(p) = hi;
+          *reinterpret_cast<__half*>(p + KBLK) = lo;
         }
         fence_async_smem();
         mbar_arrive(&sm.b2_full);
@@ -323,7 +341,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         uint32_t v[16];
         tmem_ld16(tmem_base + lane_base + TM_D2 + cg * 16, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) ctx[cg * 16 + i][q * 32 + lane] = __uint_as_float(v[i]);
+        for (int i = 0; i < 16; ++i) ctx[cg * 16 + i][q * 32 + lane] = __uint_as_float(v[i]) * w.w2_inv_scale;
       }
       if (tid == 0) sm.next_row = 0;
     }
@@ -368,6 +386,10 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           nf += __popc(bits);
         }
         __syncwarp();
+        // pad the list to a multiple of 16 with its last node: the 8- / 16-wide passes below then need no bounds checks
+        // (a duplicate changes neither the running maximum nor, with a zero weight, the weighted sum)
+        if (lane < 16 && nf + lane < ((nf + 15) & ~15)) ws.list[nf + lane] = ws.list[nf - 1];
+        __syncwarp();
         // Just-in-time L2 prefetch (fire-and-forget, no registers): every pass requests ALL of its records one pass
         // ahead of the demand loads - K here, V when the softmax starts, logit-K when the V pass starts - so the 8-deep
         // demand batches find their lines in L2.  Requesting everything up front, or the next row's records, measured
@@ -398,14 +420,15 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         for (int i0 = 0; i0 < nf; i0 += CH) {
           float4 kv[CH];
 #pragma unroll
-          for (int a = 0; a < CH; ++a) kv[a] = ldg4(kvlb + (size_t)ws.list[min(i0 + a, nf - 1)] * 384 + lane * 4);
+          for (int a = 0; a < CH; ++a) kv[a] = ldg4(kvlb + (size_t)ws.list[i0 + a] * 384 + lane * 4);
 #pragma unroll
           for (int a = 0; a < CH; ++a) {
             float p = fmaf(q[3], kv[a].w, fmaf(q[2], kv[a].z, fmaf(q[1], kv[a].y, q[0] * kv[a].x)));
             p += __shfl_xor_sync(FULL, p, 1);
             p += __shfl_xor_sync(FULL, p, 2);
             p *= 0.25f;
-            if (i0 + a < nf) { cmx = fmaxf(cmx, p); if (sub == 0) ws.pc[hd][i0 + a] = p; }
+            cmx = fmaxf(cmx, p);
+            if (sub == 0) ws.pc[hd][i0 + a] = p;
           }
         }
         __syncwarp();
@@ -423,6 +446,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           for (int i = sub; i < nf; i += 4) { const float e = expf(ws.pc[hd][i] - cmx); ws.pc[hd][i] = e; sum += e; }
           sum += __shfl_xor_sync(FULL, sum, 1);
           sum += __shfl_xor_sync(FULL, sum, 2);               // the division by `sum` is applied to the 4 head outputs below
+          if (sub == 0) { for (int i = nf; i < ((nf + 7) & ~7); ++i) ws.pc[hd][i] = 0.f; }   // padded entries weigh nothing
         }
         __syncwarp();
         RT_MARK(2);
@@ -440,9 +464,8 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
             float4 vv[CH]; float pr[CH];
 #pragma unroll
             for (int a = 0; a < CH; ++a) {
-              const int ii = min(i0 + a, nf - 1);
-              vv[a] = ldg4(kvlb + (size_t)ws.list[ii] * 384 + 128 + lane * 4);
-              pr[a] = (i0 + a < nf) ? ws.pc[hd][ii] : 0.f;
+              vv[a] = ldg4(kvlb + (size_t)ws.list[i0 + a] * 384 + 128 + lane * 4);
+              pr[a] = ws.pc[hd][i0 + a];
             }
 #pragma unroll
             for (int a = 0; a < CH; ++a) {
@@ -450,8 +473,8 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
               hv[2] = fmaf(pr[a], vv[a].z, hv[2]); hv[3] = fmaf(pr[a], vv[a].w, hv[3]);
             }
           }
-          *reinterpret_cast<float4*>(&ws.heads[lane * 4]) =
-              make_float4(__fdiv_rn(hv[0], sum), __fdiv_rn(hv[1], sum), __fdiv_rn(hv[2], sum), __fdiv_rn(hv[3], sum));
+          const float inv = div_generic(1.f, sum);           // one IEEE division per head, then 4 multiplies
+          *reinterpret_cast<float4*>(&ws.heads[lane * 4]) = make_float4(hv[0] * inv, hv[1] * inv, hv[2] * inv, hv[3] * inv);
         }
         __syncwarp();
         RT_MARK(3);
@@ -466,8 +489,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
             float4 lv[4][4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const int ii = min(i0 + u * 4 + grp, nf - 1);
-              const float* p = kvlb + (size_t)ws.list[ii] * 384 + 256 + s8 * 4;
+              const float* p = kvlb + (size_t)ws.list[i0 + u * 4 + grp] * 384 + 256 + s8 * 4;
 #pragma unroll
               for (int c = 0; c < 4; ++c) lv[u][c] = ldg4(p + c * 32);
             }
@@ -485,10 +507,10 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
             }
             // one copy of the divide / tanh / divide tail: lane (grp, s8 < 4) finishes node i0 + 4*s8 + grp
             const int i = i0 + s8 * 4 + grp;
-            if (s8 < 4 && i < nf) {
-              float z = __fdiv_rn(sel4(au, s8), sqrt_d);
+            if (s8 < 4) {                                    // (padded positions compute a duplicate nobody reads)
+              float z = div_generic(sel4(au, s8), sqrt_d);
               if (cfg.tanh_clipping > 0.f) z = tanhf(z) * cfg.tanh_clipping;
-              ws.logit[i] = __fdiv_rn(z, cfg.temp);
+              ws.logit[i] = div_generic(z, cfg.temp);
             }
           }
         }
@@ -623,18 +645,17 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           reward[o] = phys.objective ? dist : e;
           if (energy) energy[o] = e;
         }
-        // ---- running max of visited embeddings (route_feature :207-214): exact copy + TF32 (hi, lo) operand planes ----
+        // ---- running max of visited embeddings (route_feature :207-214): exact copy + fp16 (hi, lo) operand planes ----
         {
           if (t == 0) mm = ec;
           else { mm.x = fmaxf(mm.x, ec.x); mm.y = fmaxf(mm.y, ec.y); mm.z = fmaxf(mm.z, ec.z); mm.w = fmaxf(mm.w, ec.w); }
           __stcg(reinterpret_cast<float4*>(m_ws + (size_t)row * D) + lane, mm);
-          uint4 hi, lo;
-          hi.x = to_tf32(mm.x); hi.y = to_tf32(mm.y); hi.z = to_tf32(mm.z); hi.w = to_tf32(mm.w);
-          lo.x = to_tf32(mm.x - __uint_as_float(hi.x)); lo.y = to_tf32(mm.y - __uint_as_float(hi.y));
-          lo.z = to_tf32(mm.z - __uint_as_float(hi.z)); lo.w = to_tf32(mm.w - __uint_as_float(hi.w));
-          unsigned char* p = B1 + (lane >> 3) * (2 * KBLK) + lr * 128 + (((lane & 7) ^ (lr & 7)) << 4);
-          *reinterpret_cast<uint4*>(p) = hi;
-          *reinterpret_cast<uint4*>(p + KBLK) = lo;
+          const __half2 h01 = __floats2half2_rn(mm.x, mm.y), h23 = __floats2half2_rn(mm.z, mm.w);
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const __half2 l01 = __floats2half2_rn(mm.x - f01.x, mm.y - f01.y), l23 = __floats2half2_rn(mm.z - f23.x, mm.w - f23.y);
+          unsigned char* p = B1 + (lane >> 4) * (2 * KBLK) + lr * 128 + ((((lane & 15) >> 1) ^ (lr & 7)) << 4) + ((lane & 1) << 3);
+          *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+          *reinterpret_cast<uint2*>(p + KBLK) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
         }
         RT_MARK(6);
         // ---- new mask (problems/EVRP.py:105-223) ----
@@ -669,8 +690,13 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
               if (combined) mbit = (j == 0);
             }
             if (__any_sync(FULL, mbit)) {                  // look-ahead rules 5-7 only where something is still open
-              if (mbit && !reachable(phys, j, F, load, load, dm, soc, tim, sel4(dcj, jb), sel4(gcj, jb), sel4(d0j, jb),
-                                     sel4(g0j, jb), sel4(d3j, jb), sel4(s3j, jb), d4)) mbit = false;
+              const float a_dc = sel4(dcj, jb), a_gc = sel4(gcj, jb), a_d0 = sel4(d0j, jb), a_g0 = sel4(g0j, jb),
+                          a_d3 = sel4(d3j, jb), a_s3 = sel4(s3j, jb);
+              bool bad = !fastdiv;
+              bool ok = reachable_fast(phys, j, F, load, load, dm, soc, tim, a_dc, a_gc, a_d0, a_g0, a_d3, a_s3, d4, bad);
+              if (__any_sync(FULL, bad && mbit))           // out-of-range operand or another divisor: generic IEEE division
+                ok = reachable_generic(phys, j, F, load, load, dm, soc, tim, a_dc, a_gc, a_d0, a_g0, a_d3, a_s3, d4);
+              if (!ok) mbit = false;
             }
             if (j > F && mbit) cust_ok = true;
             const uint32_t bal = __ballot_sync(FULL, mbit);
@@ -693,7 +719,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           if (done) { rs.done = 1; steps_used[row] = t + 1; atomicMax(t_max, t + 1); }
           else {
             // vehicle scalars of the next step (:215-222) + trace
-            const float v1 = __fdiv_rn(soc, phys.start_soc), v2 = __fdiv_rn(tim, phys.t_limit);
+            const float v1 = div_generic(soc, phys.start_soc), v2 = div_generic(tim, phys.t_limit);
             sm.veh[lr][0] = load; sm.veh[lr][1] = v1; sm.veh[lr][2] = v2;
             const size_t o = (size_t)row * Tcap + t + 1;
             if (saved_veh) { float* sv = saved_veh + o * 3; sv[0] = load; sv[1] = v1; sv[2] = v2; }
@@ -743,10 +769,10 @@ int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, cons
   if (!w->w1max_hi || !w->w1max_lo || !w->w2_hi || !w->w2_lo) return -EVRP_E_BADARG;
   Maps maps;
   int rc;
-  if ((rc = tc::make_weight_map(&maps.w1h, w->w1max_hi, FF, D, 0, 128))) return rc;
-  if ((rc = tc::make_weight_map(&maps.w1l, w->w1max_lo, FF, D, 0, 128))) return rc;
-  if ((rc = tc::make_weight_map(&maps.w2h, w->w2_hi, D, FF, 0, 128))) return rc;
-  if ((rc = tc::make_weight_map(&maps.w2l, w->w2_lo, D, FF, 0, 128))) return rc;
+  if ((rc = tc::make_weight_map_f16(&maps.w1h, w->w1max_hi, FF, D, 128))) return rc;
+  if ((rc = tc::make_weight_map_f16(&maps.w1l, w->w1max_lo, FF, D, 128))) return rc;
+  if ((rc = tc::make_weight_map_f16(&maps.w2h, w->w2_hi, D, FF, 128))) return rc;
+  if ((rc = tc::make_weight_map_f16(&maps.w2l, w->w2_lo, D, FF, 128))) return rc;
   const int rows = B * cfg->n_replicas;
   const int mode = forced_actions ? 2 : (cfg->decode_type == EVRP_DECODE_SAMPLE ? 1 : 0);
   auto kern = mode == 2 ? rollout_tc_kernel<2> : mode == 1 ? rollout_tc_kernel<1> : rollout_tc_kernel<0>;

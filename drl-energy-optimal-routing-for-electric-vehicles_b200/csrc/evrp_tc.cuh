@@ -53,6 +53,13 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// kind::f16 (fp16 operands, fp32 accumulation): 16 K elements (32 bytes of a swizzle row) per instruction
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
@@ -74,6 +81,14 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+
+// kind::f16 instruction descriptor: D=f32 [4,6)=1, A=B=f16 (format 0), K-major, N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// host: TMA map of a row-major fp16 matrix [rows][K], box = 64 (K) x box_rows, 128-byte swizzle
+int make_weight_map_f16(CUtensorMap* map, const void* W, int rows, int K, int box_rows);
 
 // host: TMA map of a row-major fp32 matrix [rows][ld], box = 32 (K) x box_rows, 128-byte swizzle, OOB rows zero-filled
 int make_weight_map(CUtensorMap* map, const float* W, int rows, int K, int ld, int box_rows);

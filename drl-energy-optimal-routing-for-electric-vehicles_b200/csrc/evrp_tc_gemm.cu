@@ -59,7 +59,9 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
                   const __grid_constant__ CUtensorMap mapA, const float* __restrict__ A, int lda, float* __restrict__ C, int ldc, int M, int K, int n_chunks,
                   Epilogue ep) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment (swizzle atoms) by pointer arithmetic on the __shared__ array itself: the compiler keeps the
+  // address space, so every access below is an LDS/STS (an integer round trip degrades them to generic LD/ST)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   // carve: [resident W: (K/32) x (hi,lo) planes] [ring: STAGES x (A hi, A lo [, W hi, W lo])] [barriers]
   const int KB = K / BKB;
   unsigned char* wres = smem;
@@ -338,6 +340,19 @@ int make_weight_map(CUtensorMap* map, const float* W, int N, int K, int ld, int 
   cuuint32_t box[2] = {BKB, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)W, dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(int)(2000 + r);
+}
+
+int make_weight_map_f16(CUtensorMap* map, const void* W, int N, int K, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return -EVRP_E_BADARG;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)W, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -(int)(2000 + r);

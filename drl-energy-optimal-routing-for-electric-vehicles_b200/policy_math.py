@@ -52,6 +52,19 @@ def split_tf32(w):
     return hi.contiguous(), lo.contiguous()
 
 
+def split_f16(w):
+    """w (fp32) -> (hi, lo, inv_scale): fp16 planes of s*w with s a power of two chosen so that max|s*w| ~ 2^12
+    (keeps the lo plane out of the fp16 subnormal range); s*w = hi + lo to 22 significant bits."""
+    w = w.detach().float().contiguous()
+    amax = float(w.abs().max()) if w.numel() else 1.0
+    e = 12 - math.frexp(amax)[1] if amax > 0 else 0
+    e = max(-14, min(24, e))
+    ws = w * (2.0 ** e)                               # exact
+    hi = ws.half()
+    lo = (ws - hi.float()).half()
+    return hi.contiguous(), lo.contiguous(), 2.0 ** (-e)
+
+
 def pack_weights(model):
     keep = {}
     ew = _lib.EncoderWeights()
@@ -99,10 +112,13 @@ def pack_weights(model):
     dw.b1 = dev("b1", model.FF_tour[0].bias)
     dw.w2 = dev("w2", model.FF_tour[2].weight.t())
     dw.b2 = dev("b2", model.FF_tour[2].bias)
-    hi, lo = split_tf32(model.FF_tour[0].weight[:, 128:])
-    dw.w1max_hi, dw.w1max_lo = dev("w1max_hi", hi), dev("w1max_lo", lo)
-    hi, lo = split_tf32(model.FF_tour[2].weight)
-    dw.w2_hi, dw.w2_lo = dev("w2_hi", hi), dev("w2_lo", lo)
+    def dev_raw(name, t):                              # fp16 planes travel as they are
+        keep[name] = t
+        return _lib.ptr(t) if t.is_cuda else None
+    hi, lo, inv = split_f16(model.FF_tour[0].weight[:, 128:])
+    dw.w1max_hi, dw.w1max_lo, dw.w1_inv_scale = dev_raw("w1max_hi", hi), dev_raw("w1max_lo", lo), inv
+    hi, lo, inv = split_f16(model.FF_tour[2].weight)
+    dw.w2_hi, dw.w2_lo, dw.w2_inv_scale = dev_raw("w2_hi", hi), dev_raw("w2_lo", lo), inv
     dw.ff_mode = int(getattr(model, "ff_mode", 0))
     keep["enc_struct"], keep["dec_struct"] = ew, dw
     return keep

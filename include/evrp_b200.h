@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 7
+#define EVRP_ABI_VERSION 8
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -148,12 +148,14 @@ typedef struct {
   const float *b1;       /* [512]      FF_tour.0.bias                                                   */
   const float *w2;       /* [512,128]  FF_tour.2.weight^T                                               */
   const float *b2;       /* [128]      FF_tour.2.bias                                                   */
-  /* tcgen05 path (ff_mode 0): the two FF_tour matrices in nn.Linear layout [out][in], split into TF32 planes
-     (round-to-nearest, w = hi + lo; evrp_b200/policy_math.py::split_tf32), streamed by TMA every decode step   */
-  const float *w1max_hi, *w1max_lo;   /* [512,128]  FF_tour.0.weight[:, 128:]                                   */
-  const float *w2_hi, *w2_lo;         /* [128,512]  FF_tour.2.weight                                            */
-  int32_t ff_mode;       /* 0: FF_tour on tcgen05 tensor cores, 3xTF32 (fp32-faithful), one 576-thread CTA per SM;
-                            1: fp32 FFMA inside a 256-thread CTA (2 per SM)                                     */
+  /* tcgen05 path (ff_mode 0): the two FF_tour matrices in nn.Linear layout [out][in], each scaled by a power of two
+     (exact) and split into two fp16 planes with round-to-nearest, s*w = hi + lo: 22 significant bits, the same as a
+     TF32 pair at half the bytes (evrp_b200/policy_math.py::split_f16); streamed by TMA every decode step           */
+  const void *w1max_hi, *w1max_lo;    /* fp16 [512,128]  w1_scale * FF_tour.0.weight[:, 128:]                      */
+  const void *w2_hi, *w2_lo;          /* fp16 [128,512]  w2_scale * FF_tour.2.weight                               */
+  float w1_inv_scale, w2_inv_scale;   /* 1 / scale (powers of two), applied to the fp32 accumulators               */
+  int32_t ff_mode;       /* 0: FF_tour on tcgen05 tensor cores (3 x fp16 products, fp32-faithful), one 576-thread CTA
+                            per SM; 1: fp32 FFMA inside a 256-thread CTA (2 per SM)                              */
 } evrp_decoder_weights;
 
 #define EVRP_DECODE_GREEDY 0
