@@ -45,7 +45,7 @@ constexpr int ACT_BYTES = 2 * 2 * KBLK;      // 32 KB: 2 K blocks (128 channels)
 constexpr int WPLANE = 128 * 128;            // 16 KB: [128 x 64 fp16] weight tile plane
 constexpr int WSTAGE = 2 * WPLANE;           // hi + lo
 #ifndef EVRP_WSTAGES
-#define EVRP_WSTAGES 4
+#define EVRP_WSTAGES 3
 #endif
 constexpr int WSTAGES = EVRP_WSTAGES;
 constexpr int NSTAGE_STEP = 16;              // stages per decode step: 8 of W1max (4 tiles x 2 K blocks), 8 of W2
@@ -74,14 +74,14 @@ struct __align__(16) Ctl {
   float veh[RPC][4];             // load, soc/Start_SOC, time/t_limit          (:215-222)
   uint64_t full[WSTAGES], empty[WSTAGES];
   uint64_t d1_full[4];           // hidden tile j accumulated (tcgen05.commit)
-  uint64_t b2_full;              // hidden tile planes written by the 512 epilogue threads
-  uint64_t b2_empty;             // GEMM2 partial over that tile retired (tcgen05.commit)
+  uint64_t b2_full[2];           // hidden tile planes (double-buffered) written by the 512 epilogue threads
+  uint64_t b2_empty[2];          // GEMM2 partial over that buffer retired (tcgen05.commit)
   uint64_t d2_full;              // ctx accumulated
   uint32_t tmem_base;
   int next_row;
 };
 
-constexpr size_t SMEM_BYTES = 2 * (size_t)ACT_BYTES + RS_BYTES + sizeof(Ctl) + 1024;
+constexpr size_t SMEM_BYTES = 3 * (size_t)ACT_BYTES + RS_BYTES + sizeof(Ctl) + 1024;
 
 #ifdef EVRP_PHASE_TIMING
 // debug build only (tools/phase_timing.py): cycles of warp 0 in [FF hidden tiles, FF ctx + sync, row phase busy, barrier wait]
@@ -127,10 +127,10 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
   // address space, so every access below is an LDS/STS (an integer round trip degrades them to generic LD/ST)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* B1 = smem;                                  // running-max planes   [kb][plane][row][128 B]
-  unsigned char* B2 = smem + ACT_BYTES;                      // hidden tile planes   [kb][plane][row][128 B]
+  unsigned char* B2 = smem + ACT_BYTES;                      // hidden tile planes   [buf][kb][plane][row][128 B]
   float (*ctx)[D] = reinterpret_cast<float (*)[D]>(B2);      // FF_tour output (aliases B2 once GEMM2 has retired)
-  unsigned char* ring = smem + 2 * ACT_BYTES;                // weight stages (FF phase) / row scratch (row phase)
-  Ctl& sm = *reinterpret_cast<Ctl*>(smem + 2 * ACT_BYTES + RS_BYTES);
+  unsigned char* ring = smem + 3 * ACT_BYTES;                // weight stages (FF phase) / row scratch (row phase)
+  Ctl& sm = *reinterpret_cast<Ctl*>(smem + 3 * ACT_BYTES + RS_BYTES);
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   const int Tcap = cfg.max_steps;
   const int nblk = (S + 31) >> 5;
@@ -140,8 +140,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
   if (tid == 0) {
     for (int s = 0; s < WSTAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
     for (int j = 0; j < 4; ++j) mbar_init(&sm.d1_full[j], 1);
-    mbar_init(&sm.b2_full, ROW_WARPS * 32);
-    mbar_init(&sm.b2_empty, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&sm.b2_full[b], ROW_WARPS * 32); mbar_init(&sm.b2_empty[b], 1); }
     mbar_init(&sm.d2_full, 1);
     sm.next_row = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -212,8 +211,6 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
   const uint32_t tmem_base = sm.tmem_base;
   int t = 0;
   uint32_t it = 0;          // weight-ring counter (producer and MMA issuer keep their own copy in step)
-  uint32_t n_bf = 0;        // b2_full phases consumed (MMA issuer)
-  uint32_t n_be = 0;        // b2_empty phases consumed (epilogue threads)
 #ifdef EVRP_PHASE_TIMING
   long long pt_acc[4] = {0, 0, 0, 0};
   long long pt_t = clock64();
@@ -279,16 +276,17 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         }
         const uint32_t d2 = tmem_base + TM_D2;
 #pragma unroll 1
-        for (int j = 0; j < 4; ++j, ++n_bf) {                // GEMM2: K blocks 2j, 2j+1 (of 64) = hidden tile j
-          mbar_wait(&sm.b2_full, n_bf & 1);
+        for (int j = 0; j < 4; ++j) {                         // GEMM2: K blocks 2j, 2j+1 (of 64) = hidden tile j
+          mbar_wait(&sm.b2_full[j & 1], (j >> 1) & 1);           // each buffer completes twice per step
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const unsigned char* hb = B2 + (j & 1) * ACT_BYTES;
 #pragma unroll 1
           for (int kb = 0; kb < 2; ++kb, ++it) {
             const int s = it % WSTAGES;
             mbar_wait(&sm.full[s], (it / WSTAGES) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_hi = smem_u32(ring + s * WSTAGE), a_lo = a_hi + WPLANE;
-            const uint32_t b_hi = smem_u32(B2 + kb * (2 * KBLK)), b_lo = b_hi + KBLK;
+            const uint32_t b_hi = smem_u32(hb + kb * (2 * KBLK)), b_lo = b_hi + KBLK;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t dah = umma_desc(a_hi + k * 32), dal = umma_desc(a_lo + k * 32);
@@ -299,7 +297,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
             }
             umma_commit(&sm.empty[s]);
           }
-          if (j < 3) umma_commit(&sm.b2_empty);
+          if (j < 2) umma_commit(&sm.b2_empty[j]);             // the converters of tile j + 2 reuse this buffer
         }
         umma_commit(&sm.d2_full);
       }
@@ -315,9 +313,9 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t v[16];
         tmem_ld16(tmem_base + lane_base + j * RPC + cg * 16, v);
-        if (j > 0) { mbar_wait(&sm.b2_empty, n_be & 1); ++n_be; }
+        if (j >= 2) mbar_wait(&sm.b2_empty[j & 1], t & 1);     // GEMM2 over tile j - 2 has drained this buffer
         // feature 32q + lane of the tile = element (q & 1) * 32 + lane of K block q >> 1: 2 bytes at k * 2
-        unsigned char* pb = B2 + (q >> 1) * (2 * KBLK) + ((lane & 7) << 1);
+        unsigned char* pb = B2 + (j & 1) * ACT_BYTES + (q >> 1) * (2 * KBLK) + ((lane & 7) << 1);
         const int chunk = (q & 1) * 4 + (lane >> 3);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -332,7 +330,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           *reinterpret_cast<__half*>(p + KBLK) = lo;
         }
         fence_async_smem();
-        mbar_arrive(&sm.b2_full);
+        mbar_arrive(&sm.b2_full[j & 1]);
       }
       PT_MARK(0);
       mbar_wait(&sm.d2_full, t & 1);
