@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EVRP_B200_LIB") or os.path.join(_HERE, "libevrp_b200.so")   # override: instrumented debug builds (tools/)
 
 EVRP_MAX_S = 128
-ABI_VERSION = 8
+ABI_VERSION = 9
 EVRP_MAX_LAYERS = 8
 ST_NAN_LOGIT, ST_INFEASIBLE_PICK, ST_STEP_CAP, ST_NONUNIFORM_DYNAMIC, ST_NO_FEASIBLE = 1, 2, 4, 8, 16
 DECODE_GREEDY, DECODE_SAMPLE = 0, 1
@@ -37,7 +37,7 @@ class EncoderWeights(C.Structure):
     _fields_ = [(n, _FP) for n in ("depot_w", "depot_b", "station_w", "station_b", "cust_w", "cust_b")] + \
         [("n_layers", C.c_int32), ("layers", LayerWeights * EVRP_MAX_LAYERS),
          ("node_proj", _FP), ("fixed_ctx_w", _FP), ("node_proj_hi", _FP), ("node_proj_lo", _FP),
-         ("gemm_mode", C.c_int32)]
+         ("gemm_mode", C.c_int32), ("attn_mode", C.c_int32)]
 
 
 class DecoderWeights(C.Structure):

@@ -266,6 +266,9 @@ fixed_context_kernel(const float* __restrict__ emb, int S, const float* __restri
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// evrp_attn_tc.cu
+int launch_attn_tc(const float* qkv, int B, int S, float* heads, int sm_count, cudaStream_t st);
+
 // evrp_tc_gemm.cu
 int tc_gemm(int epi, const float* A, int lda, const float* Wh, const float* Wl, float* C, int ldc, int M, int N, int K,
             const float* bias, const float* resid, int ldr, const float* scale, const float* shift, int sm_count,
@@ -327,8 +330,12 @@ int evrp_encoder_forward(const evrp_encoder_weights* w, const float* static_xy, 
     if (tcm) {
       // Q|K|V = h @ Wqkv
       if ((rc = tc_gemm(0, cur, D, L.Wqkv_hi, L.Wqkv_lo, wide, 384, M, 384, D, nullptr, nullptr, 0, nullptr, nullptr, sm_count, st))) return rc;
-      self_attention_kernel<<<B, 256, attn_smem, st>>>(wide, S, heads);
-      EVRP_LAUNCH_OK();
+      if (w->attn_mode == 0 && S > 64) {                 // (<= 64 nodes: the 128-row tiles are mostly padding)
+        if ((rc = launch_attn_tc(wide, B, S, heads, sm_count, st))) return rc;
+      } else {
+        self_attention_kernel<<<B, 256, attn_smem, st>>>(wide, S, heads);
+        EVRP_LAUNCH_OK();
+      }
       // h1 = BN1(h + heads @ Wo)
       if ((rc = tc_gemm(EPI_RESID | EPI_AFFINE, heads, D, L.Wo_hi, L.Wo_lo, other, D, M, D, D, nullptr, cur, D, L.bn1_scale, L.bn1_shift, sm_count, st))) return rc;
       // f = relu(h1 @ W1^T + b1)

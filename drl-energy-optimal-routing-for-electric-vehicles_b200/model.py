@@ -116,7 +116,8 @@ class AttentionModel(nn.Module):
         self._calls = 0
         self.last_energy = None                   # [B,T] energy of the last rollout (DM trainer's 3rd output)
         self.gemm_mode = 0                        # encoder GEMMs: 0 = tcgen05 3xTF32 (fp32-faithful), 1 = fp32 FFMA
-        self.ff_mode = 0                          # FF_tour inside the rollout kernel: 0 = tcgen05 3xTF32, 1 = fp32 FFMA
+        self.ff_mode = 0                          # FF_tour inside the rollout kernel: 0 = tcgen05 (fp16-pair split), 1 = fp32 FFMA
+        self.attn_mode = 0                        # encoder self-attention: 0 = tcgen05 3xTF32 (with gemm_mode 0), 1 = fp32 FFMA2
         self.profile_events = None                # list -> (start, end) CUDA events around each rollout kernel launch
 
     # ------------------------------------------------------------------------------------------
@@ -151,7 +152,7 @@ class AttentionModel(nn.Module):
         """Kernel-side weight layouts (k-major transposes, folded BatchNorm / project_out / tour), rebuilt only
         when a parameter or buffer changed (tensor version counters)."""
         sd = list(self.parameters()) + list(self.buffers())
-        key = (tuple(t._version for t in sd), tuple(t.data_ptr() for t in sd), self.training, self.gemm_mode, self.ff_mode)
+        key = (tuple(t._version for t in sd), tuple(t.data_ptr() for t in sd), self.training, self.gemm_mode, self.ff_mode, self.attn_mode)
         if self._pack_cache is None or self._pack_cache[0] != key:
             with torch.no_grad():
                 self._pack_cache = (key, policy_math.pack_weights(self))

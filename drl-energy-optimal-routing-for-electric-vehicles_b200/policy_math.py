@@ -104,6 +104,7 @@ def pack_weights(model):
     hi, lo = split_tf32(folded_node_projection(model))
     ew.node_proj_hi, ew.node_proj_lo = dev("node_proj_hi", hi), dev("node_proj_lo", lo)
     ew.gemm_mode = int(getattr(model, "gemm_mode", 0))
+    ew.attn_mode = int(getattr(model, "attn_mode", 0))
     ew.node_proj = dev("node_proj", folded_node_projection(model).t())
     ew.fixed_ctx_w = dev("fixed_ctx_w", model.project_fixed_context.weight.t())
     dw = _lib.DecoderWeights()

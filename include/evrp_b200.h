@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 8
+#define EVRP_ABI_VERSION 9
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -121,6 +121,8 @@ typedef struct {
   const float *fixed_ctx_w;            /* [128,128]  project_fixed_context.weight^T                         */
   const float *node_proj_hi, *node_proj_lo;   /* [384,128] TF32 planes of node_proj^T (tcgen05 path)         */
   int32_t gemm_mode;                   /* 0: tcgen05 3xTF32 (fp32-faithful, tensor cores); 1: fp32 FFMA GEMM   */
+  int32_t attn_mode;                   /* self-attention core (QK^T, softmax, PV): 0: tcgen05 3xTF32, probabilities as
+                                          the TMEM A operand (used when gemm_mode == 0); 1: fp32 FFMA2 kernel          */
 } evrp_encoder_weights;
 
 size_t evrp_encoder_workspace_bytes(int B, int S);

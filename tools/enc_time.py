@@ -12,16 +12,16 @@ m.load_state_dict({k: torch.from_numpy(v) for k, v in W.items()}); m = m.cuda().
 s, d, e = O.generate_instances(B, N, seed=1000)
 st, dy = torch.from_numpy(s).cuda(), torch.from_numpy(d).cuda()
 with torch.no_grad():
-    for mode in (0, 1):
-        m.gemm_mode = mode
+    for mode, am in ((0, 0), (0, 1), (1, 1)):
+        m.gemm_mode = mode; m.attn_mode = am
         for _ in range(2): out = m.encode(st, dy)
         ts = []
         for _ in range(5):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); out = m.encode(st, dy); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
-        print(f"N={N} B={B} gemm_mode={mode}: encoder {min(ts):.2f} ms (median {sorted(ts)[2]:.2f})")
-        if mode == 0: ref = [t.clone() for t in out]
+        print(f"N={N} B={B} gemm_mode={mode} attn_mode={am}: encoder {min(ts):.2f} ms (median {sorted(ts)[2]:.2f})")
+        if (mode, am) == (0, 0): ref = [t.clone() for t in out]
         else: print("   max |emb_tc - emb_ffma| %.3e   max |kvl| diff %.3e" % (float((out[0] - ref[0]).abs().max()), float((out[1] - ref[1]).abs().max())))
     # against the numpy oracle on a few instances
     emb_o = O.encode(W, s[:8], d[:8]) if hasattr(O, "encode") else None
