@@ -65,7 +65,7 @@ struct WarpScratch {
   unsigned char list[SP];        // feasible node indices, ascending
 };
 
-constexpr int SCRATCH_BYTES = ROW_WARPS * (int)sizeof(WarpScratch);
+constexpr int SCRATCH_BYTES = (ROW_WARPS + 2) * (int)sizeof(WarpScratch);   // the two FF-phase warps walk rows as well
 constexpr int RING_BYTES = WSTAGES * WSTAGE;
 constexpr int RS_BYTES = ((SCRATCH_BYTES > RING_BYTES ? SCRATCH_BYTES : RING_BYTES) + 1023) / 1024 * 1024;
 
@@ -348,7 +348,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
     PT_MARK(1);
 
     // =========================== per-row phase: each row warp walks rows ===========================
-    if (wid < ROW_WARPS) {
+    {                                                      // all 18 warps (the TMA / MMA warps are idle in this phase)
       WarpScratch& ws = reinterpret_cast<WarpScratch*>(ring)[wid];
       const int hd = lane >> 2, sub = lane & 3;
 #pragma unroll 1
