@@ -176,10 +176,20 @@ def main():
             emb, kvl, fixed = model.encode(st, dy)
             return model.rollout(emb, kvl, fixed, dy, D, G)
 
+    host_out = {}
+
     def step_e2e():
+        """public API call with host inputs (pinned) and the results (tour, cost) read back into pinned host memory"""
         with torch.no_grad():
             pi, ll, R = model((st_h, dy_h, D, G))
-            return R.sum(1).cpu(), pi.cpu()
+            cost = R.sum(1)
+            if "pi" not in host_out or host_out["pi"].shape != pi.shape:
+                host_out["pi"] = torch.empty(pi.shape, dtype=pi.dtype).pin_memory()
+                host_out["cost"] = torch.empty(cost.shape, dtype=cost.dtype).pin_memory()
+            host_out["pi"].copy_(pi, non_blocking=True)
+            host_out["cost"].copy_(cost, non_blocking=True)
+            torch.cuda.synchronize()
+            return host_out["cost"], host_out["pi"]
 
     sampler = ClockSampler(local)                     # nvidia-smi takes a moment to start: launched before the warm-up
     for _ in range(max(a.warmup, 3)):

@@ -166,14 +166,14 @@ class AttentionModel(nn.Module):
             input = input["data"]
         if len(input) == 4:                              # nets/DRLModel.py:118-123
             static, dynamic, distances, slope = input
-            distances = distances.to(dev, torch.float32).contiguous()
-            slope = slope.to(dev, torch.float32).contiguous()
-            static = static.to(dev, torch.float32).contiguous()
+            distances = distances.to(dev, torch.float32, non_blocking=True).contiguous()
+            slope = slope.to(dev, torch.float32, non_blocking=True).contiguous()
+            static = static.to(dev, torch.float32, non_blocking=True).contiguous()
         else:                                            # nets/DRLModel.py:124-133
             static, dynamic, elevations = input
-            static = static.to(dev, torch.float32).contiguous()
-            distances, slope = policy_math.pairwise_matrices(static, elevations.to(dev, torch.float32))
-        dynamic = dynamic.to(dev, torch.float32).contiguous()
+            static = static.to(dev, torch.float32, non_blocking=True).contiguous()
+            distances, slope = policy_math.pairwise_matrices(static, elevations.to(dev, torch.float32, non_blocking=True))
+        dynamic = dynamic.to(dev, torch.float32, non_blocking=True).contiguous()
         return static, dynamic, distances, slope
 
     # ------------------------------------------------------------------------------------------
