@@ -118,7 +118,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
                   const float* __restrict__ emb, const float* __restrict__ kvl, const float* __restrict__ fixed_ctx,
                   const float* __restrict__ dynamic0, const float* __restrict__ Dm, const float* __restrict__ Gm,
                   float* station_ws, float* dem_ws, float* m_ws, int B, int S, int F, int rows_total, int rows_per_cta,
-                  int pf_lines, const int64_t* __restrict__ forced, const float* __restrict__ uniforms,
+                  int pf_lines, int walkers, const int64_t* __restrict__ forced, const float* __restrict__ uniforms,
                   int64_t* __restrict__ pi, float* __restrict__ ll, float* __restrict__ reward,
                   float* __restrict__ energy, uint32_t* __restrict__ saved_mask, float* __restrict__ saved_veh,
                   int32_t* __restrict__ steps_used, int32_t* __restrict__ t_max, int32_t* __restrict__ status) {
@@ -348,7 +348,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
     PT_MARK(1);
 
     // =========================== per-row phase: each row warp walks rows ===========================
-    {                                                      // all 18 warps (the TMA / MMA warps are idle in this phase)
+    if (wid < walkers) {                                   // (the TMA / MMA warps are idle in this phase and walk rows too)
       WarpScratch& ws = reinterpret_cast<WarpScratch*>(ring)[wid];
       const int hd = lane >> 2, sub = lane & 3;
 #pragma unroll 1
@@ -787,8 +787,10 @@ int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, cons
   grid = (rows + rows_per_cta - 1) / rows_per_cta;
   static int pf_lines = -1;              // tuning knob: bit 0 K, bit 2 V, bit 3 logit-K just-in-time prefetch
   if (pf_lines < 0) { const char* l = getenv("EVRP_PF_LINES"); pf_lines = l ? atoi(l) : 13; }
+  static int walkers = -1;
+  if (walkers < 0) { const char* e = getenv("EVRP_WALKERS"); walkers = e ? atoi(e) : ROW_WARPS + 2; }
   kern<<<grid, NT, SMEM_BYTES, st>>>(maps, *phys, *w, *cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope, station_ws,
-                                     dem_ws, m_ws, B, S, F, rows, rows_per_cta, pf_lines, forced_actions, uniforms, pi, ll, reward,
+                                     dem_ws, m_ws, B, S, F, rows, rows_per_cta, pf_lines, walkers, forced_actions, uniforms, pi, ll, reward,
                                      energy, saved_mask, saved_veh, steps_used, t_max, status);
   EVRP_LAUNCH_OK();
   return 0;

@@ -195,12 +195,13 @@ def encode_torch(model, static, dynamic):
     for layer in model.embedder.layers:
         att, bn1, ff, bn2 = layer[0].module, layer[1].normalizer, layer[2].module, layer[3].normalizer
         flat = h.reshape(B * S, d)
-        Q = torch.matmul(flat, att.W_query).view(-1, B, S, att.W_query.shape[-1])
-        K = torch.matmul(flat, att.W_key).view(-1, B, S, att.W_key.shape[-1])
-        V = torch.matmul(flat, att.W_val).view(-1, B, S, att.W_val.shape[-1])
-        attn = torch.softmax(torch.matmul(Q, K.transpose(2, 3)) / math.sqrt(Q.shape[-1]), -1)
-        heads = torch.matmul(attn, V)
-        out = torch.mm(heads.permute(1, 2, 0, 3).reshape(B * S, -1), att.W_out.reshape(-1, d)).view(B, S, d)
+        Hh, _, dk = att.W_query.shape
+        # one [128,384] projection instead of 3 x 8 narrow ones (same products; autograd scatters the gradient back)
+        Wqkv = torch.cat([w.permute(1, 0, 2).reshape(d, Hh * dk) for w in (att.W_query, att.W_key, att.W_val)], 1)
+        qkv = torch.mm(flat, Wqkv).view(B, S, 3, Hh, dk).permute(2, 0, 3, 1, 4)          # [3,B,H,S,dk]
+        attn = torch.softmax(torch.matmul(qkv[0], qkv[1].transpose(2, 3)) / math.sqrt(dk), -1)
+        heads = torch.matmul(attn, qkv[2])                                               # [B,H,S,dk]
+        out = torch.mm(heads.permute(0, 2, 1, 3).reshape(B * S, Hh * dk), att.W_out.reshape(-1, d)).view(B, S, d)
         h = _batch_norm(bn1, (h + out).view(-1, d), model.training).view(B, S, d)
         h = _batch_norm(bn2, (h + ff(h)).view(-1, d), model.training).view(B, S, d)
     kvl = Fn.linear(h, folded_node_projection(model))
