@@ -35,8 +35,17 @@ namespace dtc {
 
 using namespace tc;
 
-constexpr int RPC = 64;                      // rollout rows per CTA = MMA N
-constexpr int ROW_WARPS = 16;
+#ifndef EVRP_RPC
+#define EVRP_RPC 64          // rollout rows per CTA = MMA N
+#define EVRP_ROW_WARPS 16
+#define EVRP_NB2 2           // hidden-plane staging buffers
+#define EVRP_CTAS 1          // CTAs per SM
+#define EVRP_TMEM_COLS 512
+#endif
+constexpr int RPC = EVRP_RPC;
+constexpr int ROW_WARPS = EVRP_ROW_WARPS;
+constexpr int NB2 = EVRP_NB2;
+static_assert(RPC == 4 * ROW_WARPS, "epilogue mapping: 16 rows per (quadrant, column group) warp");
 constexpr int NT = (ROW_WARPS + 2) * 32;     // 576
 constexpr int SP = EVRP_MAX_S;               // padded node count (128)
 constexpr int PSTR = SP + 4;                 // head stride of the compat buffer
@@ -81,7 +90,7 @@ struct __align__(16) Ctl {
   int next_row;
 };
 
-constexpr size_t SMEM_BYTES = 3 * (size_t)ACT_BYTES + RS_BYTES + sizeof(Ctl) + 1024;
+constexpr size_t SMEM_BYTES = (1 + NB2) * (size_t)ACT_BYTES + RS_BYTES + sizeof(Ctl) + 1024;
 
 #ifdef EVRP_PHASE_TIMING
 // debug build only (tools/phase_timing.py): cycles of warp 0 in [FF hidden tiles, FF ctx + sync, row phase busy, barrier wait]
@@ -113,7 +122,7 @@ struct Maps { CUtensorMap w1h, w1l, w2h, w2l; };
 
 // MODE: 0 greedy, 1 sample, 2 teacher-forced
 template <int MODE>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, EVRP_CTAS)
 rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
                   const float* __restrict__ emb, const float* __restrict__ kvl, const float* __restrict__ fixed_ctx,
                   const float* __restrict__ dynamic0, const float* __restrict__ Dm, const float* __restrict__ Gm,
@@ -129,8 +138,8 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
   unsigned char* B1 = smem;                                  // running-max planes   [kb][plane][row][128 B]
   unsigned char* B2 = smem + ACT_BYTES;                      // hidden tile planes   [buf][kb][plane][row][128 B]
   float (*ctx)[D] = reinterpret_cast<float (*)[D]>(B2);      // FF_tour output (aliases B2 once GEMM2 has retired)
-  unsigned char* ring = smem + 3 * ACT_BYTES;                // weight stages (FF phase) / row scratch (row phase)
-  Ctl& sm = *reinterpret_cast<Ctl*>(smem + 3 * ACT_BYTES + RS_BYTES);
+  unsigned char* ring = smem + (1 + NB2) * ACT_BYTES;                // weight stages (FF phase) / row scratch (row phase)
+  Ctl& sm = *reinterpret_cast<Ctl*>(smem + (1 + NB2) * ACT_BYTES + RS_BYTES);
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   const int Tcap = cfg.max_steps;
   const int nblk = (S + 31) >> 5;
@@ -146,7 +155,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (wid == ROW_WARPS + 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "n"(EVRP_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
 
@@ -211,6 +220,8 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
   const uint32_t tmem_base = sm.tmem_base;
   int t = 0;
   uint32_t it = 0;          // weight-ring counter (producer and MMA issuer keep their own copy in step)
+  uint32_t n_be = 0;        // b2_empty phases consumed by the converters (single staging buffer only)
+  (void)n_be;
 #ifdef EVRP_PHASE_TIMING
   long long pt_acc[4] = {0, 0, 0, 0};
   long long pt_t = clock64();
@@ -277,9 +288,9 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         const uint32_t d2 = tmem_base + TM_D2;
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {                         // GEMM2: K blocks 2j, 2j+1 (of 64) = hidden tile j
-          mbar_wait(&sm.b2_full[j & 1], (j >> 1) & 1);           // each buffer completes twice per step
+          mbar_wait(&sm.b2_full[j % NB2], NB2 == 2 ? ((j >> 1) & 1) : (j & 1));   // completions per step: 4 / NB2
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const unsigned char* hb = B2 + (j & 1) * ACT_BYTES;
+          const unsigned char* hb = B2 + (j % NB2) * ACT_BYTES;
 #pragma unroll 1
           for (int kb = 0; kb < 2; ++kb, ++it) {
             const int s = it % WSTAGES;
@@ -297,7 +308,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
             }
             umma_commit(&sm.empty[s]);
           }
-          if (j < 2) umma_commit(&sm.b2_empty[j]);             // the converters of tile j + 2 reuse this buffer
+          if (j < 4 - NB2) umma_commit(&sm.b2_empty[j % NB2]);  // the converters of tile j + NB2 reuse this buffer
         }
         umma_commit(&sm.d2_full);
       }
@@ -313,9 +324,12 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t v[16];
         tmem_ld16(tmem_base + lane_base + j * RPC + cg * 16, v);
-        if (j >= 2) mbar_wait(&sm.b2_empty[j & 1], t & 1);     // GEMM2 over tile j - 2 has drained this buffer
+        if (j >= NB2) {                                         // GEMM2 over tile j - NB2 has drained this buffer
+          if (NB2 == 2) mbar_wait(&sm.b2_empty[j & 1], t & 1);
+          else { mbar_wait(&sm.b2_empty[0], n_be & 1); ++n_be; }
+        }
         // feature 32q + lane of the tile = element (q & 1) * 32 + lane of K block q >> 1: 2 bytes at k * 2
-        unsigned char* pb = B2 + (j & 1) * ACT_BYTES + (q >> 1) * (2 * KBLK) + ((lane & 7) << 1);
+        unsigned char* pb = B2 + (j % NB2) * ACT_BYTES + (q >> 1) * (2 * KBLK) + ((lane & 7) << 1);
         const int chunk = (q & 1) * 4 + (lane >> 3);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -330,7 +344,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           *reinterpret_cast<__half*>(p + KBLK) = lo;
         }
         fence_async_smem();
-        mbar_arrive(&sm.b2_full[j & 1]);
+        mbar_arrive(&sm.b2_full[j % NB2]);
       }
       PT_MARK(0);
       mbar_wait(&sm.d2_full, t & 1);
@@ -738,7 +752,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
 #endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (wid == ROW_WARPS + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  if (wid == ROW_WARPS + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(EVRP_TMEM_COLS) : "memory");
 }
 
 }  // namespace dtc
@@ -779,9 +793,10 @@ int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, cons
   EVRP_CUDA_OK(cudaGetDevice(&dev));
   EVRP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   // balance: whole waves of one CTA per SM, rows spread evenly (<= RPC rows per CTA)
+  const int slots = EVRP_CTAS * sms;
   const int min_ctas = (rows + RPC - 1) / RPC;
-  const int waves = (min_ctas + sms - 1) / sms;
-  int grid = waves * sms;
+  const int waves = (min_ctas + slots - 1) / slots;
+  int grid = waves * slots;
   if (grid > rows) grid = rows;
   const int rows_per_cta = (rows + grid - 1) / grid;
   grid = (rows + rows_per_cta - 1) / rows_per_cta;

@@ -233,6 +233,25 @@ def test_tensor_core_ff_matches_ffma_kernel(evrp, weights, N, B):
     assert float(d_cost.max()) < 0.05
 
 
+@pytest.mark.parametrize("N,B", [(100, 1), (100, 3), (100, 149), (100, 301), (70, 200), (122, 37)])
+def test_tensor_core_attention_matches_simt_kernel(evrp, weights, N, B):
+    """Encoder with the tcgen05 self-attention kernel (QK^T 3xTF32, softmax in registers, PV with P as the TMEM A operand)
+    against the fp32 FFMA2 attention kernel, same GEMMs: batch sizes below / above the number of SMs (persistent loop,
+    idle CTAs) and node counts that leave the 128-row tiles ragged (S = 76, 106, 128)."""
+    from oracle import evrp_oracle as O
+    m, _ = make_model(evrp, N, weights)
+    s, d, e = O.generate_instances(B, N, seed=300 + N + B)
+    st, dy = torch.from_numpy(s).cuda(), torch.from_numpy(d).cuda()
+    with torch.no_grad():
+        m.attn_mode = 1
+        ref = [t.clone() for t in m.encode(st, dy)]
+        m.attn_mode = 0
+        out = m.encode(st, dy)
+    for a, b in zip(out, ref):
+        assert torch.isfinite(a).all()
+        assert float((a - b).abs().max()) < 5e-5
+
+
 def test_dm_objective(evrp, weights):
     g = load("dm_n20.npz")
     m, _ = make_model(evrp, 20, weights, obj="DM")
