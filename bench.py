@@ -122,10 +122,19 @@ def run_reference(a):
                                        f"reference path; the Python reference itself cannot travel to the GPU box)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+def _emit(line):
+    """the ONE JSON line, written to the real stdout (everything else - e.g. NCCL's version banner - goes to stderr)"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
 
 
 def main():
+    os.dup2(2, 1)                                     # libraries that print to fd 1 must not pollute the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -294,7 +303,7 @@ def main():
             r, cores, dt, Tc = cpu_port_rate(N, a.cpu_sample)
             line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{a.cpu_sample} EM-EVRP-{N} instances, greedy, numpy oracle port, {dt:.1f} s"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
