@@ -25,7 +25,13 @@ namespace evrp {
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BKB = 32;          // tile; BKB fp32 = one 128-byte swizzle row
-constexpr int STAGES = 3;
+constexpr int MAX_STAGES = 4;
+#ifndef EVRP_GEMM_STAGES
+#define EVRP_GEMM_STAGES 4
+#endif
+#ifndef EVRP_GEMM_RAW_STAGES
+#define EVRP_GEMM_RAW_STAGES 6
+#endif
 constexpr int PLANE = BM * BKB * 4;                  // 16 KB: one [128 x 32] fp32 plane
 constexpr int NTHREADS = 320;
 constexpr int EPI_BIAS = 1, EPI_RELU = 2, EPI_RESID = 4, EPI_AFFINE = 8;
@@ -37,16 +43,16 @@ struct Epilogue {
 };
 
 struct __align__(8) Barriers {
-  uint64_t full[STAGES];      // stage filled (128 converter arrivals [+1 producer arrival carrying the TMA bytes])
-  uint64_t empty[STAGES];     // stage consumed (tcgen05.commit)
+  uint64_t full[MAX_STAGES];      // stage filled (128 converter arrivals [+1 producer arrival carrying the TMA bytes])
+  uint64_t empty[MAX_STAGES];     // stage consumed (tcgen05.commit)
   uint64_t w_ready;           // resident weights landed
   uint64_t acc_full[2];       // accumulator ready for the epilogue (tcgen05.commit)
   uint64_t acc_empty[2];      // accumulator drained (128 epilogue arrivals)
-  uint64_t raw_full[4];       // raw fp32 activation tile landed (TMA bytes)        [A_TMEM mode]
-  uint64_t raw_empty[4];      // raw tile consumed by the 128 converter threads      [A_TMEM mode]
+  uint64_t raw_full[8];       // raw fp32 activation tile landed (TMA bytes)        [A_TMEM mode]
+  uint64_t raw_empty[8];      // raw tile consumed by the 128 converter threads      [A_TMEM mode]
   uint32_t tmem_base;
 };
-constexpr int RAW_STAGES = 4;                        // raw activation staging ring (16 KB each)
+constexpr int RAW_STAGES = EVRP_GEMM_RAW_STAGES;      // raw activation staging ring (16 KB each)
 
 // A_TMEM: the converters write the activation planes into tensor memory (tcgen05.st) and the MMAs read A from
 // TMEM, so shared memory only carries the weight planes (halves the shared-memory traffic per MMA).
@@ -58,6 +64,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_constant__ CUtensorMap mapWl,
                   const __grid_constant__ CUtensorMap mapA, const float* __restrict__ A, int lda, float* __restrict__ C, int ldc, int M, int K, int n_chunks,
                   Epilogue ep) {
+  constexpr int STAGES = A_TMEM ? EVRP_GEMM_STAGES : 3;   // TMEM A staging: 64 columns per stage next to 2 x 128 accumulator columns
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte alignment (swizzle atoms) by pointer arithmetic on the __shared__ array itself: the compiler keeps the
   // address space, so every access below is an LDS/STS (an integer round trip degrades them to generic LD/ST)
@@ -366,6 +373,7 @@ static int launch_impl(const CUtensorMap& mh, const CUtensorMap& ml, const CUten
   const int m_tiles = (M + BM - 1) / BM;
   const int ctas_per_chunk = per_chunk < m_tiles ? per_chunk : m_tiles;
   const size_t a_bytes = A_TMEM ? 0 : 2 * PLANE;
+  constexpr int STAGES = A_TMEM ? EVRP_GEMM_STAGES : 3;
   const size_t smem = (RESIDENT ? (size_t)(K / BKB) * 2 * PLANE + STAGES * a_bytes : (size_t)STAGES * (a_bytes + 2 * PLANE)) +
                       (A_TMEM ? (size_t)RAW_STAGES * PLANE : 0) + sizeof(Barriers) + 1024;
   auto kern = gemm3xtf32_kernel<RESIDENT, EPI, A_TMEM>;

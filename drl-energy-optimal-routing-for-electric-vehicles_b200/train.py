@@ -304,3 +304,110 @@ def reinforce_step(actor, baseline, optimizer, batch, max_grad_norm=2.0, forced_
     optimizer.step()
     loss_global = allreduce_sum_(loss.detach().clone())
     return dict(loss=loss_global, reward=global_mean(reward.detach()), grad_norm=grad_norms[0][0], pi=pi, T=pi.shape[1])
+
+
+# ------------------------------------------------------------------------------------------------
+# per-rank trainer shell: trainer.py:21-49 validate, :73-206 train, :160-169 checkpoint format
+# ------------------------------------------------------------------------------------------------
+def rank_shard(dataset):
+    """this rank's contiguous slice of a dataset (instances are sharded)"""
+    from torch.utils.data import Subset
+    lo, hi = shard_bounds(len(dataset))
+    return Subset(dataset, range(lo, hi)) if (lo, hi) != (0, len(dataset)) else dataset
+
+
+def validate(dataset, actor, batch_size):
+    """trainer.py:21-49 without the plotting: mean greedy cost of a validation set (mean of per-batch means, as the
+    reference computes it; identical to the global mean when the batches are equal-sized).  Sharded over ranks."""
+    was_training = actor.training
+    actor.eval()
+    actor.set_decode_type("greedy")
+    sums = torch.zeros(2, dtype=torch.float64)
+    for batch in DataLoader(rank_shard(dataset), batch_size, False, num_workers=0):
+        with torch.no_grad():
+            _, _, R = actor(batch)
+        sums += torch.tensor([float(R.sum(1).mean()), 1.0], dtype=torch.float64)
+    r, w = world()
+    if w > 1:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        sums = allreduce_sum_(sums.to(dev)).cpu()
+    actor.train(was_training)
+    return float(sums[0] / max(float(sums[1]), 1.0))
+
+
+def checkpoint_state(actor, optimizer, baseline):
+    """the reference's checkpoint dictionary, key for key (trainer.py:160-169)"""
+    return {'model': actor.state_dict(), 'optimizer': optimizer.state_dict(), 'rng_state': torch.get_rng_state(),
+            'cuda_rng_state': torch.cuda.get_rng_state_all() if torch.cuda.is_available() else [],
+            'baseline': baseline.state_dict()}
+
+
+def load_checkpoint(path, actor, optimizer=None, baseline=None, map_location=None):
+    """trainer.py:277-301: restore model (+ optimizer, RNG, baseline) from a checkpoint of either code base"""
+    ck = torch.load(path, map_location=map_location, weights_only=False)
+    actor.load_state_dict({**actor.state_dict(), **ck.get('model', {})})
+    if optimizer is not None and 'optimizer' in ck:
+        optimizer.load_state_dict(ck['optimizer'])
+    if 'rng_state' in ck:
+        torch.set_rng_state(ck['rng_state'].cpu() if hasattr(ck['rng_state'], "cpu") else ck['rng_state'])
+    if baseline is not None and 'baseline' in ck:
+        baseline.load_state_dict(ck['baseline'])
+    return ck
+
+
+def train_epoch(actor, baseline, optimizer, train_data, batch_size, max_grad_norm=2.0, log_every=100, on_log=None,
+                shuffle=True):
+    """One epoch of trainer.py:100-143 on this rank's shard: wrap the dataset with the baseline values (for the rollout
+    baseline: a greedy pass of the rollout kernel over the shard), then REINFORCE steps with a flat gradient all-reduce.
+    ``batch_size`` is the PER-RANK batch.  Returns (mean reward, mean loss, steps)."""
+    data = baseline.wrap_dataset(rank_shard(train_data))
+    loader = DataLoader(data, batch_size, shuffle, num_workers=0)
+    actor.train()
+    actor.set_decode_type("sample")
+    rewards, losses = [], []
+    for batch_idx, batch in enumerate(loader):
+        out = reinforce_step(actor, baseline, optimizer, batch, max_grad_norm)
+        rewards.append(float(out["reward"]))
+        losses.append(float(out["loss"]))
+        if on_log is not None and (batch_idx + 1) % log_every == 0:
+            on_log(batch_idx, len(loader), float(np.mean(rewards[-log_every:])), float(np.mean(losses[-log_every:])))
+    return float(np.mean(rewards)) if rewards else float("nan"), float(np.mean(losses)) if losses else float("nan"), len(rewards)
+
+
+def train(actor, baseline, optimizer, lr_scheduler, train_data, valid_data, batch_size, max_grad_norm, iterations,
+          save_dir=None, log=print):
+    """trainer.py:73-206 as a per-rank loop: epochs of train_epoch -> checkpoint (rank 0, reference format) -> validate
+    -> baseline.epoch_callback -> lr_scheduler.step -> best.pt.  CSV rows [reward, loss, seconds, valid] like
+    trainer.py:177-179 go to ``save_dir/epochs.csv`` on rank 0."""
+    import csv
+    import os
+    import time
+    rank, _ = world()
+    best, epoch_reward, epoch_loss = float("inf"), [], []
+    if save_dir is not None and rank == 0:
+        os.makedirs(os.path.join(save_dir, "checkpoints"), exist_ok=True)
+    for epoch in range(iterations):
+        t0 = time.time()
+        mean_reward, mean_loss, steps = train_epoch(
+            actor, baseline, optimizer, train_data, batch_size, max_grad_norm,
+            on_log=(lambda i, n, r, l: log('Batch %d/%d, reward: %2.3f,  loss: %2.4f' % (i, n, r, l))) if rank == 0 else None)
+        epoch_reward.append(mean_reward); epoch_loss.append(mean_loss)
+        if save_dir is not None and rank == 0:
+            d = os.path.join(save_dir, "checkpoints", str(epoch))
+            os.makedirs(d, exist_ok=True)
+            torch.save(checkpoint_state(actor, optimizer, baseline), os.path.join(d, 'epoch-{}.pt'.format(epoch)))
+        mean_valid = validate(valid_data, actor, batch_size)
+        if save_dir is not None and rank == 0:
+            with open(os.path.join(save_dir, "epochs.csv"), "a", newline='') as f:
+                csv.writer(f).writerow([mean_reward, mean_loss, time.time() - t0, mean_valid])
+        baseline.epoch_callback(actor, epoch)
+        if lr_scheduler is not None:
+            lr_scheduler.step()
+        if mean_valid < best:
+            best = mean_valid
+            if save_dir is not None and rank == 0:
+                torch.save(checkpoint_state(actor, optimizer, baseline), os.path.join(save_dir, 'best.pt'))
+        if rank == 0:
+            log('Mean epoch loss/reward: %2.4f, %2.4f, %2.4f, took: %2.4fs (%d steps)' %
+                (mean_loss, mean_reward, mean_valid, time.time() - t0, steps))
+    return epoch_reward, epoch_loss

@@ -408,6 +408,37 @@ def test_reinforce_step_runs_and_learns_signal(evrp, weights):
 # ---------------------------------------------------------------------------------------------
 # size-independent properties at BASELINE.json's full config-4 size (EM-EVRP-100, B=8192)
 # ---------------------------------------------------------------------------------------------
+def test_trainer_shell_epoch_checkpoint_resume(evrp, weights, tmp_path):
+    """one epoch of the per-rank trainer shell (trainer.py:73-206) with the rollout baseline behind a warm-up
+    (wrap_dataset = a greedy pass of the rollout kernel), checkpoint in the reference's format, resume."""
+    import types
+    from evrp_b200 import train as T
+    a = args_for(20)
+    ds = evrp.VehicleRoutingDataset(96, 20, 10., 80., 50., 4, 4, 5, 11, a)
+    vs = evrp.VehicleRoutingDataset(32, 20, 10., 80., 50., 4, 4, 5, 13, a)
+    m = evrp.AttentionModel(128, 128, a, n_encode_layers=3, update_dynamic=ds.update_dynamic, update_mask=ds.update_mask)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()})
+    m = m.cuda()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    bargs = types.SimpleNamespace(batch_size=32, bl_alpha=0.05)
+    bl = T.WarmupBaseline(T.RolloutBaseline(m, vs, bargs), n_epochs=1)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda e: 1.0)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    er, el = T.train(m, bl, opt, sched, ds, vs, 32, 2.0, 2, save_dir=str(tmp_path), log=lambda *_: None)
+    assert len(er) == 2 and all(np.isfinite(er)) and all(np.isfinite(el))
+    assert any(not torch.equal(before[k], v) for k, v in m.state_dict().items() if v.dtype.is_floating_point)
+    ck = torch.load(tmp_path / "checkpoints" / "1" / "epoch-1.pt", weights_only=False)
+    assert set(ck) == {"model", "optimizer", "rng_state", "cuda_rng_state", "baseline"}      # trainer.py:160-169
+    assert set(ck["model"]) == set(before)
+    assert (tmp_path / "best.pt").exists() and len(open(tmp_path / "epochs.csv").read().strip().splitlines()) == 2
+    m2 = evrp.AttentionModel(128, 128, a, n_encode_layers=3, update_dynamic=ds.update_dynamic, update_mask=ds.update_mask).cuda()
+    opt2 = torch.optim.Adam(m2.parameters(), lr=1e-4)
+    T.load_checkpoint(tmp_path / "checkpoints" / "1" / "epoch-1.pt", m2, opt2)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, m2.state_dict()[k]), k
+    assert abs(T.validate(vs, m, 32) - T.validate(vs, m2, 32)) < 1e-4
+
+
 def test_full_size_properties_and_shard_invariance(evrp, weights):
     B, N, F = 8192, 100, 5
     static, dynamic, elev = O.generate_instances(B, N, seed=2024)
