@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EVRP_B200_LIB") or os.path.join(_HERE, "libevrp_b200.so")   # override: instrumented debug builds (tools/)
 
 EVRP_MAX_S = 128
-ABI_VERSION = 9
+ABI_VERSION = 10
 EVRP_MAX_LAYERS = 8
 ST_NAN_LOGIT, ST_INFEASIBLE_PICK, ST_STEP_CAP, ST_NONUNIFORM_DYNAMIC, ST_NO_FEASIBLE = 1, 2, 4, 8, 16
 DECODE_GREEDY, DECODE_SAMPLE = 0, 1
@@ -58,6 +58,7 @@ SIGNATURES = {
     "evrp_update_dynamic": (C.c_int, [C.POINTER(Phys), _FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int,
                                       _FP, _FP, _FP, _FP]),
     "evrp_update_mask": (C.c_int, [C.POINTER(Phys), _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, _FP, _FP, _FP]),
+    "evrp_pairwise_build": (C.c_int, [_FP, _FP, C.c_int, C.c_int, _FP, _FP, _FP]),
     "evrp_encoder_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "evrp_encoder_forward": (C.c_int, [C.POINTER(EncoderWeights), _FP, _FP, C.c_int, C.c_int, C.c_int,
                                        _FP, _FP, _FP, _FP, C.c_size_t, _FP]),

@@ -122,6 +122,30 @@ __global__ void finalize_mask_kernel(float* __restrict__ mask, size_t n, const i
     mask[i] = 0.f;
 }
 
+// distances / slope of the 3-tuple input branch (nets/DRLModel.py:128-133, problems/EVRP.py:87-92), one warp per (b, i) row:
+//   D[b,i,j] = sqrt((x_i - x_j)^2 + (y_i - y_j)^2)            separately rounded ops, IEEE sqrt
+//   G[b,i,j] = clamp((E_i - E_j) / (D[b,i,j] + 1e-6), -0.1, 0.1)
+__global__ void __launch_bounds__(256)
+pairwise_build_kernel(const float* __restrict__ xy, const float* __restrict__ elev, int B, int S,
+                      float* __restrict__ Dm, float* __restrict__ Gm) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= (long long)B * S) return;
+  const long long b = row / S;
+  const int i = (int)(row % S);
+  const float* x = xy + (b * 2 + 0) * S;
+  const float* y = xy + (b * 2 + 1) * S;
+  const float* e = elev + b * S;
+  const float xi = x[i], yi = y[i], ei = e[i];
+  for (int j = lane; j < S; j += 32) {
+    const float dx = __fsub_rn(xi, x[j]), dy = __fsub_rn(yi, y[j]);
+    const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    const float g = __fdiv_rn(__fsub_rn(ei, e[j]), __fadd_rn(d, 0.000001f));
+    Dm[row * S + j] = d;
+    Gm[row * S + j] = fminf(fmaxf(g, -0.10f), 0.10f);
+  }
+}
+
 }  // namespace evrp
 
 extern "C" {
@@ -140,6 +164,17 @@ void evrp_phys_default(evrp_phys* p, double velocity, double start_soc, double t
 }
 
 int evrp_abi_version(void) { return EVRP_ABI_VERSION; }
+
+int evrp_pairwise_build(const float* static_xy, const float* elevations, int B, int S, float* distances, float* slope,
+                        void* stream) {
+  if (!static_xy || !elevations || !distances || !slope || B < 0 || S < 1) return -EVRP_E_BADARG;
+  if (B == 0) return 0;
+  const long long rows = (long long)B * S;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  evrp::pairwise_build_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(static_xy, elevations, B, S, distances, slope);
+  EVRP_LAUNCH_OK();
+  return 0;
+}
 
 int evrp_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;

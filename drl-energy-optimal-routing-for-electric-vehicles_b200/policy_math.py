@@ -126,7 +126,17 @@ def pack_weights(model):
 
 
 def pairwise_matrices(static, elevations):
-    """nets/DRLModel.py:128-133 / problems/EVRP.py:87-92, vectorised (no Python loop over S)."""
+    """nets/DRLModel.py:128-133 / problems/EVRP.py:87-92.  CUDA tensors: one fused kernel (evrp_pairwise_build);
+    CPU tensors (host-side dataset construction): vectorised torch, no Python loop over S."""
+    if static.is_cuda:
+        static = static.float().contiguous()
+        elevations = elevations.to(static.device, torch.float32).contiguous()
+        B, _, S = static.shape
+        D = torch.empty(B, S, S, device=static.device)
+        G = torch.empty(B, S, S, device=static.device)
+        _lib.check(_lib.lib().evrp_pairwise_build(_lib.ptr(static), _lib.ptr(elevations), B, S, _lib.ptr(D), _lib.ptr(G),
+                                                  _lib.stream_ptr()), "evrp_pairwise_build")
+        return D, G
     diff = static[:, :, :, None] - static[:, :, None, :]
     D = torch.sqrt((diff * diff).sum(1))
     G = torch.clamp((elevations[:, :, None] - elevations[:, None, :]) / (D + 0.000001), min=-0.10, max=0.10)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 9
+#define EVRP_ABI_VERSION 10
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -82,6 +82,11 @@ int evrp_update_dynamic(const evrp_phys* phys, const float* dynamic, const float
 int evrp_update_mask(const evrp_phys* phys, const float* dynamic, const float* distances, const float* slope,
                      const int64_t* chosen_idx, int B, int S, int F, float* mask /*[B,S] 0/1*/,
                      int32_t* any_demand, void* stream);
+
+/* distances / slope build of the 3-tuple input (static, dynamic, Elevations): nets/DRLModel.py:124-133 and the dataset's
+ * own build problems/EVRP.py:87-92.  static_xy [B,2,S], elevations [B,S] -> distances, slope [B,S,S]. */
+int evrp_pairwise_build(const float* static_xy, const float* elevations, int B, int S, float* distances, float* slope,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (2) encoder + decoder precompute:  AttentionModel._init_embed        nets/DRLModel.py:192-200

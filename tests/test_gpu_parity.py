@@ -260,6 +260,16 @@ def test_dm_objective(evrp, weights):
     assert np.array_equal(o["E"].cpu().numpy(), g["E"])          # energy carried as side output
 
 
+@pytest.mark.parametrize("N,B", [(20, 7), (100, 129)])
+def test_pairwise_build_kernel_bit_exact_vs_oracle(evrp, N, B):
+    """the 3-tuple input branch's distance / slope build (nets/DRLModel.py:128-133) as one kernel: bit-exact with the oracle"""
+    from oracle import evrp_oracle as O
+    s, d, e = O.generate_instances(B, N, seed=40 + N)
+    Do, Go = O.pairwise_matrices(s, e)
+    D, G = evrp.policy_math.pairwise_matrices(torch.from_numpy(s).cuda(), torch.from_numpy(e).cuda())
+    assert np.array_equal(D.cpu().numpy(), Do) and np.array_equal(G.cpu().numpy(), Go)
+
+
 def test_three_tuple_input_matches_four_tuple(evrp, weights):
     g = load("greedy_n20.npz")
     m, _ = make_model(evrp, 20, weights)
