@@ -42,12 +42,23 @@ def peaks():
 
 
 def synth(B, N, seed):
-    from oracle import evrp_oracle as O          # generator only (instance distribution of problems/EVRP.py:43-92)
-    return O.generate_instances(B, N, seed=seed)
+    import evrp_b200                              # the package's own generator (distribution of problems/EVRP.py:43-92)
+    return evrp_b200.synthetic_instances(B, N, seed=seed)
 
 
 def golden_weights():
+    """cpu_baseline / reference legs only: the torch.manual_seed(0) weights as numpy arrays for the oracle"""
     return dict(np.load(os.path.join(ROOT, "tests", "golden", "weights_seed0.npz")))
+
+
+def seeded_model(evrp_b200, args, ds, dev, seed=0):
+    """random-init policy exactly as the reference builds it: torch.manual_seed(seed), then construct (parameter creation
+    order and initialisers are the reference's, tests/test_boundary.py pins this against tests/golden/weights_seed0.npz)"""
+    import torch
+    torch.manual_seed(seed)
+    m = evrp_b200.AttentionModel(128, 128, args, n_encode_layers=3, update_dynamic=ds.update_dynamic,
+                                 update_mask=ds.update_mask)
+    return m.to(dev)
 
 
 def cpu_port_rate(N, sample, threads=None):
@@ -137,8 +148,8 @@ def main():
     os.dup2(2, 1)                                     # libraries that print to fd 1 must not pollute the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=8192, help="instances per GPU per step (BASELINE configs[3])")
     ap.add_argument("--nodes", type=int, default=100)
@@ -165,10 +176,7 @@ def main():
     S = N + F + 1
     args = types.SimpleNamespace(CVRP_lib_test=False, Start_SOC=80., t_limit=10., num_nodes=N, charging_num=F)
     ds = evrp_b200.VehicleRoutingDataset(2, N, 10., 80., 50., 4, 4, F, 1, args)
-    model = evrp_b200.AttentionModel(128, 128, args, n_encode_layers=3, update_dynamic=ds.update_dynamic,
-                                     update_mask=ds.update_mask)
-    model.load_state_dict({k: torch.from_numpy(v) for k, v in golden_weights().items()})   # torch.manual_seed(0) init
-    model = model.to(dev).eval()
+    model = seeded_model(evrp_b200, args, ds, dev).eval()                                  # torch.manual_seed(0) init
     model.set_decode_type("greedy")
     static, dynamic, elev = synth(B, N, seed=1000 + rank)
     st_h = torch.from_numpy(static).pin_memory(); dy_h = torch.from_numpy(dynamic).pin_memory()
@@ -246,10 +254,7 @@ def main():
     if a.train_steps > 0:
         from evrp_b200 import train as Tr
         tb = a.train_batch
-        tm_model = evrp_b200.AttentionModel(128, 128, args, n_encode_layers=3, update_dynamic=ds.update_dynamic,
-                                            update_mask=ds.update_mask)
-        tm_model.load_state_dict({k: torch.from_numpy(v) for k, v in golden_weights().items()})
-        tm_model = tm_model.to(dev).train()
+        tm_model = seeded_model(evrp_b200, args, ds, dev).train()
         tm_model.set_decode_type("sample")
         opt = torch.optim.Adam(tm_model.parameters(), lr=1e-4)
         bl = Tr.ExponentialBaseline(0.8)

@@ -7,6 +7,6 @@ Python identifier); the repo-root shim ``evrp_b200/`` loads it under the name ``
 from . import _lib
 from ._lib import EvrpLibraryError, lib
 from .model import AttentionModel
-from .problem import VehicleRoutingDataset, parse_cvrplib
+from .problem import VehicleRoutingDataset, parse_cvrplib, synthetic_instances
 
-__all__ = ["AttentionModel", "VehicleRoutingDataset", "parse_cvrplib", "EvrpLibraryError", "lib"]
+__all__ = ["AttentionModel", "VehicleRoutingDataset", "parse_cvrplib", "synthetic_instances", "EvrpLibraryError", "lib"]

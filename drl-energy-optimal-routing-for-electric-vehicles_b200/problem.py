@@ -46,6 +46,28 @@ def parse_cvrplib(path):
     return coords, demands, capacity
 
 
+def synthetic_instances(B, N, F=5, seed=0, t_limit=10., Start_SOC=80., max_load=4, max_demand=4):
+    """B synthetic EVRP instances with the distribution and value grid of problems/EVRP.py:43-92 (layout
+    [depot, F stations, N customers]): depot in [25,75)^2, station i in quadrant i % 4, customers on the integer grid
+    [0,100]^2, demand in {1..max_demand} * 0.25 / max_load, elevation in {0..100} / 1000, dynamic0 = [1, demand,
+    Start_SOC, t_limit].  numpy generator (bulk benchmark input; ``VehicleRoutingDataset`` reproduces the reference's
+    torch RNG stream).  -> static [B,2,S], dynamic [B,4,S], elevation [B,S] (float32)."""
+    rng = np.random.RandomState(seed)
+    S = N + F + 1
+    f32 = np.float32
+    lo = rng.randint(0, 50, (2, B, F)); hi = rng.randint(51, 101, (2, B, F))
+    q = np.arange(F) % 4
+    stations = np.stack([np.where(q < 2, lo[0], hi[0]), np.where(q % 2 == 0, lo[1], hi[1])], 1).astype(f32)
+    depot = rng.randint(25, 75, (B, 2, 1)).astype(f32)
+    cust = rng.randint(0, 101, (B, 2, N)).astype(f32)
+    static = np.concatenate([depot, stations, cust], 2)
+    demand = rng.randint(1, max_demand + 1, (B, S)).astype(f32) * f32(0.25) / f32(max_load)
+    demand[:, :F + 1] = 0
+    elevation = rng.randint(0, 101, (B, S)).astype(f32) / f32(1000)
+    dynamic = np.stack([np.ones((B, S), f32), demand, np.full((B, S), Start_SOC, f32), np.full((B, S), t_limit, f32)], 1)
+    return static, dynamic, elevation
+
+
 class VehicleRoutingDataset(Dataset):
     _evrp_b200_native = True
 
