@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8192, help="instances per GPU per step (BASELINE configs[3])")
     ap.add_argument("--nodes", type=int, default=100)
     ap.add_argument("--cpu-sample", type=int, default=1024)
-    ap.add_argument("--ref-sample", type=int, default=1024)
+    ap.add_argument("--ref-sample", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-steps", type=int, default=3, help="timed REINFORCE steps (0 = skip)")
     ap.add_argument("--train-batch", type=int, default=1024)
