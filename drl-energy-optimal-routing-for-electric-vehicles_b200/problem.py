@@ -46,6 +46,48 @@ def parse_cvrplib(path):
     return coords, demands, capacity
 
 
+# ------------------------------------------------------------------------------------------------
+# test-set files: the reference's pickle format, trainer.py:361-381 (writer) / :469-482 (reader),
+# utils/data_utils.py:11-31 -- a list of (static [2,S], dynamic [4,S], distances [S,S], slope [S,S]) nested lists,
+# the exact files the classical solvers (BaselineAlgorithms/ACO.py:27-34) consume.
+# ------------------------------------------------------------------------------------------------
+def check_extension(filename):
+    import os
+    return filename if os.path.splitext(filename)[1] == ".pkl" else filename + ".pkl"
+
+
+def save_dataset(dataset, filename):
+    """``dataset``: a VehicleRoutingDataset (4-tuple items) or an iterable of (static, dynamic, distances, slope)."""
+    import os
+    import pickle
+    rows = []
+    for item in (dataset[i] for i in range(len(dataset))) if hasattr(dataset, "__getitem__") else dataset:
+        if len(item) != 4:
+            raise ValueError("the test-set file stores 4-tuples (static, dynamic, distances, slope)")
+        rows.append(tuple(torch.as_tensor(t).detach().cpu().tolist() for t in item))
+    d = os.path.split(filename)[0]
+    if d and not os.path.isdir(d):
+        os.makedirs(d)
+    with open(check_extension(filename), "wb") as f:
+        pickle.dump(rows, f, pickle.HIGHEST_PROTOCOL)
+    return check_extension(filename)
+
+
+def load_dataset(filename):
+    import pickle
+    with open(check_extension(filename), "rb") as f:
+        return pickle.load(f)
+
+
+def EVRPDataset(filename=None, num_samples=256, offset=0, device=None):
+    """trainer.py:476-482: list of 4-tuples of tensors (on ``device``), ready for a DataLoader / ``AttentionModel``."""
+    import os
+    assert os.path.splitext(filename)[1] == ".pkl"
+    device = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
+    return [tuple(torch.tensor(t, dtype=torch.float32, device=device) for t in row)
+            for row in load_dataset(filename)[offset:offset + num_samples]]
+
+
 def synthetic_instances(B, N, F=5, seed=0, t_limit=10., Start_SOC=80., max_load=4, max_demand=4):
     """B synthetic EVRP instances with the distribution and value grid of problems/EVRP.py:43-92 (layout
     [depot, F stations, N customers]): depot in [25,75)^2, station i in quadrant i % 4, customers on the integer grid

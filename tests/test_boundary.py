@@ -188,3 +188,21 @@ def test_cvrplib_parser(tmp_path):
     assert len(ds) == 1 and ds.static.shape == (1, 2, 9)
     assert torch.allclose(ds.dynamic[0, 1, 6:], torch.tensor([0.19, 0.30, 0.16]))
     assert torch.equal(ds.static[0, :, 0], torch.tensor([30., 40.]))
+
+
+def test_test_set_pickle_round_trip(tmp_path):
+    """the reference's test-set file (trainer.py:361-381 writer, :469-482 reader): nested-list 4-tuples"""
+    import pickle
+    import evrp_b200
+    a = types.SimpleNamespace(CVRP_lib_test=False, Start_SOC=80., t_limit=10., num_nodes=10, charging_num=5)
+    ds = evrp_b200.VehicleRoutingDataset(6, 10, 10., 80., 50., 4, 4, 5, 77, a, device="cpu")
+    path = evrp_b200.save_dataset(ds, str(tmp_path / "test_data" / "10" / "6_seed77"))
+    assert path.endswith(".pkl")
+    raw = pickle.load(open(path, "rb"))
+    assert isinstance(raw, list) and len(raw) == 6 and len(raw[0]) == 4 and isinstance(raw[0][0], list)
+    assert np.asarray(raw[0][0]).shape == (2, 16) and np.asarray(raw[0][2]).shape == (16, 16)
+    back = evrp_b200.EVRPDataset(path, num_samples=4, offset=1, device="cpu")
+    assert len(back) == 4
+    for i, item in enumerate(back):
+        for got, want in zip(item, ds[i + 1]):
+            assert torch.equal(got, torch.as_tensor(want).float().cpu())
