@@ -309,11 +309,18 @@ def route_context(P, c, dynamic, run_max):
     return _linear(h1, P["FF_tour.2.weight"], P["FF_tour.2.bias"])
 
 
-def step_log_p(P, fixed, emb, now, mask, ctx, tanh_clipping=10., temp=1.0, n_heads=8):
-    """nets/DRLModel.py:379-452 -> log_p [B,S]."""
+def step_context_am(P, emb, dynamic, now):
+    """nets/AM.py:333-377: project_step_context([emb[now], load]) -- the AM variant's query term (no route context)."""
+    B = emb.shape[0]
+    cat = np.concatenate([emb[np.arange(B), now], dynamic[:, 0, 0:1]], 1).astype(f32)
+    return _linear(cat, P["project_step_context.weight"])
+
+
+def step_log_p(P, fixed, emb, now, mask, ctx, tanh_clipping=10., temp=1.0, n_heads=8, add_now=True):
+    """nets/DRLModel.py:379-452 -> log_p [B,S].  add_now=False: nets/AM.py:336-337 (query = fixed context + ctx)."""
     fixed_ctx, gK, gV, lK = fixed
     B, S, d = emb.shape
-    q = (fixed_ctx + ctx) + emb[np.arange(B), now]
+    q = (fixed_ctx + ctx) + emb[np.arange(B), now] if add_now else fixed_ctx + ctx
     qh = q.reshape(B, n_heads, 1, -1)
     compat = np.matmul(qh, np.swapaxes(gK, 2, 3))[:, :, 0, :] / f32(math.sqrt(d // n_heads))   # [B,H,S]
     infeasible = (mask == 0)
@@ -345,6 +352,7 @@ def rollout(P, static, dynamic, D, G, consts=None, decode_type="greedy", forced=
     mask = np.ones((B, S), f32)
     now = np.zeros(B, np.int64)
     run_max = np.zeros((B, emb.shape[2]), f32)
+    am = "project_step_context.weight" in P
     pis, lls, Rs, Es, logps, masks, dyns = [], [], [], [], [], [], []
     ar = np.arange(B)
     for t in range(max_steps):
@@ -353,8 +361,11 @@ def rollout(P, static, dynamic, D, G, consts=None, decode_type="greedy", forced=
                 break
         elif not mask.any():
             break
-        ctx = route_context(P, c, dynamic, run_max)
-        log_p = step_log_p(P, fixed, emb, now, mask, ctx, temp=temp)
+        if am:                                              # nets/AM.py variant
+            log_p = step_log_p(P, fixed, emb, now, mask, step_context_am(P, emb, dynamic, now), temp=temp, add_now=False)
+        else:
+            ctx = route_context(P, c, dynamic, run_max)
+            log_p = step_log_p(P, fixed, emb, now, mask, ctx, temp=temp)
         if forced is not None:
             sel = forced[:, t].astype(np.int64)
         elif decode_type == "greedy":

@@ -170,6 +170,37 @@ def dm_fixture(name, N, B, seed=12345):
     print(name, "T=", pi.shape[1], "mean distance", float(a["t_dist"].sum(1).mean()))
 
 
+def am_fixture(name, N, B, seed=12345):
+    """nets/AM.py variant: greedy tours, per-step log-probs, and a sampled rollout with its REINFORCE
+    gradients; weights torch.manual_seed(0) -> weights_am_seed0.npz"""
+    ds, args = ref_shim.make_dataset(B, N, seed)
+    m = ref_shim.make_model_am(ds, args, 0)
+    np.savez_compressed(os.path.join(OUT, "weights_am_seed0.npz"), **{k: v.numpy() for k, v in m.state_dict().items()})
+    m.eval(); m.set_decode_type("greedy")
+    bat = batch_of(ds, B)
+    cap = {}
+    orig = m._calc_log_likelihood
+    def spy(_log_p, a):
+        cap["log_p"] = _log_p.detach().numpy().copy()
+        return orig(_log_p, a)
+    m._calc_log_likelihood = spy
+    with torch.no_grad():
+        pi, ll, R = m(bat)
+    d = inputs_dict(ds, bat, B)
+    d.update(pi=pi.numpy(), ll=ll.numpy(), R=R.numpy(), t_log_p=cap["log_p"])
+    # sampled rollout + gradients of mean((R.sum - mean) * ll.sum) (eval-mode BatchNorm)
+    m.set_decode_type("sample")
+    torch.manual_seed(seed + 1)
+    m.zero_grad()
+    spi, sll, sR = m(bat)
+    adv = (sR.sum(1) - sR.sum(1).mean()).detach()
+    (adv * sll.sum(1)).mean().backward()
+    d.update(s_pi=spi.numpy(), s_ll=sll.detach().numpy(), s_R=sR.numpy(), s_adv=adv.numpy(),
+             **{"grad." + k: p.grad.numpy().copy() for k, p in m.named_parameters()})
+    np.savez_compressed(os.path.join(OUT, name), **d)
+    print(name, "T=", pi.shape[1], "mean cost", float(R.sum(1).mean()), "sampled T=", spi.shape[1])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ds, args = ref_shim.make_dataset(2, 20, 1)
@@ -182,6 +213,7 @@ def main():
     greedy_fixture("greedy_n100.npz", 100, 6)
     sample_fixture("sample_n20.npz", 20, 16)
     dm_fixture("dm_n20.npz", 20, 8)
+    am_fixture("am_n20.npz", 20, 16)
 
 
 if __name__ == "__main__":

@@ -106,3 +106,15 @@ def make_model(ds, args, weight_seed=0):
            mask_inner=True, mask_logits=True,
            update_dynamic=ds.update_dynamic, update_mask=ds.update_mask)
     return m
+
+
+def make_model_am(ds, args, weight_seed=0):
+    """the reference's nets/AM.py variant of the policy (query = fixed context + project_step_context([emb[now], load]))"""
+    import importlib
+    import torch
+    load()
+    am = importlib.import_module("nets.AM")
+    torch.manual_seed(weight_seed)
+    return am.AttentionModel(128, 128, args, n_encode_layers=3, normalization='batch', tanh_clipping=10.,
+                             mask_inner=True, mask_logits=True,
+                             update_dynamic=ds.update_dynamic, update_mask=ds.update_mask)

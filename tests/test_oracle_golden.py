@@ -103,3 +103,18 @@ def test_generated_instances_shape_and_grid():
     assert np.array_equal(s, np.round(s)) and s.min() >= 0 and s.max() <= 100
     assert set(np.unique(d[:, 1, 6:] * 16).tolist()) <= {1.0, 2.0, 3.0, 4.0}
     assert (d[:, 1, :6] == 0).all() and (d[:, 0] == 1).all() and (d[:, 2] == 80).all() and (d[:, 3] == 10).all()
+
+
+def test_oracle_am_variant_matches_reference():
+    """the nets/AM.py policy variant (query = fixed context + project_step_context([emb[now], load])) -- oracle
+    against outputs recorded from the reference's own nets/AM.py (oracle/make_golden.py::am_fixture)."""
+    g = np.load(os.path.join(GOLDEN, "am_n20.npz"))
+    W = dict(np.load(os.path.join(GOLDEN, "weights_am_seed0.npz")))
+    o = O.rollout(W, g["static"], g["dynamic"], g["distances"], g["slope"], forced=g["pi"], trace=True)
+    assert np.array_equal(o["R"], g["R"])                                   # rewards bit-exact (teacher-forced)
+    live = np.isfinite(g["t_log_p"]) & np.isfinite(o["log_p"])
+    assert np.array_equal(np.isfinite(g["t_log_p"]), np.isfinite(o["log_p"]))   # same feasibility pattern
+    assert np.abs(o["log_p"][live] - g["t_log_p"][live]).max() < 2e-5
+    free = O.rollout(W, g["static"], g["dynamic"], g["distances"], g["slope"])
+    T = min(free["pi"].shape[1], g["pi"].shape[1])
+    assert (free["pi"][:, :T] == g["pi"][:, :T]).all(1).mean() >= 0.8
