@@ -6,9 +6,9 @@ Python identifier); the repo-root shim ``evrp_b200/`` loads it under the name ``
 """
 from . import _lib
 from ._lib import EvrpLibraryError, lib
-from .model import AttentionModel
+from .model import AttentionModel, AttentionModelAM
 from .problem import (EVRPDataset, VehicleRoutingDataset, load_dataset, parse_cvrplib, save_dataset,
                       synthetic_instances)
 
-__all__ = ["AttentionModel", "VehicleRoutingDataset", "parse_cvrplib", "synthetic_instances", "save_dataset",
+__all__ = ["AttentionModel", "AttentionModelAM", "VehicleRoutingDataset", "parse_cvrplib", "synthetic_instances", "save_dataset",
            "load_dataset", "EVRPDataset", "EvrpLibraryError", "lib"]

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EVRP_B200_LIB") or os.path.join(_HERE, "libevrp_b200.so")   # override: instrumented debug builds (tools/)
 
 EVRP_MAX_S = 128
-ABI_VERSION = 10
+ABI_VERSION = 11
 EVRP_MAX_LAYERS = 8
 ST_NAN_LOGIT, ST_INFEASIBLE_PICK, ST_STEP_CAP, ST_NONUNIFORM_DYNAMIC, ST_NO_FEASIBLE = 1, 2, 4, 8, 16
 DECODE_GREEDY, DECODE_SAMPLE = 0, 1
@@ -37,12 +37,14 @@ class EncoderWeights(C.Structure):
     _fields_ = [(n, _FP) for n in ("depot_w", "depot_b", "station_w", "station_b", "cust_w", "cust_b")] + \
         [("n_layers", C.c_int32), ("layers", LayerWeights * EVRP_MAX_LAYERS),
          ("node_proj", _FP), ("fixed_ctx_w", _FP), ("node_proj_hi", _FP), ("node_proj_lo", _FP),
+         ("step_proj", _FP), ("step_proj_hi", _FP), ("step_proj_lo", _FP),
          ("gemm_mode", C.c_int32), ("attn_mode", C.c_int32)]
 
 
 class DecoderWeights(C.Structure):
-    _fields_ = [(n, _FP) for n in ("w1_veh", "w1_max", "b1", "w2", "b2", "w1max_hi", "w1max_lo", "w2_hi", "w2_lo")] + \
-        [("w1_inv_scale", C.c_float), ("w2_inv_scale", C.c_float), ("ff_mode", C.c_int32)]
+    _fields_ = [(n, _FP) for n in ("w1_veh", "w1_max", "b1", "w2", "b2", "w1max_hi", "w1max_lo", "w2_hi", "w2_lo",
+                                   "am_w_load")] + \
+        [("w1_inv_scale", C.c_float), ("w2_inv_scale", C.c_float), ("ff_mode", C.c_int32), ("policy", C.c_int32)]
 
 
 class RolloutCfg(C.Structure):
@@ -61,7 +63,7 @@ SIGNATURES = {
     "evrp_pairwise_build": (C.c_int, [_FP, _FP, C.c_int, C.c_int, _FP, _FP, _FP]),
     "evrp_encoder_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "evrp_encoder_forward": (C.c_int, [C.POINTER(EncoderWeights), _FP, _FP, C.c_int, C.c_int, C.c_int,
-                                       _FP, _FP, _FP, _FP, C.c_size_t, _FP]),
+                                       _FP, _FP, _FP, _FP, _FP, C.c_size_t, _FP]),
     "evrp_rollout": (C.c_int, [C.POINTER(Phys), C.POINTER(DecoderWeights), C.POINTER(RolloutCfg),
                                _FP, _FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int,
                                _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_size_t, _FP]),

@@ -79,7 +79,10 @@ __device__ __forceinline__ T sel4(const T (&a)[4], int i) { return i == 0 ? a[0]
 
 // MODE: 0 greedy, 1 sample, 2 teacher-forced (separate instantiations keep each kernel's code small: the row phase
 // is instruction-cache sensitive)
-template <int MODE>
+// POLICY: 0 = the paper's model (route context through FF_tour, nets/DRLModel.py:203-237,394); 1 = nets/AM.py
+// (:336-337,352-377): query = fixed_ctx + project_step_context([emb[now], load]) -- no FF phase at all; `emb` is the
+// encoder's step table (emb @ project_step_context.weight[:, :128]^T), so the step context is one row read + one FMA
+template <int MODE, int POLICY>
 __global__ void __launch_bounds__(NT, 2)
 rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
                const float* __restrict__ emb, const float* __restrict__ kvl, const float* __restrict__ fixed_ctx,
@@ -171,6 +174,7 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
     __syncthreads();
     PT_MARK(3);
 
+    if constexpr (POLICY == 0) {
     // ---- FF_tour layer 1: h1[r][n] = relu(b1[n] + W1veh^T veh_r + W1max^T m_r); 8 rows x 8 cols per thread,
     //      accumulators packed as float2 pairs and updated with FFMA2 (2 fp32 FMAs per issue slot) ----
     {
@@ -256,6 +260,7 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
           *reinterpret_cast<float4*>(&sm.u.att.ctx[r0 + r][c0]) = make_float4(acc[r][0].x, acc[r][0].y, acc[r][1].x, acc[r][1].y);
       }
     }
+    }
     __syncthreads();
     PT_MARK(1);
 
@@ -298,12 +303,21 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       {
         const float4 fc = ldg4(fixed_ctx + (size_t)inst * D + lane * 4);
         const float4 en = ldg4(embb + (size_t)now * D + lane * 4);
-        const float4 cx = *reinterpret_cast<const float4*>(&sm.u.att.ctx[lr][lane * 4]);
-        const float4 b2 = ldg4(w.b2 + lane * 4);
-        q[0] = (fc.x + (cx.x + b2.x)) + en.x;
-        q[1] = (fc.y + (cx.y + b2.y)) + en.y;
-        q[2] = (fc.z + (cx.z + b2.z)) + en.z;
-        q[3] = (fc.w + (cx.w + b2.w)) + en.w;
+        if constexpr (POLICY == 0) {
+          const float4 cx = *reinterpret_cast<const float4*>(&sm.u.att.ctx[lr][lane * 4]);
+          const float4 b2 = ldg4(w.b2 + lane * 4);
+          q[0] = (fc.x + (cx.x + b2.x)) + en.x;
+          q[1] = (fc.y + (cx.y + b2.y)) + en.y;
+          q[2] = (fc.z + (cx.z + b2.z)) + en.z;
+          q[3] = (fc.w + (cx.w + b2.w)) + en.w;
+        } else {                                       // nets/AM.py:336-337: en = step_tab[now], + load * w[:, 128]
+          const float4 wl = ldg4(w.am_w_load + lane * 4);
+          const float ld = rs.load;
+          q[0] = fc.x + fmaf(ld, wl.x, en.x);
+          q[1] = fc.y + fmaf(ld, wl.y, en.y);
+          q[2] = fc.z + fmaf(ld, wl.z, en.z);
+          q[3] = fc.w + fmaf(ld, wl.w, en.w);
+        }
       }
       // ---- compat[h][i] = q_h . K[j_i, h] / 4 ; CH rows (CH x 512 B) in flight per warp ----
       constexpr int CH = 8;
@@ -472,7 +486,8 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       // ---- loads for the transition and the new mask, issued together ----
       const float dist = __ldg(Db + (size_t)now * S + c_node);
       const float slp = __ldg(Gb + (size_t)now * S + c_node);
-      const float4 ec = ldg4(embb + (size_t)c_node * D + lane * 4);
+      float4 ec = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (POLICY == 0) ec = ldg4(embb + (size_t)c_node * D + lane * 4);
       float dcj[4], gcj[4], d0j[4], g0j[4], d3j[4], s3j[4], dmj[4];
 #pragma unroll
       for (int jb = 0; jb < 4; ++jb) {
@@ -514,7 +529,7 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
         if (energy) energy[o] = e;
       }
       // ---- running max of visited embeddings (route_feature :207-214) ----
-      {
+      if constexpr (POLICY == 0) {
         float4 mm = *reinterpret_cast<float4*>(&sm.m[lr][lane * 4]);
         if (t == 0) mm = ec;
         else { mm.x = fmaxf(mm.x, ec.x); mm.y = fmaxf(mm.y, ec.y); mm.z = fmaxf(mm.z, ec.z); mm.w = fmaxf(mm.w, ec.w); }
@@ -651,7 +666,9 @@ int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evr
   if (B == 0) return 0;
   const int rows = B * cfg->n_replicas;
   cudaStream_t st = (cudaStream_t)stream;
-  if (w->ff_mode == 0) {
+  if (w->policy == 1 && !w->am_w_load) return -EVRP_E_BADARG;
+  if (w->policy != 1 && (!w->w1_veh || !w->w1_max || !w->b1 || !w->w2 || !w->b2)) return -EVRP_E_BADARG;
+  if (w->ff_mode == 0 && w->policy != 1) {
     float* station_ws = (float*)workspace;
     float* dem_ws = station_ws + (size_t)B * 2 * EVRP_MAX_S;
     float* m_ws = dem_ws + (size_t)rows * EVRP_MAX_S;
@@ -661,7 +678,8 @@ int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evr
   }
   const size_t smem = sizeof(DecodeSmem);
   const int mode = forced_actions ? 2 : (cfg->decode_type == EVRP_DECODE_SAMPLE ? 1 : 0);
-  auto kern = mode == 2 ? rollout_kernel<2> : mode == 1 ? rollout_kernel<1> : rollout_kernel<0>;
+  auto kern = w->policy == 1 ? (mode == 2 ? rollout_kernel<2, 1> : mode == 1 ? rollout_kernel<1, 1> : rollout_kernel<0, 1>)
+                             : (mode == 2 ? rollout_kernel<2, 0> : mode == 1 ? rollout_kernel<1, 0> : rollout_kernel<0, 0>);
   EVRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // balance: fill whole waves of (2 CTAs x SMs) slots and spread the rows evenly over them (<= RPC rows per CTA)
   int dev = 0, sms = 148;

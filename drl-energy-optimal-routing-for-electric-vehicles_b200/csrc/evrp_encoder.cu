@@ -285,8 +285,8 @@ size_t evrp_encoder_workspace_bytes(int B, int S) {
 }
 
 int evrp_encoder_forward(const evrp_encoder_weights* w, const float* static_xy, const float* dynamic, int B, int S,
-                         int F, float* emb, float* kvl, float* fixed_ctx, void* workspace, size_t workspace_bytes,
-                         void* stream) {
+                         int F, float* emb, float* kvl, float* fixed_ctx, float* step_tab, void* workspace,
+                         size_t workspace_bytes, void* stream) {
   using namespace evrp;
   if (!w || !static_xy || !dynamic || !emb || !kvl || !fixed_ctx || !workspace || B < 0 || S < 2 || F < 1 || F >= S ||
       w->n_layers < 0 || w->n_layers > EVRP_MAX_LAYERS)
@@ -357,6 +357,15 @@ int evrp_encoder_forward(const evrp_encoder_weights* w, const float* static_xy, 
     if ((rc = tc_gemm(0, emb, D, w->node_proj_hi, w->node_proj_lo, kvl, 384, M, 384, D, nullptr, nullptr, 0, nullptr, nullptr, sm_count, st))) return rc;
   } else {
     if ((rc = launch_sgemm<0>(emb, D, w->node_proj, 384, kvl, 384, M, 384, D, nullptr, nullptr, 0, nullptr, nullptr, st))) return rc;
+  }
+  if (step_tab) {                                        // nets/AM.py:336-337: emb @ project_step_context.weight[:, :128]^T
+    if (tcm) {
+      if (!w->step_proj_hi || !w->step_proj_lo) return -EVRP_E_BADARG;
+      if ((rc = tc_gemm(0, emb, D, w->step_proj_hi, w->step_proj_lo, step_tab, D, M, D, D, nullptr, nullptr, 0, nullptr, nullptr, sm_count, st))) return rc;
+    } else {
+      if (!w->step_proj) return -EVRP_E_BADARG;
+      if ((rc = launch_sgemm<0>(emb, D, w->step_proj, D, step_tab, D, M, D, D, nullptr, nullptr, 0, nullptr, nullptr, st))) return rc;
+    }
   }
   fixed_context_kernel<<<B, 128, 0, st>>>(emb, S, w->fixed_ctx_w, fixed_ctx);
   EVRP_LAUNCH_OK();

@@ -104,11 +104,7 @@ class AttentionModel(nn.Module):
         self.init_embed_station = nn.Linear(2, embedding_dim)
         self.init_embed = nn.Linear(3, embedding_dim)
         self.embedder = _EncoderParams(n_heads, embedding_dim, n_encode_layers, normalization)
-        self.tour = nn.Linear(3, embedding_dim, bias=False)
-        self.FF_tour = nn.Sequential(nn.Linear(2 * embedding_dim, 512), nn.ReLU(), nn.Linear(512, embedding_dim))
-        self.project_node_embeddings = nn.Linear(embedding_dim, 3 * embedding_dim, bias=False)
-        self.project_fixed_context = nn.Linear(embedding_dim, embedding_dim, bias=False)
-        self.project_out = nn.Linear(embedding_dim, embedding_dim, bias=False)
+        self._make_decoder_params(embedding_dim)
         self._pack_cache = None
         self._enc_ws = None
         self.max_steps = 1000                     # nets/DRLModel.py:255
@@ -119,6 +115,15 @@ class AttentionModel(nn.Module):
         self.ff_mode = 0                          # FF_tour inside the rollout kernel: 0 = tcgen05 (fp16-pair split), 1 = fp32 FFMA
         self.attn_mode = 0                        # encoder self-attention: 0 = tcgen05 3xTF32 (with gemm_mode 0), 1 = fp32 FFMA2
         self.profile_events = None                # list -> (start, end) CUDA events around each rollout kernel launch
+
+    policy = 0                                    # decoder query: 0 = nets/DRLModel.py:394 (route context), 1 = nets/AM.py
+
+    def _make_decoder_params(self, embedding_dim):       # nets/DRLModel.py:89-102, in the reference's order
+        self.tour = nn.Linear(3, embedding_dim, bias=False)
+        self.FF_tour = nn.Sequential(nn.Linear(2 * embedding_dim, 512), nn.ReLU(), nn.Linear(512, embedding_dim))
+        self.project_node_embeddings = nn.Linear(embedding_dim, 3 * embedding_dim, bias=False)
+        self.project_fixed_context = nn.Linear(embedding_dim, embedding_dim, bias=False)
+        self.project_out = nn.Linear(embedding_dim, embedding_dim, bias=False)
 
     # ------------------------------------------------------------------------------------------
     def set_decode_type(self, decode_type, temp=None):   # nets/DRLModel.py:104-107
@@ -178,7 +183,9 @@ class AttentionModel(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def encode(self, static, dynamic):
-        """kernels: init-embed + encoder layers + precompute.  -> emb [B,S,128], kvl [B,S,384], fixed [B,128]"""
+        """kernels: init-embed + encoder layers + precompute.  -> tab [B,S,128], kvl [B,S,384], fixed [B,128].
+        ``tab`` is the per-node table the decoder's step query reads at the current node: the node embeddings for
+        the paper's model, emb @ project_step_context.weight[:, :128]^T for the nets/AM.py variant."""
         L = _lib.lib()
         B, _, S = static.shape
         pk = self.packed_weights()
@@ -190,11 +197,12 @@ class AttentionModel(nn.Module):
         ws = self._enc_ws                                   # scratch activations: reused across calls
         if ws is None or ws.numel() < nbytes or ws.device != dev:
             ws = self._enc_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        tab = torch.empty(B, S, 128, device=dev) if self.policy == 1 else None
         rc = L.evrp_encoder_forward(pk["enc_struct"], _lib.ptr(static), _lib.ptr(dynamic), B, S, self.charging_num,
-                                    _lib.ptr(emb), _lib.ptr(kvl), _lib.ptr(fixed), _lib.ptr(ws), nbytes,
+                                    _lib.ptr(emb), _lib.ptr(kvl), _lib.ptr(fixed), _lib.ptr(tab), _lib.ptr(ws), nbytes,
                                     _lib.stream_ptr())
         _lib.check(rc, "evrp_encoder_forward")
-        return emb, kvl, fixed
+        return (emb if tab is None else tab), kvl, fixed
 
     def rollout(self, emb, kvl, fixed, dynamic, distances, slope, n_replicas=1, forced=None, uniforms=None,
                 save_trace=False, decode_type=None, max_steps=None):
@@ -277,7 +285,8 @@ class AttentionModel(nn.Module):
         # running buffers, nets/GraphEncoder.py:144-145), kernel rollout, teacher-forced differentiable log-probs
         emb, kvl, fixed = policy_math.encode_torch(self, static, dynamic)
         with torch.no_grad():
-            o = self.rollout(emb.detach().contiguous(), kvl.detach().contiguous(), fixed.detach().contiguous(),
+            tab = emb.detach() if self.policy == 0 else emb.detach() @ self.project_step_context.weight[:, :128].t()
+            o = self.rollout(tab.contiguous(), kvl.detach().contiguous(), fixed.detach().contiguous(),
                              dynamic, distances, slope, save_trace=True, forced=forced_actions)
         ll = policy_math.teacher_forced_ll(self, emb, kvl, fixed, o["pi"], o["mask_bits"], o["veh"], o["steps"])
         self.last_energy = o["E"]
@@ -317,3 +326,19 @@ class AttentionModel(nn.Module):
             minpis = pis[torch.arange(B, device=pis.device), arg]
             self.last_energy = torch.stack(energies, 1)[torch.arange(B, device=pis.device), arg]
         return mincosts, minpis
+
+
+class AttentionModelAM(AttentionModel):
+    """nets/AM.py:42 ``AttentionModel`` (the Kool-style ablation of the reference) on the same kernels.
+    Same constructor and API; 46 parameter tensors: no ``tour`` / ``FF_tour``, one ``project_step_context``
+    (Linear(129 -> 128), nets/AM.py:90) whose input is [emb[now], load] (nets/AM.py:352-377).  The decoder query is
+    ``fixed_ctx + project_step_context(...)`` (nets/AM.py:336-337) -- the embedding of the current node is NOT added
+    a second time.  On the device the 128 embedding columns are tabulated per node by the encoder (one more GEMM),
+    so a decode step reads one 512-byte row and adds ``load * weight[:, 128]``."""
+    policy = 1
+
+    def _make_decoder_params(self, embedding_dim):       # nets/AM.py:87-93, in the reference's order
+        self.project_node_embeddings = nn.Linear(embedding_dim, 3 * embedding_dim, bias=False)
+        self.project_fixed_context = nn.Linear(embedding_dim, embedding_dim, bias=False)
+        self.project_step_context = nn.Linear(embedding_dim + 1, embedding_dim, bias=False)
+        self.project_out = nn.Linear(embedding_dim, embedding_dim, bias=False)

@@ -108,6 +108,16 @@ def pack_weights(model):
     ew.node_proj = dev("node_proj", folded_node_projection(model).t())
     ew.fixed_ctx_w = dev("fixed_ctx_w", model.project_fixed_context.weight.t())
     dw = _lib.DecoderWeights()
+    dw.policy = int(getattr(model, "policy", 0))
+    if dw.policy == 1:                                 # nets/AM.py:90: project_step_context = [emb columns | load column]
+        Ws = model.project_step_context.weight
+        ew.step_proj = dev("step_proj", Ws[:, :128].t())
+        hi, lo = split_tf32(Ws[:, :128])
+        ew.step_proj_hi, ew.step_proj_lo = dev("step_proj_hi", hi), dev("step_proj_lo", lo)
+        dw.am_w_load = dev("am_w_load", Ws[:, 128])
+        dw.ff_mode = 1
+        keep["enc_struct"], keep["dec_struct"] = ew, dw
+        return keep
     dw.w1_veh = dev("w1_veh", folded_tour_weight(model).t())
     dw.w1_max = dev("w1_max", model.FF_tour[0].weight[:, 128:].t())
     dw.b1 = dev("b1", model.FF_tour[0].bias)
@@ -233,15 +243,19 @@ def teacher_forced_ll(model, emb, kvl, fixed, pi, mask_bits, veh, steps):
     evaluated as one batch."""
     B, T = pi.shape
     S, d, Hh = emb.shape[1], emb.shape[2], model.n_heads
-    idx = pi[..., None].expand(B, T, d)
-    visited = emb.gather(1, idx)                                           # emb[pi_t]
-    run_max = torch.cummax(visited, 1)[0]
-    run_max = torch.cat([torch.zeros_like(run_max[:, :1]), run_max[:, :-1]], 1)    # zeros before first pick
-    W1 = model.FF_tour[0]
-    h1 = torch.relu(Fn.linear(veh, folded_tour_weight(model)) + Fn.linear(run_max, W1.weight[:, 128:]) + W1.bias)
-    ctx = model.FF_tour[2](h1)
     now = torch.cat([torch.zeros_like(pi[:, :1]), pi[:, :-1]], 1)
-    q = (fixed[:, None] + ctx) + emb.gather(1, now[..., None].expand(B, T, d))
+    emb_now = emb.gather(1, now[..., None].expand(B, T, d))
+    if getattr(model, "policy", 0) == 1:                                   # nets/AM.py:336-337,352-377
+        q = fixed[:, None] + model.project_step_context(torch.cat([emb_now, veh[..., 0:1]], -1))
+    else:
+        idx = pi[..., None].expand(B, T, d)
+        visited = emb.gather(1, idx)                                       # emb[pi_t]
+        run_max = torch.cummax(visited, 1)[0]
+        run_max = torch.cat([torch.zeros_like(run_max[:, :1]), run_max[:, :-1]], 1)    # zeros before first pick
+        W1 = model.FF_tour[0]
+        h1 = torch.relu(Fn.linear(veh, folded_tour_weight(model)) + Fn.linear(run_max, W1.weight[:, 128:]) + W1.bias)
+        ctx = model.FF_tour[2](h1)
+        q = (fixed[:, None] + ctx) + emb_now
     live = torch.arange(T, device=pi.device)[None] < steps[:, None]
     mask = bits_to_mask(mask_bits, S)
     mask = mask | (~live[..., None] & (torch.arange(S, device=pi.device) == 0))   # padded steps: depot only

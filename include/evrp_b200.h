@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 10
+#define EVRP_ABI_VERSION 11
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -125,6 +125,11 @@ typedef struct {
                                           logits[j] = heads . lK[j]           (nets/DRLModel.py:436-444)     */
   const float *fixed_ctx_w;            /* [128,128]  project_fixed_context.weight^T                         */
   const float *node_proj_hi, *node_proj_lo;   /* [384,128] TF32 planes of node_proj^T (tcgen05 path)         */
+  /* nets/AM.py policy variant only, else NULL: project_step_context.weight[:, :128] (nets/AM.py:90),
+     the part of the step-context projection that multiplies emb[now] (nets/AM.py:336-337,352-377).  The encoder
+     tabulates it per node (step_tab below), so the rollout reads one 512-byte row per step instead of a mat-vec. */
+  const float *step_proj;                     /* [128,128] k-major (weight[:, :128]^T), gemm_mode 1            */
+  const float *step_proj_hi, *step_proj_lo;   /* [128,128] [out][in] TF32 planes, gemm_mode 0                  */
   int32_t gemm_mode;                   /* 0: tcgen05 3xTF32 (fp32-faithful, tensor cores); 1: fp32 FFMA GEMM   */
   int32_t attn_mode;                   /* self-attention core (QK^T, softmax, PV): 0: tcgen05 3xTF32, probabilities as
                                           the TMEM A operand (used when gemm_mode == 0); 1: fp32 FFMA2 kernel          */
@@ -133,10 +138,11 @@ typedef struct {
 size_t evrp_encoder_workspace_bytes(int B, int S);
 
 /* Eval-mode forward (BatchNorm folded to per-channel affine).  Outputs: emb [B,S,128] node embeddings,
- * kvl [B,S,384] = per node (glimpse-K | glimpse-V | folded logit-K), fixed_ctx [B,128]. */
+ * kvl [B,S,384] = per node (glimpse-K | glimpse-V | folded logit-K), fixed_ctx [B,128], and -- AM variant only,
+ * else NULL -- step_tab [B,S,128] = emb @ project_step_context.weight[:, :128]^T. */
 int evrp_encoder_forward(const evrp_encoder_weights* w, const float* static_xy /*[B,2,S]*/,
                          const float* dynamic /*[B,4,S]*/, int B, int S, int F,
-                         float* emb, float* kvl, float* fixed_ctx,
+                         float* emb, float* kvl, float* fixed_ctx, float* step_tab,
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -160,9 +166,14 @@ typedef struct {
      TF32 pair at half the bytes (evrp_b200/policy_math.py::split_f16); streamed by TMA every decode step           */
   const void *w1max_hi, *w1max_lo;    /* fp16 [512,128]  w1_scale * FF_tour.0.weight[:, 128:]                      */
   const void *w2_hi, *w2_lo;          /* fp16 [128,512]  w2_scale * FF_tour.2.weight                               */
+  const float *am_w_load;             /* [128] project_step_context.weight[:, 128] (the load column), policy 1     */
   float w1_inv_scale, w2_inv_scale;   /* 1 / scale (powers of two), applied to the fp32 accumulators               */
   int32_t ff_mode;       /* 0: FF_tour on tcgen05 tensor cores (3 x fp16 products, fp32-faithful), one 576-thread CTA
                             per SM; 1: fp32 FFMA inside a 256-thread CTA (2 per SM)                              */
+  int32_t policy;        /* step query of the decoder.  0: nets/DRLModel.py:394  fixed_ctx + FF_tour(route context) +
+                            emb[now] (the fields above).  1: nets/AM.py:336-337  fixed_ctx + project_step_context(
+                            [emb[now], load]) = fixed_ctx + step_tab[now] + load * am_w_load: no FF_tour, and the `emb`
+                            argument of evrp_rollout is the encoder's step_tab                                   */
 } evrp_decoder_weights;
 
 #define EVRP_DECODE_GREEDY 0

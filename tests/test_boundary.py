@@ -72,6 +72,48 @@ def test_constructor_reproduces_reference_initialisation():
         assert np.array_equal(sd[k].numpy(), W[k]), k
 
 
+def test_am_constructor_reproduces_reference_initialisation():
+    """nets/AM.py variant: torch.manual_seed(0) + construction == the reference's weights, bit for bit"""
+    W = np.load(os.path.join(GOLDEN, "weights_am_seed0.npz"))
+    torch.manual_seed(0)
+    m = evrp_b200.AttentionModelAM(128, 128, args_for(20), n_encode_layers=3)
+    sd = m.state_dict()
+    assert set(sd.keys()) == set(W.files) and len(list(m.parameters())) == 46
+    assert not hasattr(m, "FF_tour") and m.project_step_context.weight.shape == (128, 129)
+    for k in W.files:
+        assert np.array_equal(sd[k].numpy(), W[k]), k
+
+
+def test_am_training_math_matches_reference_gradients():
+    """nets/AM.py variant: encode_torch + teacher_forced_ll against the reference's REINFORCE gradients (CPU, fp32)"""
+    g = np.load(os.path.join(GOLDEN, "am_n20.npz"))
+    W = dict(np.load(os.path.join(GOLDEN, "weights_am_seed0.npz")))
+    m = evrp_b200.AttentionModelAM(128, 128, args_for(20), n_encode_layers=3)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in W.items()})
+    m.eval()
+    o = O.rollout(W, g["static"], g["dynamic"], g["distances"], g["slope"], forced=g["s_pi"], trace=True)
+    assert np.array_equal(o["R"], g["s_R"])
+    B, T = g["s_pi"].shape
+    mask = o["mask"].astype(bool)
+    bits = np.zeros((B, T, 4), np.int64)
+    for j in range(26):
+        bits[..., j >> 5] |= mask[..., j].astype(np.int64) << (j & 31)
+    bits = torch.from_numpy(bits.astype(np.uint32).view(np.int32).reshape(B, T, 4))
+    before = np.concatenate([g["dynamic"][:, None], o["dynamic"][:, :-1]], 1)
+    veh = torch.from_numpy(np.stack([before[:, :, 0, 0], before[:, :, 2, 0] / np.float32(80),
+                                     before[:, :, 3, 0] / np.float32(10)], -1).astype(np.float32))
+    emb, kvl, fixed = PM.encode_torch(m, torch.from_numpy(g["static"]), torch.from_numpy(g["dynamic"]))
+    ll = PM.teacher_forced_ll(m, emb, kvl, fixed, torch.from_numpy(g["s_pi"]), bits, veh,
+                              torch.full((B,), T, dtype=torch.int32))
+    assert float((ll.detach() - torch.from_numpy(g["s_ll"])).abs().max()) < 2e-5
+    (torch.from_numpy(g["s_adv"]) * ll.sum(1)).mean().backward()
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        ref = torch.from_numpy(g["grad." + k])
+        num += float((p.grad - ref).norm() ** 2); den += float(ref.norm() ** 2)
+    assert (num / den) ** 0.5 < 1e-4
+
+
 def test_dataset_reproduces_reference_rng_stream():
     g = np.load(os.path.join(GOLDEN, "greedy_n20.npz"))
     ds = evrp_b200.VehicleRoutingDataset(32, 20, 10., 80., 50., 4, 4, 5, 12345, args_for(20), device="cpu")

@@ -351,6 +351,108 @@ def test_sample_many_min_over_replicas(evrp, weights):
 
 
 # ---------------------------------------------------------------------------------------------
+# f3: nets/AM.py policy variant on the same kernels (rollout_kernel<MODE, 1>, encoder step table)
+# ---------------------------------------------------------------------------------------------
+def make_model_am(evrp, N, W):
+    a = args_for(N)
+    ds = evrp.VehicleRoutingDataset(2, N, 10., 80., 50., 4, 4, 5, 1, a)
+    m = evrp.AttentionModelAM(128, 128, a, n_encode_layers=3, update_dynamic=ds.update_dynamic,
+                              update_mask=ds.update_mask)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in W.items()})
+    return m.cuda().eval()
+
+
+@pytest.fixture(scope="module")
+def weights_am():
+    return dict(load("weights_am_seed0.npz"))
+
+
+@pytest.mark.parametrize("gemm_mode", [0, 1])
+def test_am_teacher_forced_rollout(evrp, weights_am, gemm_mode):
+    g = load("am_n20.npz")
+    m = make_model_am(evrp, 20, weights_am)
+    m.gemm_mode = gemm_mode
+    o = m.forward_forced(batch_of(g), torch.from_numpy(g["pi"]), save_trace=True)
+    assert o["status"] == 0
+    assert np.array_equal(o["R"].cpu().numpy(), g["R"])                       # rewards bit-exact
+    assert np.abs(o["ll"].cpu().numpy() - g["ll"]).max() < LOGP_TOL
+    steps = o["steps"].cpu().numpy()
+    got = mask_from_bits(o["mask_bits"], 26)
+    want = np.isfinite(g["t_log_p"]).astype(np.uint8)                         # feasible <=> finite log-prob
+    for b in range(len(steps)):
+        assert np.array_equal(got[b, :steps[b]], want[b, :steps[b]]), f"mask differs, instance {b}"
+
+
+def test_am_free_running_greedy_tours(evrp, weights_am):
+    g = load("am_n20.npz")
+    m = make_model_am(evrp, 20, weights_am)
+    m.set_decode_type("greedy")
+    with torch.no_grad():
+        pi, ll, R = m(batch_of(g))
+    pi, R = pi.cpu().numpy(), R.cpu().numpy()
+    ref, lp = g["pi"], g["t_log_p"]
+    exact = 0
+    for b in range(ref.shape[0]):
+        T = min(pi.shape[1], ref.shape[1])
+        neq = np.nonzero(pi[b, :T] != ref[b, :T])[0]
+        if len(neq) == 0:
+            exact += 1
+            assert abs(R[b].sum() - g["R"][b].sum()) <= 1e-4 * abs(g["R"][b].sum())
+            continue
+        t = neq[0]
+        assert abs(lp[b, t, pi[b, t]] - lp[b, t, ref[b, t]]) < NEAR_TIE, f"instance {b} diverges at step {t}"
+    assert exact >= 0.8 * ref.shape[0], f"only {exact}/{ref.shape[0]} tours identical"
+
+
+@pytest.mark.parametrize("N,B", [(50, 333), (100, 257)])
+def test_am_rollout_vs_oracle_larger_graphs(evrp, weights_am, N, B):
+    """free-running greedy on the GPU, then the oracle teacher-forced on those tours: costs bit-exact, ll 2e-5"""
+    static, dynamic, elev = O.generate_instances(B, N, seed=5)
+    D, G = O.pairwise_matrices(static, elev)
+    m = make_model_am(evrp, N, weights_am)
+    m.set_decode_type("greedy")
+    bat = tuple(torch.from_numpy(x).cuda() for x in (static, dynamic, D, G))
+    with torch.no_grad():
+        pi, ll, R = m(bat)
+    sub = slice(0, 48)                                                          # oracle replay on a subset (seconds)
+    o = O.rollout(weights_am, static[sub], dynamic[sub], D[sub], G[sub], forced=pi[sub].cpu().numpy())
+    assert np.array_equal(o["R"], R[sub].cpu().numpy())
+    lls = ll[sub].cpu().numpy()
+    Ts = int(np.isfinite(o["ll"]).all(0).sum())          # the subset finishes before the batch: the oracle's global
+    assert Ts > 2 * N and (lls[:, Ts:] == 0).all()       # termination rule (problems/EVRP.py:127) masks everything after
+    assert np.abs(o["ll"][:, :Ts] - lls[:, :Ts]).max() < LOGP_TOL
+    served = torch.zeros(B, N + 6, dtype=torch.bool, device="cuda").scatter_(1, pi, True)
+    assert bool(served[:, 6:].all())                                            # every customer visited
+
+
+def test_am_reinforce_gradients(evrp, weights_am):
+    g = load("am_n20.npz")
+    m = make_model_am(evrp, 20, weights_am)                                     # eval-mode BatchNorm, like the fixture
+    pi = torch.from_numpy(g["s_pi"]).cuda()
+    m.zero_grad()
+    pi2, ll, R = m(batch_of(g), forced_actions=pi)
+    assert torch.equal(pi2, pi) and np.array_equal(R.cpu().numpy(), g["s_R"])
+    assert np.abs(ll.detach().cpu().numpy() - g["s_ll"]).max() < LOGP_TOL
+    (torch.from_numpy(g["s_adv"]).cuda() * ll.sum(1)).mean().backward()
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        ref = torch.from_numpy(g["grad." + k]).cuda()
+        assert p.grad is not None, k
+        num += float((p.grad - ref).norm() ** 2); den += float(ref.norm() ** 2)
+    assert (num / den) ** 0.5 < 1e-3
+
+
+def test_am_sampled_rollout_and_sample_many(evrp, weights_am):
+    g = load("am_n20.npz")
+    m = make_model_am(evrp, 20, weights_am)
+    m.set_decode_type("sample")
+    mincost, minpi = m.sample_many(batch_of(g), batch_rep=64, iter_rep=1)
+    o = O.rollout(weights_am, g["static"], g["dynamic"], g["distances"], g["slope"], forced=minpi.cpu().numpy())
+    assert np.allclose(o["R"].sum(1), mincost.cpu().numpy(), rtol=1e-5)
+    assert (mincost.cpu().numpy() <= g["R"].sum(1) * 1.5).all()
+
+
+# ---------------------------------------------------------------------------------------------
 # a10: REINFORCE gradients, teacher-forced on the reference's sampled actions
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("mode", ["eval", "train"])
