@@ -77,14 +77,16 @@ def cpu_port_rate(N, sample, threads=None):
 
 
 class ClockSampler:
+    """ONE nvidia-smi process (started by rank 0) samples every GPU of the job: 8 ranks each polling NVML at 50 ms
+    measurably stall each other's launches on an 8-GPU box."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,index"
 
-    def __init__(self, index):
+    def __init__(self, indices, period_ms=50):
         self.rows, self.p = [], None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "50"],
+            self.p = subprocess.Popen(["nvidia-smi", "--id=" + ",".join(str(i) for i in indices), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", str(period_ms)],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -106,8 +108,14 @@ class ClockSampler:
         sm = sorted(float(r[0]) for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
-                "samples": len(rows), "power_w_max": max(float(r[2]) for r in rows)}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+               "samples": len(rows), "power_w_max": max(float(r[2]) for r in rows)}
+        gpus = sorted({r[7] for r in rows if len(r) >= 8})
+        if len(gpus) > 1:                                   # per-GPU median SM clock / max power (multi-GPU runs)
+            out["sm_mhz_min_gpu"] = min(sorted(float(r[0]) for r in rows if r[7] == g)[len([r for r in rows if r[7] == g]) // 2] for g in gpus)
+            out["per_gpu"] = {g: {"sm_mhz": sorted(float(r[0]) for r in rows if r[7] == g)[len([r for r in rows if r[7] == g]) // 2],
+                                  "power_w_max": max(float(r[2]) for r in rows if r[7] == g)} for g in gpus}
+        return out
 
 
 def run_reference(a):
@@ -188,9 +196,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    enc_events = []
+
     def step_resident():
         with torch.no_grad():
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
             emb, kvl, fixed = model.encode(st, dy)
+            ev[1].record()
+            enc_events.append(ev)
             return model.rollout(emb, kvl, fixed, dy, D, G)
 
     host_out = {}
@@ -208,11 +222,15 @@ def main():
             torch.cuda.synchronize()
             return host_out["cost"], host_out["pi"]
 
-    sampler = ClockSampler(local)                     # nvidia-smi takes a moment to start: launched before the warm-up
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    phys_ids = [int(x) for x in vis.split(",")][:world] if vis and all(x.strip().isdigit() for x in vis.split(",")) \
+        else list(range(world))
+    sampler = ClockSampler(phys_ids, 50 if world == 1 else 100) if rank == 0 else None   # started before the warm-up
     for _ in range(max(a.warmup, 3)):
         o = step_resident()
     # ---------------- device-resident timing ----------------
     model.profile_events = []
+    del enc_events[:]
     barrier()
     t0 = time.perf_counter()
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -225,9 +243,10 @@ def main():
     barrier()
     inst_steps = int(inst_steps_dev)
     t1 = time.perf_counter()
-    clocks = sampler.stop(t0, t1)
+    clocks = sampler.stop(t0, t1) if sampler is not None else None
     ms_total = e_start.elapsed_time(e_end)
     roll_ms = [s.elapsed_time(e) for s, e in model.profile_events]
+    enc_ms = [s.elapsed_time(e) for s, e in enc_events]
     model.profile_events = None
     T = int(o["pi"].shape[1])
     # ---------------- end-to-end through the public API, host buffers ----------------
@@ -242,7 +261,14 @@ def main():
     h2d = st_h.numel() * 4 + dy_h.numel() * 4
     d2h = cost.numel() * 4 + pi_host.numel() * 8
     tm = torch.tensor([ms_total, e2e_s * 1e3, float(np.mean(roll_ms)), float(inst_steps)], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        mine = torch.tensor([ms_total / a.steps, float(np.mean(enc_ms)), float(np.mean(roll_ms)), e2e_s * 1e3 / a.steps],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"columns": ["ms_per_step", "encoder_ms", "rollout_kernel_ms", "e2e_ms_per_step"],
+                    "rows": [[round(float(v), 3) for v in t.tolist()] for t in allr]}
         mx = tm.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = tm.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms_total, e2e_ms, roll_avg_ms = mx[0].item(), mx[1].item(), mx[2].item()
@@ -302,12 +328,27 @@ def main():
                              "dram_achieved": (traffic / (roll_avg_ms * 1e-3) / 1e9) if traffic else None,
                              "kernel_ms": roll_avg_ms, "kernel_share_of_step": roll_avg_ms / (ms_total / a.steps),
                              "algorithmic_bytes_per_launch": alg_bytes_per_launch}}
+        line["breakdown"] = {"encoder_ms": float(np.mean(enc_ms)), "rollout_kernel_ms": float(np.mean(roll_ms)),
+                             "note": "rank 0, CUDA events inside the timed region"}
+        if per_rank is not None:
+            line["per_rank"] = per_rank
         if train is not None:
             line["train"] = train
         if world == 1 and not a.no_cpu_baseline:
-            r, cores, dt, Tc = cpu_port_rate(N, a.cpu_sample)
-            line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{a.cpu_sample} EM-EVRP-{N} instances, greedy, numpy oracle port, {dt:.1f} s"}
+            # a clean child process (no CUDA context, no torch thread pools competing with numpy's BLAS threads)
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                                      "--warmup", "1", "--nodes", str(N), "--ref-sample", str(a.cpu_sample)],
+                                     capture_output=True, text=True, timeout=900).stdout.strip().splitlines()[-1]
+                ref = json.loads(out)
+                line["cpu_baseline"] = {"value": ref["value"], "unit": UNIT, "cores": ref["cpu_baseline"]["cores"],
+                                        "kind": "port", "sample": f"{a.cpu_sample} EM-EVRP-{N} instances, greedy, numpy "
+                                        f"oracle port, {ref['ms_per_step'] / 1e3:.1f} s (child process)"}
+            except Exception as ex:                                   # fall back to timing in this process
+                r, cores, dt, Tc = cpu_port_rate(N, a.cpu_sample)
+                line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
+                                        "sample": f"{a.cpu_sample} EM-EVRP-{N} instances, greedy, numpy oracle port, "
+                                                  f"{dt:.1f} s (in-process: {type(ex).__name__})"}
         _emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("EVRP_B200_LIB") or os.path.join(_HERE, "libevrp_b200.
 EVRP_MAX_S = 128
 ABI_VERSION = 11
 EVRP_MAX_LAYERS = 8
-ST_NAN_LOGIT, ST_INFEASIBLE_PICK, ST_STEP_CAP, ST_NONUNIFORM_DYNAMIC, ST_NO_FEASIBLE = 1, 2, 4, 8, 16
+ST_NAN_LOGIT, ST_INFEASIBLE_PICK, ST_STEP_CAP, ST_NONUNIFORM_DYNAMIC, ST_NO_FEASIBLE, ST_STUCK_AT_DEPOT = 1, 2, 4, 8, 16, 32
 DECODE_GREEDY, DECODE_SAMPLE = 0, 1
 
 _FP = C.c_void_p   # device pointers travel as void*

@@ -720,6 +720,13 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           if ((mk[0] | mk[1] | mk[2] | mk[3]) == 0u) {
             if (lane == 0) atomicOr(status, EVRP_ST_NO_FEASIBLE);
             done = true;
+          } else if (is_depot && mk[0] == 1u && (mk[1] | mk[2] | mk[3]) == 0u) {
+            // fixed point: back at the depot (state reset to load 1 / Start_SOC / t_limit, :254-276) with open demand
+            // that no move can reach, so rule 8 leaves the depot as the only choice -- every further step repeats
+            // (pi 0, log-prob 0, reward 0) until the reference's step cap (nets/DRLModel.py:255).  The outputs are
+            // already zero: retire the row now and let the host widen T to max_steps.
+            if (lane == 0) atomicOr(status, EVRP_ST_STUCK_AT_DEPOT);
+            done = true;
           } else if (t + 1 >= Tcap) {
             if (lane == 0) atomicOr(status, EVRP_ST_STEP_CAP);
             done = true;

@@ -264,6 +264,15 @@ class AttentionModel(nn.Module):
         out = dict(pi=pi[:, :T], ll=ll[:, :T], R=R[:, :T], E=E[:, :T], steps=steps, status=status, t_max=t_max)
         if save_trace:
             out.update(mask_bits=smask[:, :T], veh=sveh[:, :T])
+        if status & _lib.ST_STUCK_AT_DEPOT and forced is None and T < self.max_steps:
+            # an instance sits at the depot with demand nothing can reach: the reference keeps emitting (0, 0.0, 0.0)
+            # for it until its step cap (nets/DRLModel.py:255-260), so the batch is max_steps wide; the kernel retired
+            # the row at the fixed point, the remaining columns are zeros (``steps`` holds the step it got stuck at)
+            pad = self.max_steps - T
+            for k in ("pi", "ll", "R", "E", "mask_bits", "veh"):
+                if k in out:
+                    v = out[k]
+                    out[k] = torch.cat([v, v.new_zeros((v.shape[0], pad) + tuple(v.shape[2:]))], 1)
         return out
 
     # ------------------------------------------------------------------------------------------
@@ -288,7 +297,11 @@ class AttentionModel(nn.Module):
             tab = emb.detach() if self.policy == 0 else emb.detach() @ self.project_step_context.weight[:, :128].t()
             o = self.rollout(tab.contiguous(), kvl.detach().contiguous(), fixed.detach().contiguous(),
                              dynamic, distances, slope, save_trace=True, forced=forced_actions)
-        ll = policy_math.teacher_forced_ll(self, emb, kvl, fixed, o["pi"], o["mask_bits"], o["veh"], o["steps"])
+        Tl = o["pi"].shape[1] if forced_actions is not None else max(int(o["t_max"]), 1)   # columns beyond: stuck-row padding
+        ll = policy_math.teacher_forced_ll(self, emb, kvl, fixed, o["pi"][:, :Tl], o["mask_bits"][:, :Tl],
+                                           o["veh"][:, :Tl], o["steps"])
+        if Tl < o["pi"].shape[1]:                           # log-prob of the forced depot pick is exactly 0 (no gradient)
+            ll = torch.cat([ll, ll.new_zeros(ll.shape[0], o["pi"].shape[1] - Tl)], 1)
         self.last_energy = o["E"]
         return o["pi"], ll, o["R"]
 

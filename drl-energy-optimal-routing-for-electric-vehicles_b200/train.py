@@ -9,6 +9,7 @@ path:
     BaselineDataset         utils/reinforce_baselines.py:279-295
     clip_grad_norms         trainer.py:53-70
     reinforce_step          trainer.py:111-127   (one optimisation step)
+    eval_dataset / _eval_dataset / eval_widths   trainer.py:382-466 (test-time greedy / sampled evaluation sweep)
 
 Multi-GPU: one process per GPU, instances sharded by contiguous index range, weights
 replicated.  Rollouts need no collective.  Training adds exactly two NCCL collectives: one flat all-reduce of
@@ -411,3 +412,69 @@ def train(actor, baseline, optimizer, lr_scheduler, train_data, valid_data, batc
             log('Mean epoch loss/reward: %2.4f, %2.4f, %2.4f, took: %2.4fs (%d steps)' %
                 (mean_loss, mean_reward, mean_valid, time.time() - t0, steps))
     return epoch_reward, epoch_loss
+
+
+# ------------------------------------------------------------------------------------------------
+# test-time evaluation: trainer.py:382-384 width sweep, :388-419 eval_dataset, :421-466 _eval_dataset
+# ------------------------------------------------------------------------------------------------
+def _eval_dataset(model, dataset, width, softmax_temp, args):
+    """trainer.py:421-466: per batch ``sample_many`` with (batch_rep, iter_rep) derived from ``width`` exactly as the
+    reference does (greedy: width 0, one replica; sample: ``width`` replicas, split into ``iter_rep`` passes of
+    ``max_calc_batch_size`` when they do not fit).  -> [(costs [b] (device), seconds)].  Like the reference,
+    ``softmax_temp`` is accepted but NOT applied (``set_decode_type`` is called without it, trainer.py:424-425);
+    pass ``args.apply_softmax_temperature = True`` to apply it.  Beam search ('bs') is unreachable in the reference
+    (``self.problem`` undefined, nets/DRLModel.py:143) and raises here."""
+    import time
+    model.eval()
+    greedy = args.decode_strategy in ('bs', 'greedy')
+    if getattr(args, "apply_softmax_temperature", False):
+        model.set_decode_type("greedy" if greedy else "sample", temp=softmax_temp)
+    else:
+        model.set_decode_type("greedy" if greedy else "sample")
+    results = []
+    for batch in DataLoader(dataset, args.eval_batch_size, False, num_workers=0):
+        torch.cuda.synchronize()
+        start = time.time()
+        with torch.no_grad():
+            if args.decode_strategy == 'greedy':
+                assert width == 0, "Do not set width when using greedy"
+                assert args.eval_batch_size <= args.max_calc_batch_size, \
+                    "eval_batch_size should be smaller than calc batch size"
+                batch_rep, iter_rep = 1, 1
+            elif args.decode_strategy == 'sample':
+                if width * args.eval_batch_size > args.max_calc_batch_size:
+                    assert args.eval_batch_size == 1
+                    assert width % args.max_calc_batch_size == 0
+                    batch_rep, iter_rep = args.max_calc_batch_size, width // args.max_calc_batch_size
+                else:
+                    batch_rep, iter_rep = width, 1
+                assert batch_rep > 0
+            else:
+                raise NotImplementedError("decode_strategy 'bs': beam search is broken in the reference itself")
+            costs, _ = model.sample_many(batch, batch_rep=batch_rep, iter_rep=iter_rep)
+        torch.cuda.synchronize()
+        results.append((costs, time.time() - start))
+    return results
+
+
+def eval_dataset(test_data, width, softmax_temp, args, actor, csv_path=None):
+    """trainer.py:388-419 -> (mean cost, durations).  ``csv_path`` (optional) receives the reference's rows
+    [cost, batch duration] + the mean row; the reference's hard-coded ExperimentalLog/ path is not reproduced."""
+    import csv
+    results = _eval_dataset(actor, test_data, width, softmax_temp, args)
+    costs, durations = zip(*results)
+    costs = torch.cat(costs, 0).cpu().numpy()
+    if csv_path is not None:
+        with open(csv_path, "a", newline='') as f:
+            w = csv.writer(f)
+            per = len(costs) // max(len(durations), 1)
+            for i in range(len(costs)):
+                w.writerow([costs[i], durations[min(i // max(per, 1), len(durations) - 1)]])
+            w.writerow(["mean", float(np.mean(costs)), float(np.mean(durations))])
+    return float(np.mean(costs)), durations
+
+
+def eval_widths(test_data, args, actor, csv_path=None):
+    """trainer.py:382-384: one evaluation per entry of ``args.width`` (None -> [0])"""
+    widths = args.width if getattr(args, "width", None) is not None else [0]
+    return [eval_dataset(test_data, w, getattr(args, "softmax_temperature", 1.0), args, actor, csv_path)[0] for w in widths]

@@ -44,6 +44,11 @@ extern "C" {
 #define EVRP_ST_STEP_CAP 4         /* nets/DRLModel.py:255      an instance did not finish within max_steps  */
 #define EVRP_ST_NONUNIFORM_DYNAMIC 8 /* load/SOC/time rows of `dynamic` are not one scalar broadcast over S   */
 #define EVRP_ST_NO_FEASIBLE 16     /* every node masked for an unfinished instance                            */
+#define EVRP_ST_STUCK_AT_DEPOT 32  /* an instance is back at the depot with open demand nothing can reach (rule 8 of
+                                      problems/EVRP.py:220-221 leaves only the depot): the reference repeats (pi 0, ll 0,
+                                      R 0) until its 1000-step cap (nets/DRLModel.py:255); the kernel retires the row at
+                                      the fixed point, the outputs beyond are the zeros already there, and the caller
+                                      reports T = the step cap                                                  */
 
 /* Vehicle / problem constants.  problems/EVRP.py:21-41.  The caller fills the folded fp32 constants with
  * the SAME double-precision expressions the reference evaluates in Python, so that the state recipe is

@@ -452,6 +452,32 @@ def test_am_sampled_rollout_and_sample_many(evrp, weights_am):
     assert (mincost.cpu().numpy() <= g["R"].sum(1) * 1.5).all()
 
 
+def test_eval_dataset_width_sweep(evrp, weights, tmp_path):
+    """trainer.py:382-466: greedy (width 0) reproduces the rollout costs; 64 sampled replicas beat 4 on the batch mean;
+    the CSV has one row per instance + the mean row"""
+    import types
+    from evrp_b200 import train as T
+    g = load("greedy_n20.npz")
+    m, _ = make_model(evrp, 20, weights)
+    data = [tuple(torch.from_numpy(g[k][i]).cuda() for k in ("static", "dynamic", "distances", "slope"))
+            for i in range(g["static"].shape[0])]                        # what trainer.py:477 EVRPDataset yields
+    a = types.SimpleNamespace(decode_strategy="greedy", eval_batch_size=16, max_calc_batch_size=10000, width=None,
+                              softmax_temperature=1.0)
+    csvp = str(tmp_path / "eval.csv")
+    mean0, dur = T.eval_dataset(data, 0, 1.0, a, m, csv_path=csvp)
+    assert abs(mean0 - float(g["R"].sum(1).mean())) < 1e-4 * abs(mean0) and len(dur) == 2
+    assert len(open(csvp).read().strip().splitlines()) == len(data) + 1
+    a.decode_strategy, a.width = "sample", [4, 64]
+    c4, c64 = T.eval_widths(data, a, m)
+    assert c64 <= c4 + 1e-6 and c64 <= mean0 * 1.2
+    a.eval_batch_size, a.max_calc_batch_size = 1, 32                     # width split into iter_rep passes
+    mean_split, _ = T.eval_dataset(data[:3], 64, 1.0, a, m)
+    assert np.isfinite(mean_split)
+    a.decode_strategy = "bs"
+    with pytest.raises(NotImplementedError):
+        T.eval_dataset(data[:2], 2, 1.0, a, m)
+
+
 # ---------------------------------------------------------------------------------------------
 # a10: REINFORCE gradients, teacher-forced on the reference's sampled actions
 # ---------------------------------------------------------------------------------------------
@@ -584,6 +610,47 @@ def test_full_size_properties_and_shard_invariance(evrp, weights):
         assert np.array_equal(e[:, 0], Rn[:, t])
         now = pin[idx, t]
     assert (dyn[:, 1] == 0).all()                         # all demand served
+
+
+@pytest.mark.parametrize("ff_mode", [0, 1])
+def test_unreachable_customers_run_to_the_step_cap_like_the_reference(evrp, weights, ff_mode):
+    """Customers nothing can reach (t_limit = 2.5 h: a round trip beyond ~54 distance units does not fit): once
+    everything reachable is served the reference sits at the depot -- rule 8 (problems/EVRP.py:220-221) leaves only the
+    depot -- and emits (pi 0, ll 0, R 0) until its 1000-step cap (nets/DRLModel.py:255-260).  The kernel retires such a
+    row at the fixed point and the host widens T; outputs must equal the oracle's full 1000-step run."""
+    import types
+    TL = 2.5
+    static, dynamic, elev = O.generate_instances(6, 20, seed=31, t_limit=TL)
+    D, G = O.pairwise_matrices(static, elev)
+    c = O.EVRPConsts(t_limit=TL)
+    a = types.SimpleNamespace(CVRP_lib_test=False, Start_SOC=80., t_limit=TL, num_nodes=20, charging_num=5, velocity=50., obj="EM")
+    ds = evrp.VehicleRoutingDataset(2, 20, TL, 80., 50., 4, 4, 5, 1, a)
+    m = evrp.AttentionModel(128, 128, a, n_encode_layers=3, update_dynamic=ds.update_dynamic, update_mask=ds.update_mask)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()})
+    m = m.cuda().eval()
+    m.ff_mode = ff_mode
+    m.set_decode_type("greedy")
+    bat = tuple(torch.from_numpy(x).cuda() for x in (static, dynamic, D, G))
+    with torch.no_grad():
+        pi, ll, R = m(bat)
+    assert pi.shape[1] == 1000 and ll.shape[1] == 1000 and R.shape[1] == 1000
+    pin = pi.cpu().numpy()
+    o = O.rollout(weights, static, dynamic, D, G, consts=c, forced=pin[:, :150])
+    assert np.array_equal(o["R"], R.cpu().numpy()[:, :150])
+    assert np.abs(o["ll"] - ll.cpu().numpy()[:, :150]).max() < LOGP_TOL
+    free = O.rollout(weights, static, dynamic, D, G, consts=c, max_steps=1000)      # the reference's own loop ...
+    assert free["pi"].shape[1] == 1000                                              # ... really does run to the cap
+    same = (free["pi"] == pin).all(1)
+    assert same.sum() >= 5                                                          # (near-tie flips aside)
+    assert np.array_equal(free["R"][same], R.cpu().numpy()[same])
+    assert bool((pi[:, 150:] == 0).all()) and float(R[:, 150:].abs().sum()) == 0.0 and float(ll[:, 150:].abs().sum()) == 0.0
+    served = torch.zeros(6, 26, dtype=torch.bool, device="cuda").scatter_(1, pi, True)
+    assert not bool(served[:, 6:].all())                                            # some customer was never reached
+    # training forward: same width, zero log-prob (and no gradient) on the padded steps
+    m.train(); m.set_decode_type("sample")
+    pi2, ll2, R2 = m(bat)
+    assert pi2.shape[1] == 1000 and ll2.shape == pi2.shape and float(ll2[:, 300:].abs().sum()) == 0.0
+    ll2.sum().backward()
 
 
 def test_ragged_and_tiny_batches(evrp, weights):
