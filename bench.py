@@ -161,7 +161,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=8192, help="instances per GPU per step (BASELINE configs[3])")
     ap.add_argument("--nodes", type=int, default=100)
-    ap.add_argument("--cpu-sample", type=int, default=1024)
+    ap.add_argument("--cpu-sample", type=int, default=512)
     ap.add_argument("--ref-sample", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-steps", type=int, default=3, help="timed REINFORCE steps (0 = skip)")
@@ -337,13 +337,13 @@ def main():
         if world == 1 and not a.no_cpu_baseline:
             # a clean child process (no CUDA context, no torch thread pools competing with numpy's BLAS threads)
             try:
-                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2",
                                       "--warmup", "1", "--nodes", str(N), "--ref-sample", str(a.cpu_sample)],
                                      capture_output=True, text=True, timeout=900).stdout.strip().splitlines()[-1]
                 ref = json.loads(out)
                 line["cpu_baseline"] = {"value": ref["value"], "unit": UNIT, "cores": ref["cpu_baseline"]["cores"],
-                                        "kind": "port", "sample": f"{a.cpu_sample} EM-EVRP-{N} instances, greedy, numpy "
-                                        f"oracle port, {ref['ms_per_step'] / 1e3:.1f} s (child process)"}
+                                        "kind": "port", "sample": f"2 x {a.cpu_sample} EM-EVRP-{N} instances, greedy, numpy "
+                                        f"oracle port, {2 * ref['ms_per_step'] / 1e3:.1f} s (child process)"}
             except Exception as ex:                                   # fall back to timing in this process
                 r, cores, dt, Tc = cpu_port_rate(N, a.cpu_sample)
                 line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",

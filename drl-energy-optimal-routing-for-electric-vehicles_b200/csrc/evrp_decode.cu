@@ -72,6 +72,13 @@ __device__ unsigned long long g_phase_cycles[4];
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// K / V / logit-K records are consumed once per decode step: L2::evict_first (see evrp_decode_tc.cu)
+__device__ __forceinline__ float4 ldg4_pol(const float* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
 
 // register-array select without dynamic indexing (keeps the arrays out of local memory)
 template <typename T>
@@ -143,6 +150,8 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
     }
   }
   __syncthreads();
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   int t = 0;
 #ifdef EVRP_PHASE_TIMING
   long long pt_acc[4] = {0, 0, 0, 0};
@@ -324,7 +333,7 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       for (int i0 = 0; i0 < nf; i0 += CH) {
         float4 kv[CH];
 #pragma unroll
-        for (int a = 0; a < CH; ++a) kv[a] = ldg4(kvlb + (size_t)ws.list[min(i0 + a, nf - 1)] * 384 + lane * 4);
+        for (int a = 0; a < CH; ++a) kv[a] = ldg4_pol(kvlb + (size_t)ws.list[min(i0 + a, nf - 1)] * 384 + lane * 4, pol);
 #pragma unroll
         for (int a = 0; a < CH; ++a) {
           float p = fmaf(q[3], kv[a].w, fmaf(q[2], kv[a].z, fmaf(q[1], kv[a].y, q[0] * kv[a].x)));
@@ -355,7 +364,7 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
 #pragma unroll
           for (int a = 0; a < CH; ++a) {
             const int ii = min(i0 + a, nf - 1);
-            vv[a] = ldg4(kvlb + (size_t)ws.list[ii] * 384 + 128 + lane * 4);
+            vv[a] = ldg4_pol(kvlb + (size_t)ws.list[ii] * 384 + 128 + lane * 4, pol);
             pr[a] = (i0 + a < nf) ? ws.pc[hd][ii] : 0.f;
           }
 #pragma unroll
@@ -381,7 +390,7 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
             const int ii = min(i0 + u * 4 + grp, nf - 1);
             const float* p = kvlb + (size_t)ws.list[ii] * 384 + 256 + s8 * 4;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) lv[u][c] = ldg4(p + c * 32);
+            for (int c = 0; c < 4; ++c) lv[u][c] = ldg4_pol(p + c * 32, pol);
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {

@@ -105,6 +105,15 @@ __device__ unsigned long long g_row_cycles_tc[8];   // per-pass cycles of warp 0
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// Record loads of the row phase carry an L2::evict_first policy: every K / V / logit-K record is consumed exactly once
+// per decode step, so marking the line for early eviction keeps L2 for the records that the just-in-time prefetches
+// have requested but the passes have not read yet (25.2 -> 22.1 ms at B = 8192, N = 100; profiles/r1_l2_policy.md).
+__device__ __forceinline__ float4 ldg4_pol(const float* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -218,6 +227,9 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = sm.tmem_base;
+  uint64_t pol;                                   // record loads: consumed once per step (knob bit 16 off: evict_normal)
+  if (pf_lines & 0x10000) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
   int t = 0;
   uint32_t it = 0;          // weight-ring counter (producer and MMA issuer keep their own copy in step)
   uint32_t n_be = 0;        // b2_empty phases consumed by the converters (single staging buffer only)
@@ -432,7 +444,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         for (int i0 = 0; i0 < nf; i0 += CH) {
           float4 kv[CH];
 #pragma unroll
-          for (int a = 0; a < CH; ++a) kv[a] = ldg4(kvlb + (size_t)ws.list[i0 + a] * 384 + lane * 4);
+          for (int a = 0; a < CH; ++a) kv[a] = ldg4_pol(kvlb + (size_t)ws.list[i0 + a] * 384 + lane * 4, pol);
 #pragma unroll
           for (int a = 0; a < CH; ++a) {
             float p = fmaf(q[3], kv[a].w, fmaf(q[2], kv[a].z, fmaf(q[1], kv[a].y, q[0] * kv[a].x)));
@@ -476,7 +488,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
             float4 vv[CH]; float pr[CH];
 #pragma unroll
             for (int a = 0; a < CH; ++a) {
-              vv[a] = ldg4(kvlb + (size_t)ws.list[i0 + a] * 384 + 128 + lane * 4);
+              vv[a] = ldg4_pol(kvlb + (size_t)ws.list[i0 + a] * 384 + 128 + lane * 4, pol);
               pr[a] = ws.pc[hd][i0 + a];
             }
 #pragma unroll
@@ -503,7 +515,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
             for (int u = 0; u < 4; ++u) {
               const float* p = kvlb + (size_t)ws.list[i0 + u * 4 + grp] * 384 + 256 + s8 * 4;
 #pragma unroll
-              for (int c = 0; c < 4; ++c) lv[u][c] = ldg4(p + c * 32);
+              for (int c = 0; c < 4; ++c) lv[u][c] = ldg4_pol(p + c * 32, pol);
             }
             float au[4];
 #pragma unroll
@@ -807,8 +819,9 @@ int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, cons
   if (grid > rows) grid = rows;
   const int rows_per_cta = (rows + grid - 1) / grid;
   grid = (rows + rows_per_cta - 1) / rows_per_cta;
-  static int pf_lines = -1;              // tuning knob: bit 0 K, bit 2 V, bit 3 logit-K just-in-time prefetch
-  if (pf_lines < 0) { const char* l = getenv("EVRP_PF_LINES"); pf_lines = l ? atoi(l) : 13; }
+  static int pf_lines = -1;              // tuning knob: bit 0 K, bit 2 V, bit 3 logit-K just-in-time prefetch,
+                                         // bit 16 record loads with L2::evict_first
+  if (pf_lines < 0) { const char* l = getenv("EVRP_PF_LINES"); pf_lines = l ? atoi(l) : (13 | 0x10000); }
   static int walkers = -1;
   if (walkers < 0) { const char* e = getenv("EVRP_WALKERS"); walkers = e ? atoi(e) : ROW_WARPS + 2; }
   kern<<<grid, NT, SMEM_BYTES, st>>>(maps, *phys, *w, *cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope, station_ws,

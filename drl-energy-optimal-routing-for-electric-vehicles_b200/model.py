@@ -132,6 +132,10 @@ class AttentionModel(nn.Module):
             self.temp = temp
 
     # ------------------------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):                  # .cuda() / .to() / .float(): parameters may be re-created
+        self.__dict__["_tensor_list"] = None
+        return super()._apply(fn, *a, **k)
+
     def _device(self):
         return self.project_out.weight.device
 
@@ -156,7 +160,10 @@ class AttentionModel(nn.Module):
     def packed_weights(self):
         """Kernel-side weight layouts (k-major transposes, folded BatchNorm / project_out / tour), rebuilt only
         when a parameter or buffer changed (tensor version counters)."""
-        sd = list(self.parameters()) + list(self.buffers())
+        sd = self.__dict__.get("_tensor_list")
+        if sd is None:                               # walking the module tree costs ~0.6 ms: done once (reset by _apply)
+            sd = list(self.parameters()) + list(self.buffers())
+            self.__dict__["_tensor_list"] = sd
         key = (tuple(t._version for t in sd), tuple(t.data_ptr() for t in sd), self.training, self.gemm_mode, self.ff_mode, self.attn_mode)
         if self._pack_cache is None or self._pack_cache[0] != key:
             with torch.no_grad():
