@@ -225,7 +225,10 @@ def main():
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     phys_ids = [int(x) for x in vis.split(",")][:world] if vis and all(x.strip().isdigit() for x in vis.split(",")) \
         else list(range(world))
-    sampler = ClockSampler(phys_ids, 50 if world == 1 else 100) if rank == 0 else None   # started before the warm-up
+    # period: the profiling recipe's 200 ms -- polling NVML every 50 ms measurably slows the GPUs it queries (the device-
+    # timed loop ran 1.6 ms / step slower than the e2e loop that follows it, 3.5 ms with 4 GPUs polled)
+    period = int(os.environ.get("EVRP_BENCH_SAMPLER_MS", "200"))
+    sampler = ClockSampler(phys_ids, period) if rank == 0 and period > 0 else None        # started before the warm-up
     for _ in range(max(a.warmup, 3)):
         o = step_resident()
     # ---------------- device-resident timing ----------------
@@ -243,7 +246,7 @@ def main():
     barrier()
     inst_steps = int(inst_steps_dev)
     t1 = time.perf_counter()
-    clocks = sampler.stop(t0, t1) if sampler is not None else None
+    clocks = sampler.stop(t0, t1) if sampler is not None else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler off"]}
     ms_total = e_start.elapsed_time(e_end)
     roll_ms = [s.elapsed_time(e) for s, e in model.profile_events]
     enc_ms = [s.elapsed_time(e) for s, e in enc_events]
