@@ -229,8 +229,14 @@ def main():
     # timed loop ran 1.6 ms / step slower than the e2e loop that follows it, 3.5 ms with 4 GPUs polled)
     period = int(os.environ.get("EVRP_BENCH_SAMPLER_MS", "200"))
     sampler = ClockSampler(phys_ids, period) if rank == 0 and period > 0 else None        # started before the warm-up
+    # warm-up steps are EXACTLY the timed steps (same event records, same step-count accumulation): the first launch of
+    # any kernel -- including torch's int32 sum / int64 add behind `inst_steps_dev +=` -- loads its module lazily
+    # and stalls the stream for milliseconds (tools/loop_gap.py)
+    model.profile_events = []
+    inst_steps_dev = torch.zeros((), dtype=torch.int64, device=dev)
     for _ in range(max(a.warmup, 3)):
         o = step_resident()
+        inst_steps_dev += o["steps"].sum()
     # ---------------- device-resident timing ----------------
     model.profile_events = []
     del enc_events[:]
