@@ -201,6 +201,35 @@ def test_free_running_greedy_tours(evrp, weights, name, ff_mode):
     assert exact >= 0.8 * ref.shape[0], f"only {exact}/{ref.shape[0]} tours identical"
 
 
+def test_free_running_greedy_vs_oracle_at_headline_size(evrp, weights):
+    """EM-EVRP-100 (the bench workload), fresh synthetic instances: the GPU's free-running greedy tours against the
+    oracle's own free-running rollout; a differing tour must leave the oracle's tour at a near-tie of the oracle's
+    log-probs, and its cost must still equal the oracle's replay of that tour bit for bit"""
+    B, N = 40, 100
+    static, dynamic, elev = O.generate_instances(B, N, seed=77)
+    D, G = O.pairwise_matrices(static, elev)
+    m, _ = make_model(evrp, N, weights)
+    m.set_decode_type("greedy")
+    with torch.no_grad():
+        pi, ll, R = m(tuple(torch.from_numpy(x).cuda() for x in (static, dynamic, D, G)))
+    pi, R = pi.cpu().numpy(), R.cpu().numpy()
+    o = O.rollout(weights, static, dynamic, D, G, trace=True)
+    exact = 0
+    for b in range(B):
+        T = min(pi.shape[1], o["pi"].shape[1])
+        neq = np.nonzero(pi[b, :T] != o["pi"][b, :T])[0]
+        if len(neq) == 0:
+            exact += 1
+            assert np.array_equal(R[b, :T], o["R"][b, :T])
+            continue
+        t = neq[0]
+        gap = abs(o["log_p"][b, t, pi[b, t]] - o["log_p"][b, t, o["pi"][b, t]])
+        assert gap < NEAR_TIE, f"instance {b} diverges at step {t}, log-prob gap {gap} is not a near-tie"
+    assert exact >= 0.8 * B, f"only {exact}/{B} tours identical"
+    replay = O.rollout(weights, static, dynamic, D, G, forced=pi)
+    assert np.array_equal(replay["R"], R)
+
+
 @pytest.mark.parametrize("N,B", [(20, 300), (50, 777), (100, 1500)])
 def test_tensor_core_ff_matches_ffma_kernel(evrp, weights, N, B):
     """The two rollout kernels (FF_tour on tcgen05 3xTF32 vs fp32 FFMA) on ragged batches that leave CTAs partly
@@ -664,6 +693,44 @@ def test_ragged_and_tiny_batches(evrp, weights):
             pi, _, R = m(tuple(t[:B].contiguous() for t in full))
             assert torch.equal(R.sum(1), R_full[:B].sum(1))
             assert torch.equal(pi, pi_full[:B, :pi.shape[1]])
+
+
+@pytest.mark.parametrize("N,F,B", [(122, 5, 19), (37, 2, 65), (64, 9, 33), (3, 1, 5)])
+@pytest.mark.parametrize("ff_mode", [0, 1])
+def test_graph_size_and_station_count_edges(evrp, weights, N, F, B, ff_mode):
+    """S = N + F + 1 up to the kernel maximum of 128 nodes, station counts other than the default 5, node counts that
+    are not multiples of the 32-lane blocks, tiny graphs: free-running greedy on the GPU, oracle replay of the tours"""
+    import types
+    static, dynamic, elev = O.generate_instances(B, N, F=F, seed=100 + N)
+    D, G = O.pairwise_matrices(static, elev)
+    c = O.EVRPConsts(charging_num=F)
+    a = types.SimpleNamespace(CVRP_lib_test=False, Start_SOC=80., t_limit=10., num_nodes=N, charging_num=F, velocity=50., obj="EM")
+    ds = evrp.VehicleRoutingDataset(2, N, 10., 80., 50., 4, 4, F, 1, a)
+    m = evrp.AttentionModel(128, 128, a, n_encode_layers=3, update_dynamic=ds.update_dynamic, update_mask=ds.update_mask)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in weights.items()})
+    m = m.cuda().eval()
+    m.ff_mode = ff_mode
+    m.set_decode_type("greedy")
+    bat = tuple(torch.from_numpy(x).cuda() for x in (static, dynamic, D, G))
+    with torch.no_grad():
+        pi, ll, R = m(bat)
+    T = min(pi.shape[1], 400)
+    pin = pi.cpu().numpy()[:, :T]
+    o = O.rollout(weights, static, dynamic, D, G, consts=c, forced=pin)
+    assert np.array_equal(o["R"], R.cpu().numpy()[:, :T])
+    fin = np.isfinite(o["ll"]).all(0)                       # (columns after the whole batch is done: oracle's rule-0 mask)
+    # (beyond the reference's sizes -- S = 128 -- the log-probs reach -4.5 and fp32 summation-order noise scales with them)
+    assert (np.abs(o["ll"][:, fin] - ll.cpu().numpy()[:, :T][:, fin]) <= LOGP_TOL + 5e-6 * np.abs(o["ll"][:, fin])).all()
+    # stand-alone step kernels on the same instances, first steps of these tours
+    dyn = torch.from_numpy(dynamic).cuda(); now = torch.zeros(B, dtype=torch.int64, device="cuda")
+    dn = dynamic.copy(); nown = np.zeros(B, np.int64)
+    for t in range(min(T, 12)):
+        new_dyn, r = ds.update_dynamic(dyn, bat[2], bat[3], now, pi[:, t])
+        dn, e, _ = O.update_dynamic(c, dn, D, G, nown, pin[:, t])
+        assert np.array_equal(new_dyn.cpu().numpy(), dn) and np.array_equal(r[:, 0].cpu().numpy(), e[:, 0])
+        mask = ds.update_mask(new_dyn, bat[2], bat[3], pi[:, t])
+        assert np.array_equal(mask.cpu().numpy(), O.update_mask(c, dn, D, G, pin[:, t]))
+        dyn, now, nown = new_dyn, pi[:, t], pin[:, t]
 
 
 def test_errors_are_loud(evrp, weights):
