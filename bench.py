@@ -337,6 +337,16 @@ def main():
                              "dram_achieved": (traffic / (roll_avg_ms * 1e-3) / 1e9) if traffic else None,
                              "kernel_ms": roll_avg_ms, "kernel_share_of_step": roll_avg_ms / (ms_total / a.steps),
                              "algorithmic_bytes_per_launch": alg_bytes_per_launch}}
+        f_enc = (1278720 * S + 1536 * S * S + 32768) * B               # SURVEY §8d algorithmic encoder FLOPs per launch set
+        enc_s = float(np.mean(enc_ms)) * 1e-3
+        tf32_peak = pk["bf16_tflops"] / 2.0                            # kind::tf32 runs at half the bf16 rate
+        line["roofline_encoder"] = {"bound": "tensor", "kernels": "init_embed + 3 x (QKV gemm, attention, Wo gemm, FF1, FF2) "
+                                    "+ node projection + fixed context", "achieved": f_enc / enc_s / 1e12,
+                                    "executed": 3 * f_enc / enc_s / 1e12, "peak": tf32_peak, "peak_source": pk_src + " bf16 / 2",
+                                    "unit": "TFLOP/s", "frac": f_enc / enc_s / 1e12 / tf32_peak,
+                                    "frac_executed": 3 * f_enc / enc_s / 1e12 / tf32_peak, "ms": enc_s * 1e3,
+                                    "note": "every product is a 3-MMA error-compensated split (fp32-faithful): executed = 3 x "
+                                            "algorithmic; per-kernel tensor-pipe activity by ncu: profiles/r1_tcgemm_ncu.md"}
         line["breakdown"] = {"encoder_ms": float(np.mean(enc_ms)), "rollout_kernel_ms": float(np.mean(roll_ms)),
                              "note": "rank 0, CUDA events inside the timed region"}
         if per_rank is not None:
