@@ -229,6 +229,37 @@ def encode_torch(model, static, dynamic):
     return h, kvl, fixed
 
 
+class PointerLogProb(torch.autograd.Function):
+    """ll[b,t] of the recorded actions from the step queries q and the encoder records kvl, forward and backward on the
+    kernels of csrc/evrp_logp.cu (evrp_pointer_logp_forward / _backward).  Gradients flow to q (-> FF_tour, fixed
+    context, emb[now]) and kvl (-> node projection, encoder); the trace tensors are constants."""
+
+    @staticmethod
+    def forward(ctx, q, kvl, mask_bits, pi, steps, tanh_clipping, temp):
+        B, T, _ = q.shape
+        S = kvl.shape[1]
+        ll = torch.empty(B, T, device=q.device, dtype=torch.float32)
+        _lib.check(_lib.lib().evrp_pointer_logp_forward(
+            _lib.ptr(q), _lib.ptr(kvl), _lib.ptr(mask_bits), _lib.ptr(pi), _lib.ptr(steps), B, T, S, tanh_clipping, temp,
+            _lib.ptr(ll), _lib.stream_ptr()), "evrp_pointer_logp_forward")
+        ctx.save_for_backward(q, kvl, mask_bits, pi, steps)
+        ctx.consts = (tanh_clipping, temp)
+        return ll
+
+    @staticmethod
+    def backward(ctx, g):
+        q, kvl, mask_bits, pi, steps = ctx.saved_tensors
+        B, T, _ = q.shape
+        S = kvl.shape[1]
+        gq = torch.empty_like(q)
+        gk = torch.empty_like(kvl)
+        _lib.check(_lib.lib().evrp_pointer_logp_backward(
+            _lib.ptr(q), _lib.ptr(kvl), _lib.ptr(mask_bits), _lib.ptr(pi), _lib.ptr(steps), _lib.ptr(g.contiguous()),
+            B, T, S, ctx.consts[0], ctx.consts[1], _lib.ptr(gq), _lib.ptr(gk), _lib.stream_ptr()),
+            "evrp_pointer_logp_backward")
+        return gq, gk, None, None, None, None, None
+
+
 def bits_to_mask(bits, S):
     """[...,4] int32 mask words -> [...,S] bool"""
     j = torch.arange(S, device=bits.device)
@@ -256,6 +287,18 @@ def teacher_forced_ll(model, emb, kvl, fixed, pi, mask_bits, veh, steps):
         h1 = torch.relu(Fn.linear(veh, folded_tour_weight(model)) + Fn.linear(run_max, W1.weight[:, 128:]) + W1.bias)
         ctx = model.FF_tour[2](h1)
         q = (fixed[:, None] + ctx) + emb_now
+    if q.is_cuda:                                                          # product path: hand-written forward + backward
+        return PointerLogProb.apply(q.contiguous(), kvl.contiguous(), mask_bits.contiguous(), pi.contiguous(),
+                                    steps.to(torch.int32).contiguous(), float(model.tanh_clipping), float(model.temp))
+    # CPU tensors (tests only): the plain-PyTorch fp32 statement of the same op, the kernels' numerical reference
+    return pointer_log_prob_torch(q, kvl, mask_bits, pi, steps, model.tanh_clipping, model.temp, Hh)
+
+
+def pointer_log_prob_torch(q, kvl, mask_bits, pi, steps, tanh_clipping, temp, Hh=8):
+    """nets/DRLModel.py:411-452 + :182-190 for all T steps at once in plain PyTorch (fp32 reference of
+    csrc/evrp_logp.cu; materialises the [B,H,T,S] tensors the kernels avoid)."""
+    B, T, d = q.shape
+    S = kvl.shape[1]
     live = torch.arange(T, device=pi.device)[None] < steps[:, None]
     mask = bits_to_mask(mask_bits, S)
     mask = mask | (~live[..., None] & (torch.arange(S, device=pi.device) == 0))   # padded steps: depot only
@@ -266,9 +309,9 @@ def teacher_forced_ll(model, emb, kvl, fixed, pi, mask_bits, veh, steps):
     compat = compat.masked_fill(~mask[:, None], -math.inf)
     heads = torch.einsum("bhts,bshd->bthd", torch.softmax(compat, -1), gV).reshape(B, T, d)
     logits = torch.einsum("btd,bsd->bts", heads, lK) / math.sqrt(d)
-    if model.tanh_clipping > 0:
-        logits = torch.tanh(logits) * model.tanh_clipping
+    if tanh_clipping > 0:
+        logits = torch.tanh(logits) * tanh_clipping
     logits = logits.masked_fill(~mask, -math.inf)
-    log_p = torch.log_softmax(logits / model.temp, -1)
+    log_p = torch.log_softmax(logits / temp, -1)
     ll = log_p.gather(2, pi[..., None])[..., 0]
     return torch.where(live, ll, torch.zeros_like(ll))

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 11
+#define EVRP_ABI_VERSION 12
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -221,6 +221,23 @@ int evrp_reinforce_loss(const float* ll /*[B,T]*/, const float* R /*[B,T]*/, con
                         int baseline_is_scalar, int B, int T, float inv_global_batch, float* reward /*[B]*/,
                         float* advantage /*[B]*/, float* grad_ll /*[B,T]*/, float* loss /*[1]*/, float* scratch /*[B]*/,
                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (5) teacher-forced decoder log-probabilities and their backward (the differentiable half of
+ *     nets/DRLModel.py:379-452 for the REINFORCE step, trainer.py:115-127).  Inputs: the step queries
+ *     q[b,t,:] = fixed_ctx + route context + emb[now] (nets/DRLModel.py:394), the encoder's kvl records, and the
+ *     rollout's trace (mask bit words, actions, step counts).  forward: ll[b,t] = log_softmax(clip * tanh(
+ *     glimpse(q) . lK / sqrt(128)) / temp)[pi[b,t]], 0 on padded steps.  backward: d ll -> d q, d kvl.
+ *     No [B,H,T,S] tensor is materialised; one CTA per instance, d kvl accumulated in shared memory.
+ * ---------------------------------------------------------------------------------------------- */
+int evrp_pointer_logp_forward(const float* q /*[B,T,128]*/, const float* kvl /*[B,S,384]*/,
+                              const uint32_t* mask_bits /*[B,T,4]*/, const int64_t* pi /*[B,T]*/,
+                              const int32_t* steps /*[B]*/, int B, int T, int S, float tanh_clipping, float temp,
+                              float* ll /*[B,T]*/, void* stream);
+int evrp_pointer_logp_backward(const float* q, const float* kvl, const uint32_t* mask_bits, const int64_t* pi,
+                               const int32_t* steps, const float* grad_ll /*[B,T]*/, int B, int T, int S,
+                               float tanh_clipping, float temp, float* grad_q /*[B,T,128]*/,
+                               float* grad_kvl /*[B,S,384]*/, void* stream);
 
 #ifdef __cplusplus
 }

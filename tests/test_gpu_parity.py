@@ -540,6 +540,41 @@ def test_reinforce_gradients(evrp, weights, mode):
                 assert np.allclose(v.cpu().numpy(), g["bn_after/" + k], rtol=1e-4, atol=1e-5), k
 
 
+@pytest.mark.parametrize("B,T,S,clip,temp", [(5, 17, 26, 10., 1.0), (3, 40, 106, 10., 1.7), (2, 9, 128, 0., 1.0), (7, 23, 37, 10., 0.5)])
+def test_pointer_logp_kernels_match_torch(evrp, B, T, S, clip, temp):
+    """csrc/evrp_logp.cu (forward and backward) against the plain-PyTorch fp32 statement of the same op: random
+    queries / records, random feasibility masks (ragged, incl. single-node sets), padded steps"""
+    from evrp_b200 import policy_math as PM
+    gen = torch.Generator(device="cpu").manual_seed(B * 1000 + S)
+    q = torch.randn(B, T, 128, generator=gen).cuda().requires_grad_(True)
+    kvl = (torch.randn(B, S, 384, generator=gen) * 0.7).cuda().requires_grad_(True)
+    dens = torch.rand(B, T, 1, generator=gen)
+    mask = torch.rand(B, T, S, generator=gen) < dens
+    pi = torch.randint(0, S, (B, T), generator=gen)
+    mask.scatter_(2, pi[..., None], True)                                 # the chosen node is feasible
+    mask[0, 0] = False; mask[0, 0, pi[0, 0]] = True                       # a single-node set: ll = 0 exactly
+    bits = torch.zeros(B, T, 4, dtype=torch.int64)
+    for j in range(S):
+        bits[..., j >> 5] |= mask[..., j].long() << (j & 31)
+    bits = torch.from_numpy(bits.numpy().astype(np.uint32).view(np.int32).reshape(B, T, 4))
+    steps = torch.randint(1, T + 1, (B,), generator=gen).to(torch.int32)
+    steps[0] = T
+    bits, pi, steps = bits.cuda(), pi.cuda(), steps.cuda()
+    ll = PM.PointerLogProb.apply(q, kvl, bits, pi, steps, clip, temp)
+    w = torch.randn(B, T, generator=gen).cuda()
+    (ll * w).sum().backward()
+    gq, gk = q.grad.clone(), kvl.grad.clone()
+    q.grad = None; kvl.grad = None
+    ref = PM.pointer_log_prob_torch(q, kvl, bits, pi, steps, clip, temp)
+    (ref * w).sum().backward()
+    assert float(ll[0, 0]) == 0.0
+    assert float((ll - ref).abs().max()) < 2e-5
+    assert float((gq - q.grad).norm() / q.grad.norm()) < 1e-5
+    assert float((gk - kvl.grad).norm() / kvl.grad.norm()) < 1e-5
+    live = torch.arange(T, device="cuda")[None] < steps[:, None]
+    assert float(gq[~live].abs().max() if (~live).any() else 0.0) == 0.0   # padded steps carry no gradient
+
+
 def test_fused_reinforce_loss_kernel(evrp):
     """csrc/evrp_loss.cu against trainer.py:116-121 written out in torch (value and d loss / d ll)"""
     from evrp_b200 import train as T
