@@ -218,15 +218,53 @@ def encode_torch(model, static, dynamic):
         Hh, _, dk = att.W_query.shape
         # one [128,384] projection instead of 3 x 8 narrow ones (same products; autograd scatters the gradient back)
         Wqkv = torch.cat([w.permute(1, 0, 2).reshape(d, Hh * dk) for w in (att.W_query, att.W_key, att.W_val)], 1)
-        qkv = torch.mm(flat, Wqkv).view(B, S, 3, Hh, dk).permute(2, 0, 3, 1, 4)          # [3,B,H,S,dk]
-        attn = torch.softmax(torch.matmul(qkv[0], qkv[1].transpose(2, 3)) / math.sqrt(dk), -1)
-        heads = torch.matmul(attn, qkv[2])                                               # [B,H,S,dk]
-        out = torch.mm(heads.permute(0, 2, 1, 3).reshape(B * S, Hh * dk), att.W_out.reshape(-1, d)).view(B, S, d)
+        qkv = torch.mm(flat, Wqkv)                                                       # [B*S, Q|K|V x (h, dk)]
+        if qkv.is_cuda and Hh == 8 and dk == 16:              # product path: flash-style forward / backward kernels
+            heads_flat = SelfAttention.apply(qkv.view(B, S, 3 * d)).reshape(B * S, d)
+        else:                                                 # CPU tensors (tests): plain PyTorch statement of the same op
+            heads_flat = self_attention_torch(qkv.view(B, S, 3 * d), Hh).reshape(B * S, d)
+        out = torch.mm(heads_flat, att.W_out.reshape(-1, d)).view(B, S, d)
         h = _batch_norm(bn1, (h + out).view(-1, d), model.training).view(B, S, d)
         h = _batch_norm(bn2, (h + ff(h)).view(-1, d), model.training).view(B, S, d)
     kvl = Fn.linear(h, folded_node_projection(model))
     fixed = model.project_fixed_context(h.mean(1))
     return h, kvl, fixed
+
+
+def self_attention_torch(qkv, Hh=8):
+    """nets/GraphEncoder.py:81-102 in plain PyTorch: qkv [B,S,3*d] (Q | K | V, head-major) -> heads [B,S,d]
+    (fp32 reference of csrc/evrp_attn_train.cu; materialises the [B,H,S,S] scores)"""
+    B, S, d3 = qkv.shape
+    dk = d3 // 3 // Hh
+    x = qkv.view(B, S, 3, Hh, dk).permute(2, 0, 3, 1, 4)                               # [3,B,H,S,dk]
+    attn = torch.softmax(torch.matmul(x[0], x[1].transpose(2, 3)) / math.sqrt(dk), -1)
+    return torch.matmul(attn, x[2]).permute(0, 2, 1, 3).reshape(B, S, Hh * dk)
+
+
+class SelfAttention(torch.autograd.Function):
+    """encoder self-attention core of the training path on csrc/evrp_attn_train.cu (forward keeps the row
+    log-sum-exp, backward recomputes the probabilities; no [B,H,S,S] tensor)"""
+
+    @staticmethod
+    def forward(ctx, qkv):
+        qkv = qkv.contiguous()
+        B, S, _ = qkv.shape
+        heads = torch.empty(B, S, 128, device=qkv.device, dtype=torch.float32)
+        lse = torch.empty(B, 8, S, device=qkv.device, dtype=torch.float32)
+        _lib.check(_lib.lib().evrp_self_attention_forward(_lib.ptr(qkv), B, S, _lib.ptr(heads), _lib.ptr(lse),
+                                                          _lib.stream_ptr()), "evrp_self_attention_forward")
+        ctx.save_for_backward(qkv, heads, lse)
+        return heads
+
+    @staticmethod
+    def backward(ctx, g):
+        qkv, heads, lse = ctx.saved_tensors
+        B, S, _ = qkv.shape
+        gq = torch.empty_like(qkv)
+        _lib.check(_lib.lib().evrp_self_attention_backward(_lib.ptr(qkv), _lib.ptr(heads), _lib.ptr(lse),
+                                                           _lib.ptr(g.contiguous()), B, S, _lib.ptr(gq),
+                                                           _lib.stream_ptr()), "evrp_self_attention_backward")
+        return gq
 
 
 class PointerLogProb(torch.autograd.Function):

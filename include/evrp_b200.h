@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 12
+#define EVRP_ABI_VERSION 13
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -238,6 +238,15 @@ int evrp_pointer_logp_backward(const float* q, const float* kvl, const uint32_t*
                                const int32_t* steps, const float* grad_ll /*[B,T]*/, int B, int T, int S,
                                float tanh_clipping, float temp, float* grad_q /*[B,T,128]*/,
                                float* grad_kvl /*[B,S,384]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (6) encoder self-attention for the TRAINING path (nets/GraphEncoder.py:81-102 and its autograd backward): fp32 SIMT,
+ *     flash-style (no [B,H,S,S] tensor).  qkv [B,S,384] = Q | K | V projections, head-major inside each block;
+ *     heads [B,S,128]; lse [B,8,S] = row log-sum-exp of the scaled scores, kept for the backward.
+ * ---------------------------------------------------------------------------------------------- */
+int evrp_self_attention_forward(const float* qkv, int B, int S, float* heads, float* lse, void* stream);
+int evrp_self_attention_backward(const float* qkv, const float* heads, const float* lse, const float* grad_heads,
+                                 int B, int S, float* grad_qkv, void* stream);
 
 #ifdef __cplusplus
 }

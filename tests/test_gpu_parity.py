@@ -575,6 +575,22 @@ def test_pointer_logp_kernels_match_torch(evrp, B, T, S, clip, temp):
     assert float(gq[~live].abs().max() if (~live).any() else 0.0) == 0.0   # padded steps carry no gradient
 
 
+@pytest.mark.parametrize("B,S", [(3, 26), (5, 106), (2, 128), (4, 7)])
+def test_self_attention_train_kernels_match_torch(evrp, B, S):
+    """csrc/evrp_attn_train.cu (forward and backward) against the plain-PyTorch fp32 statement of nets/GraphEncoder.py:81-102"""
+    from evrp_b200 import policy_math as PM
+    gen = torch.Generator(device="cpu").manual_seed(S)
+    qkv = (torch.randn(B, S, 384, generator=gen) * 1.3).cuda().requires_grad_(True)
+    w = torch.randn(B, S, 128, generator=gen).cuda()
+    out = PM.SelfAttention.apply(qkv)
+    (out * w).sum().backward()
+    g = qkv.grad.clone(); qkv.grad = None
+    ref = PM.self_attention_torch(qkv, 8)
+    (ref * w).sum().backward()
+    assert float((out - ref).abs().max()) < 2e-6 * max(1.0, float(ref.abs().max()))
+    assert float((g - qkv.grad).norm() / qkv.grad.norm()) < 2e-6
+
+
 def test_fused_reinforce_loss_kernel(evrp):
     """csrc/evrp_loss.cu against trainer.py:116-121 written out in torch (value and d loss / d ll)"""
     from evrp_b200 import train as T
