@@ -306,8 +306,9 @@ def main():
             dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
         train = {"metric": "REINFORCE train step/sec (EM-EVRP-100)", "value": a.train_steps / tsec.item(),
                  "unit": "step/s", "per_gpu_batch": tb, "global_batch": tb * world, "decode_steps": int(out["T"]),
-                 "includes": "sampled rollout kernel + teacher-forced log-probs + fused loss kernel + backward + "
-                             "flat NCCL gradient all-reduce + clip + Adam"}
+                 "includes": "train-mode encoder (attention core on evrp_attn_train.cu, projections / FF / BatchNorm through "
+                             "autograd) + sampled rollout kernel + decoder log-prob forward / backward kernels "
+                             "(evrp_logp.cu) + fused loss kernel + flat NCCL gradient all-reduce + clip + Adam"}
     if rank == 0:
         pk, pk_src = peaks()
         a_step = 1568 * S + 2048                                   # SURVEY §8d algorithmic bytes per instance-step
@@ -329,7 +330,7 @@ def main():
                            "parallelism": f"dp{world} (instances sharded, no data-path collective)"},
                 "e2e": {"value": world * B * a.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h},
-                "gpu_launches": a.steps * (1 + 5 * 3 + 2 + 1),
+                "gpu_launches": a.steps * (1 + 5 * 3 + 2 + 1),      # init embed, 3 x (QKV, attention, Wo, FF1, FF2), node projection + fixed context, rollout
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "evrp::dtc::rollout_tc_kernel", "achieved": achieved,
                              "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s",
