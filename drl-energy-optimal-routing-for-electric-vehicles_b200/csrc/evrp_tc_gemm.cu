@@ -403,7 +403,7 @@ int tc_gemm(int epi, const float* A, int lda, const float* Wh, const float* Wl, 
             const float* bias, const float* resid, int ldr, const float* scale, const float* shift, int sm_count,
             cudaStream_t st) {
   using namespace tc;
-  if (N % BN || (K != 128 && K != 512)) return -EVRP_E_BADARG;
+  if (N % BN || K % BKB || K < BKB || (K != 128 && K != 512 && epi != 0)) return -EVRP_E_BADARG;
   CUtensorMap mh, ml, ma;
   int rc;
   if ((rc = make_weight_map(&mh, Wh, N, K, 0, BN))) return rc;
@@ -418,8 +418,26 @@ int tc_gemm(int epi, const float* A, int lda, const float* Wh, const float* Wl, 
     }
   } else if (epi == (EPI_BIAS | EPI_RESID | EPI_AFFINE)) {
     return launch<false, EPI_BIAS | EPI_RESID | EPI_AFFINE>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
+  } else if (epi == 0) {                       // plain product with streamed weights: any K that is a multiple of 32
+    return launch<false, 0>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
   }
   return -EVRP_E_BADARG;
 }
 
 }  // namespace evrp
+
+// C ABI: the encoder's fp32-faithful tensor-core GEMM on its own (training path: forward products and the
+// input-gradient products of the projections / feed-forward layers).
+extern "C" int evrp_gemm_3xtf32(int epilogue, const float* A, int lda, const float* W_hi, const float* W_lo, float* C,
+                                int ldc, int M, int N, int K, const float* bias, const float* resid, int ldr,
+                                const float* scale, const float* shift, void* stream) {
+  using namespace evrp::tc;
+  if (!A || !W_hi || !W_lo || !C || M < 0 || N < 1 || K < 1 || lda < K || ldc < N) return -EVRP_E_BADARG;
+  if (((epilogue & EPI_BIAS) && !bias) || ((epilogue & EPI_RESID) && !resid) || ((epilogue & EPI_AFFINE) && (!scale || !shift)))
+    return -EVRP_E_BADARG;
+  if (M == 0) return 0;
+  int dev = 0, sms = 148;
+  EVRP_CUDA_OK(cudaGetDevice(&dev));
+  EVRP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  return evrp::tc_gemm(epilogue, A, lda, W_hi, W_lo, C, ldc, M, N, K, bias, resid, ldr, scale, shift, sms, (cudaStream_t)stream);
+}

@@ -218,17 +218,101 @@ def encode_torch(model, static, dynamic):
         Hh, _, dk = att.W_query.shape
         # one [128,384] projection instead of 3 x 8 narrow ones (same products; autograd scatters the gradient back)
         Wqkv = torch.cat([w.permute(1, 0, 2).reshape(d, Hh * dk) for w in (att.W_query, att.W_key, att.W_val)], 1)
-        qkv = torch.mm(flat, Wqkv)                                                       # [B*S, Q|K|V x (h, dk)]
-        if qkv.is_cuda and Hh == 8 and dk == 16:              # product path: flash-style forward / backward kernels
+        if flat.is_cuda and Hh == 8 and dk == 16 and d == 128:
+            # product path: projections / feed-forward on the tcgen05 3xTF32 GEMM (forward and input gradients), the
+            # attention core on the flash-style kernels; BatchNorm (batch statistics) and weight gradients through torch
+            qkv = TCLinear.apply(flat, Wqkv.t(), None, None, False)                      # [B*S, Q|K|V x (h, dk)]
             heads_flat = SelfAttention.apply(qkv.view(B, S, 3 * d)).reshape(B * S, d)
-        else:                                                 # CPU tensors (tests): plain PyTorch statement of the same op
-            heads_flat = self_attention_torch(qkv.view(B, S, 3 * d), Hh).reshape(B * S, d)
+            x1 = TCLinear.apply(heads_flat, att.W_out.reshape(-1, d).t(), None, flat, False)        # h + heads @ W_out
+            h1 = _batch_norm(bn1, x1, model.training)
+            f = TCLinear.apply(h1, ff[0].weight, ff[0].bias, None, True)
+            x2 = TCLinear.apply(f, ff[2].weight, ff[2].bias, h1, False)                             # h1 + FF(h1)
+            h = _batch_norm(bn2, x2, model.training).view(B, S, d)
+            continue
+        # CPU tensors (tests): the plain PyTorch statement of the same layer
+        qkv = torch.mm(flat, Wqkv)
+        heads_flat = self_attention_torch(qkv.view(B, S, 3 * d), Hh).reshape(B * S, d)
         out = torch.mm(heads_flat, att.W_out.reshape(-1, d)).view(B, S, d)
         h = _batch_norm(bn1, (h + out).view(-1, d), model.training).view(B, S, d)
         h = _batch_norm(bn2, (h + ff(h)).view(-1, d), model.training).view(B, S, d)
-    kvl = Fn.linear(h, folded_node_projection(model))
+    if h.is_cuda and d == 128:
+        kvl = TCLinear.apply(h.reshape(B * S, d), folded_node_projection(model), None, None, False).view(B, S, 3 * d)
+    else:
+        kvl = Fn.linear(h, folded_node_projection(model))
     fixed = model.project_fixed_context(h.mean(1))
     return h, kvl, fixed
+
+
+_AFFINE_ID = {}
+
+
+def _affine_identity(dev, n):
+    key = (str(dev), n)
+    if key not in _AFFINE_ID:
+        _AFFINE_ID[key] = (torch.ones(n, device=dev), torch.zeros(n, device=dev))
+    return _AFFINE_ID[key]
+
+
+def tc_gemm(x, W, bias=None, resid=None, relu=False):
+    """((x @ W^T + bias) [relu] + resid) on the tcgen05 3xTF32 GEMM of csrc/evrp_tc_gemm.cu (evrp_gemm_3xtf32).
+    x [M,K], W [N,K] (nn.Linear layout), fp32 CUDA.  Epilogues the kernel does not instantiate are finished in torch."""
+    x = x.contiguous(); W = W.detach().contiguous()
+    M, K = x.shape
+    N = W.shape[0]
+    assert W.shape[1] == K and N % 128 == 0 and K % 32 == 0, (tuple(x.shape), tuple(W.shape))
+    hi, lo = split_tf32(W)
+    y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    one, zero = _affine_identity(x.device, N)
+    epi, post_bias, post_relu, post_resid = 0, None, False, None
+    if bias is not None and relu and resid is None and K == 128:
+        epi = 1 | 2
+    elif bias is None and not relu and resid is not None and K == 128:
+        epi = 4 | 8
+    elif bias is not None and not relu and resid is not None and K == 512:
+        epi = 1 | 4 | 8
+    else:
+        post_bias, post_relu, post_resid = bias, relu, resid
+    b = bias.detach().contiguous() if (epi & 1) else None
+    r = resid.detach().contiguous() if (epi & 4) else None
+    _lib.check(_lib.lib().evrp_gemm_3xtf32(epi, _lib.ptr(x), K, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(y), N, M, N, K,
+                                           _lib.ptr(b), _lib.ptr(r), N, _lib.ptr(one) if epi & 8 else None,
+                                           _lib.ptr(zero) if epi & 8 else None, _lib.stream_ptr()), "evrp_gemm_3xtf32")
+    if post_bias is not None:
+        y = y + post_bias
+    if post_relu:
+        y = torch.relu(y)
+    if post_resid is not None:
+        y = y + post_resid
+    return y
+
+
+class TCLinear(torch.autograd.Function):
+    """y = ((x @ W^T + bias) [relu] + resid): the forward product and the input-gradient product run on the tcgen05
+    3xTF32 GEMM (fp32-faithful); the weight gradient (contraction over all B*S rows) is a cuBLAS fp32 GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, resid, relu):
+        y = tc_gemm(x.detach(), W, bias, resid.detach() if resid is not None else None, relu)
+        ctx.save_for_backward(x, W, y if relu else None)
+        ctx.flags = (bias is not None, resid is not None, relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W, y = ctx.saved_tensors
+        has_bias, has_resid, relu = ctx.flags
+        gy = gy.contiguous()
+        if relu:
+            gy = gy * (y > 0)
+        N, K = W.shape
+        gx = gW = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = tc_gemm(gy, W.t()) if (K % 128 == 0 and N % 32 == 0) else gy @ W
+        if ctx.needs_input_grad[1]:
+            gW = gy.t() @ x
+        if has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(0)
+        return gx, gW, gb, (gy if has_resid else None), None
 
 
 def self_attention_torch(qkv, Hh=8):
@@ -322,9 +406,15 @@ def teacher_forced_ll(model, emb, kvl, fixed, pi, mask_bits, veh, steps):
         run_max = torch.cummax(visited, 1)[0]
         run_max = torch.cat([torch.zeros_like(run_max[:, :1]), run_max[:, :-1]], 1)    # zeros before first pick
         W1 = model.FF_tour[0]
-        h1 = torch.relu(Fn.linear(veh, folded_tour_weight(model)) + Fn.linear(run_max, W1.weight[:, 128:]) + W1.bias)
-        ctx = model.FF_tour[2](h1)
-        q = (fixed[:, None] + ctx) + emb_now
+        if emb.is_cuda and d == 128:                                       # FF_tour over all B*T steps on the tcgen05 GEMM
+            hm = TCLinear.apply(run_max.reshape(B * T, d), W1.weight[:, 128:], None, None, False)
+            h1 = torch.relu(Fn.linear(veh, folded_tour_weight(model)).view(B * T, -1) + hm + W1.bias)
+            base = (fixed[:, None] + emb_now).reshape(B * T, d)
+            q = TCLinear.apply(h1, model.FF_tour[2].weight, model.FF_tour[2].bias, base, False).view(B, T, d)
+        else:
+            h1 = torch.relu(Fn.linear(veh, folded_tour_weight(model)) + Fn.linear(run_max, W1.weight[:, 128:]) + W1.bias)
+            ctx = model.FF_tour[2](h1)
+            q = (fixed[:, None] + ctx) + emb_now
     if q.is_cuda:                                                          # product path: hand-written forward + backward
         return PointerLogProb.apply(q.contiguous(), kvl.contiguous(), mask_bits.contiguous(), pi.contiguous(),
                                     steps.to(torch.int32).contiguous(), float(model.tanh_clipping), float(model.temp))

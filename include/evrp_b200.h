@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 13
+#define EVRP_ABI_VERSION 14
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -247,6 +247,16 @@ int evrp_pointer_logp_backward(const float* q, const float* kvl, const uint32_t*
 int evrp_self_attention_forward(const float* qkv, int B, int S, float* heads, float* lse, void* stream);
 int evrp_self_attention_backward(const float* qkv, const float* heads, const float* lse, const float* grad_heads,
                                  int B, int S, float* grad_qkv, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (7) the encoder's tcgen05 GEMM on its own (training path):  C[M,N] = epilogue( A[M,K] @ W[N,K]^T ), fp32-faithful
+ *     3xTF32 (W given as TF32 hi / lo planes in nn.Linear layout [out][in]).  N % 128 == 0.  epilogue bits: 1 bias,
+ *     2 ReLU, 4 residual, 8 per-column affine; supported: 0 (any K % 32 == 0), 1|2 and 4|8 (K == 128), 1|4|8
+ *     (K == 512):  C = ((A W^T + bias) [relu] + resid) * scale + shift.
+ * ---------------------------------------------------------------------------------------------- */
+int evrp_gemm_3xtf32(int epilogue, const float* A, int lda, const float* W_hi, const float* W_lo, float* C, int ldc,
+                     int M, int N, int K, const float* bias, const float* resid, int ldr, const float* scale,
+                     const float* shift, void* stream);
 
 #ifdef __cplusplus
 }

@@ -520,8 +520,11 @@ def test_reinforce_gradients(evrp, weights, mode):
     m.zero_grad()
     pi2, ll, R = m(batch_of(g), forced_actions=pi)
     assert torch.equal(pi2, pi) and np.array_equal(R.cpu().numpy(), g["R"])
-    # train-mode BatchNorm divides by batch statistics of 416 rows: cuBLAS-vs-MKL summation noise is amplified ~3x
-    assert np.abs(ll.detach().cpu().numpy() - g[f"ll_{mode}"]).max() < (LOGP_TOL if mode == "eval" else 6e-5)
+    # train-mode BatchNorm divides by the batch statistics of only 416 rows, which amplifies the rounding-level differences
+    # of the products (3xTF32 split here, MKL fp32 in the reference); the log-probs of this fixture reach -11.8, so the
+    # bar is relative there: 5e-5 + 2e-5 |ll| (measured 1.4e-4 at |ll| = 11.8, mean 1e-5)
+    dll = np.abs(ll.detach().cpu().numpy() - g[f"ll_{mode}"])
+    assert (dll.max() < LOGP_TOL) if mode == "eval" else (dll <= 5e-5 + 2e-5 * np.abs(g[f"ll_{mode}"])).all()
     loss = (torch.from_numpy(g["adv"]).cuda() * ll.sum(1)).mean()
     loss.backward()
     assert abs(loss.item() - float(g[f"loss_{mode}"])) < 1e-4 * abs(float(g[f"loss_{mode}"]))
@@ -589,6 +592,41 @@ def test_self_attention_train_kernels_match_torch(evrp, B, S):
     (ref * w).sum().backward()
     assert float((out - ref).abs().max()) < 2e-6 * max(1.0, float(ref.abs().max()))
     assert float((g - qkv.grad).norm() / qkv.grad.norm()) < 2e-6
+
+
+@pytest.mark.parametrize("M,K,N,bias,resid,relu", [
+    (1000, 128, 384, False, False, False), (777, 128, 128, False, True, False), (2600, 128, 512, True, False, True),
+    (515, 512, 128, True, True, False), (300, 384, 128, False, False, False), (129, 512, 128, False, False, False),
+    (64, 128, 128, True, False, False)])
+def test_tc_linear_matches_torch(evrp, M, K, N, bias, resid, relu):
+    """policy_math.TCLinear (tcgen05 3xTF32 GEMM forward + input gradient, evrp_gemm_3xtf32) against fp32 torch in
+    double-checked form: every epilogue combination the training path uses, ragged M, K = 128 / 384 / 512"""
+    from evrp_b200 import policy_math as PM
+    gen = torch.Generator(device="cpu").manual_seed(M + K)
+    x = torch.randn(M, K, generator=gen).cuda().requires_grad_(True)
+    W = (torch.randn(N, K, generator=gen) / K ** 0.5).cuda().requires_grad_(True)
+    b = torch.randn(N, generator=gen).cuda().requires_grad_(True) if bias else None
+    r = torch.randn(M, N, generator=gen).cuda().requires_grad_(True) if resid else None
+    w = torch.randn(M, N, generator=gen).cuda()
+    y = PM.TCLinear.apply(x, W, b, r, relu)
+    (y * w).sum().backward()
+    got = [t.grad.clone() for t in (x, W, b, r) if t is not None]
+    for t in (x, W, b, r):
+        if t is not None:
+            t.grad = None
+    ref = x.double() @ W.double().t()
+    if bias:
+        ref = ref + b.double()
+    if relu:
+        ref = torch.relu(ref)
+    if resid:
+        ref = ref + r.double()
+    (ref * w.double()).sum().backward()
+    want = [t.grad for t in (x, W, b, r) if t is not None]
+    # 3xTF32 drops the lo x lo term (2^-22 per product): worst element 3.6e-6 of the output range at K = 512
+    assert float((y.double() - ref).abs().max()) < 6e-6 * max(1.0, float(ref.abs().max()))
+    for g, wv in zip(got, want):
+        assert float((g.double() - wv.double()).norm() / wv.double().norm()) < 1e-5     # fp32 noise of contractions up to 2600 long
 
 
 def test_fused_reinforce_loss_kernel(evrp):
