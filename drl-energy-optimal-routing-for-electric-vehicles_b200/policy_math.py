@@ -199,9 +199,19 @@ class _GlobalBatchNorm(torch.autograd.Function):
         return gx, gw, gb, None
 
 
-def _batch_norm(bn, x, training):
+def _batch_norm(bn, x, training, force_global=False):
     import torch.distributed as dist
-    if training and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if training and dist.is_available() and dist.is_initialized() and (dist.get_world_size() > 1 or force_global):
+        if x.is_cuda:
+            # CUDA: the same global-batch statistics through PyTorch's fused synchronized-BatchNorm kernels
+            # (batch_norm_stats / gather_stats_with_counts / elemt / backward_reduce / backward_elemt): one all-gather
+            # forward, one all-reduce backward, no chain of elementwise passes over [B*S,128]
+            from torch.nn.modules._functions import SyncBatchNorm as _SyncBN
+            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
+            with torch.no_grad():
+                bn.num_batches_tracked += 1
+            return _SyncBN.apply(x.contiguous(), bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, m,
+                                 dist.group.WORLD, dist.get_world_size())
         return _GlobalBatchNorm.apply(x, bn.weight, bn.bias, bn)
     return bn(x)
 

@@ -629,6 +629,36 @@ def test_tc_linear_matches_torch(evrp, M, K, N, bias, resid, relu):
         assert float((g.double() - wv.double()).norm() / wv.double().norm()) < 1e-5     # fp32 noise of contractions up to 2600 long
 
 
+def test_global_batch_norm_cuda_path_matches_batchnorm1d(evrp):
+    """the multi-rank BatchNorm path of the training forward (global-batch statistics) on CUDA, exercised through a
+    one-rank NCCL group: outputs, gradients and running statistics equal nn.BatchNorm1d on the same batch"""
+    import torch.distributed as dist
+    from evrp_b200 import policy_math as PM
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29577", rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+    try:
+        torch.manual_seed(3)
+        x = (torch.randn(777, 128, device="cuda") * 2 + 0.5).requires_grad_(True)
+        w = torch.randn(777, 128, device="cuda")
+        a, b = torch.nn.BatchNorm1d(128).cuda().train(), torch.nn.BatchNorm1d(128).cuda().train()
+        with torch.no_grad():
+            for bn in (a, b):
+                bn.weight.copy_(torch.linspace(0.5, 1.5, 128)); bn.bias.copy_(torch.linspace(-0.2, 0.2, 128))
+        ya = PM._batch_norm(a, x, True, force_global=True)
+        (ya * w).sum().backward()
+        ga, gwa, gba = x.grad.clone(), a.weight.grad.clone(), a.bias.grad.clone()
+        x.grad = None
+        yb = b(x)
+        (yb * w).sum().backward()
+        assert torch.allclose(ya, yb, atol=2e-5) and torch.allclose(ga, x.grad, atol=2e-5)
+        assert torch.allclose(gwa, b.weight.grad, rtol=1e-4, atol=1e-3) and torch.allclose(gba, b.bias.grad, rtol=1e-4, atol=1e-3)
+        assert torch.allclose(a.running_mean, b.running_mean, atol=1e-6) and torch.allclose(a.running_var, b.running_var, rtol=1e-5)
+        assert int(a.num_batches_tracked) == int(b.num_batches_tracked) == 1
+    finally:
+        dist.destroy_process_group()
+
+
 def test_fused_reinforce_loss_kernel(evrp):
     """csrc/evrp_loss.cu against trainer.py:116-121 written out in torch (value and d loss / d ll)"""
     from evrp_b200 import train as T
