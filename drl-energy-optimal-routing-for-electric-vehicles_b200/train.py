@@ -433,7 +433,8 @@ def _eval_dataset(model, dataset, width, softmax_temp, args):
         model.set_decode_type("greedy" if greedy else "sample")
     results = []
     for batch in DataLoader(dataset, args.eval_batch_size, False, num_workers=0):
-        torch.cuda.synchronize()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
         start = time.time()
         with torch.no_grad():
             if args.decode_strategy == 'greedy':
@@ -452,7 +453,8 @@ def _eval_dataset(model, dataset, width, softmax_temp, args):
             else:
                 raise NotImplementedError("decode_strategy 'bs': beam search is broken in the reference itself")
             costs, _ = model.sample_many(batch, batch_rep=batch_rep, iter_rep=iter_rep)
-        torch.cuda.synchronize()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
         results.append((costs, time.time() - start))
     return results
 

@@ -248,3 +248,43 @@ def test_test_set_pickle_round_trip(tmp_path):
     for i, item in enumerate(back):
         for got, want in zip(item, ds[i + 1]):
             assert torch.equal(got, torch.as_tensor(want).float().cpu())
+
+
+def test_eval_dataset_derives_replicas_like_the_reference(tmp_path):
+    """trainer.py:421-466: (batch_rep, iter_rep) from width / eval_batch_size / max_calc_batch_size, the greedy and
+    beam-search guards, the CSV -- host logic only, with a stub model"""
+    import types
+    from evrp_b200 import train as T
+    calls = []
+
+    class Stub:
+        def eval(self): pass
+        def set_decode_type(self, t, temp=None): calls.append(("type", t, temp))
+        def sample_many(self, batch, batch_rep=1, iter_rep=1):
+            calls.append(("sample_many", batch[0].shape[0], batch_rep, iter_rep))
+            return torch.full((batch[0].shape[0],), float(batch_rep * iter_rep)), None
+
+    data = [(torch.zeros(2, 5), torch.zeros(4, 5), torch.zeros(5, 5), torch.zeros(5, 5)) for _ in range(6)]
+    a = types.SimpleNamespace(decode_strategy="greedy", eval_batch_size=4, max_calc_batch_size=100, width=None,
+                              softmax_temperature=2.0)
+    mean, dur = T.eval_dataset(data, 0, 2.0, a, Stub(), csv_path=str(tmp_path / "e.csv"))
+    assert mean == 1.0 and len(dur) == 2 and calls[0] == ("type", "greedy", None)          # temperature NOT applied (as the reference)
+    assert [c for c in calls if c[0] == "sample_many"] == [("sample_many", 4, 1, 1), ("sample_many", 2, 1, 1)]
+    assert len(open(tmp_path / "e.csv").read().strip().splitlines()) == 7
+    with pytest.raises(AssertionError):
+        T.eval_dataset(data, 8, 1.0, a, Stub())                                           # "Do not set width when using greedy"
+    del calls[:]
+    a.decode_strategy, a.width = "sample", [8, 16]
+    assert T.eval_widths(data, a, Stub()) == [8.0, 16.0]
+    a.eval_batch_size, a.max_calc_batch_size = 1, 32                                      # width split into passes
+    mean, _ = T.eval_dataset(data[:2], 128, 1.0, a, Stub())
+    assert mean == 128.0 and calls[-1] == ("sample_many", 1, 32, 4)
+    with pytest.raises(AssertionError):
+        T.eval_dataset(data[:2], 100, 1.0, a, Stub())                                     # width % max_calc_batch_size != 0
+    a.apply_softmax_temperature = True
+    del calls[:]
+    T.eval_dataset(data[:1], 32, 0.5, a, Stub())
+    assert calls[0] == ("type", "sample", 0.5)
+    a.decode_strategy = "bs"
+    with pytest.raises(NotImplementedError):
+        T.eval_dataset(data[:1], 2, 1.0, a, Stub())
