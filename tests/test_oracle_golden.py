@@ -118,3 +118,53 @@ def test_oracle_am_variant_matches_reference():
     free = O.rollout(W, g["static"], g["dynamic"], g["distances"], g["slope"])
     T = min(free["pi"].shape[1], g["pi"].shape[1])
     assert (free["pi"][:, :T] == g["pi"][:, :T]).all(1).mean() >= 0.8
+
+
+def test_oracle_environment_invariants_on_random_walks():
+    """Domain properties of the a7 / a8 recipe (problems/EVRP.py:105-280) that must hold for ANY feasible walk, checked on
+    random feasible walks of the oracle: the rules the reference encodes, stated independently of its arithmetic."""
+    rs = np.random.RandomState(5)
+    for N, F in ((20, 5), (37, 2), (12, 9)):
+        B = 24
+        static, dynamic, elev = O.generate_instances(B, N, F=F, seed=N)
+        D, G = O.pairwise_matrices(static, elev)
+        c = O.EVRPConsts(charging_num=F)
+        S = N + F + 1
+        ar = np.arange(B)
+        dyn, now = dynamic.copy(), np.zeros(B, np.int64)
+        mask = np.ones((B, S), np.float32)
+        served0 = dynamic[:, 1].sum(1)
+        for t in range(6 * N):
+            live = mask.any(1)
+            if not live.any():
+                break
+            p = mask + 1e-9 * (~live)[:, None]                       # finished rows: any pick (ignored below)
+            sel = np.array([rs.choice(S, p=p[b] / p[b].sum()) for b in range(B)])
+            new, e, dist = O.update_dynamic(c, dyn, D, G, now, sel)
+            m2 = O.update_mask(c, new, D, G, sel)
+            L, dem, soc, tim = new[:, 0, 0], new[:, 1], new[:, 2, 0], new[:, 3, 0]
+            at_depot, at_station, at_cust = sel == 0, (sel >= 1) & (sel <= F), sel > F
+            # state: rows load / SOC / time stay one scalar broadcast over the nodes; recharge / reload semantics
+            assert (new[:, 0] == L[:, None]).all() and (new[:, 2] == soc[:, None]).all() and (new[:, 3] == tim[:, None]).all()
+            assert (soc[at_depot | at_station] == 80).all() and (L[at_depot] == 1).all() and (tim[at_depot] == 10).all()
+            assert (dist[:, 0] == D[ar, now, sel]).all()
+            assert (dem[ar, sel][at_cust & live] == 0).all()          # a feasible customer visit serves its whole demand
+            assert (dem[:, 1:] >= 0).all() and (L >= 0).all() and (L <= 1).all()
+            # (the look-ahead rules do NOT guarantee time >= 0: rule 7 prices a station visit without its charging hour
+            #  and uses one broadcast station-to-depot distance, problems/EVRP.py:196-214 -- so no such invariant here)
+            assert (tim[live] > -1.34).all() and np.isfinite(soc).all()
+            # mask rules: never the node just visited (unless rule 8 re-opens the depot), no station -> station, no depot -> station
+            chosen_bit = m2[ar, sel]
+            assert (chosen_bit[sel != 0] == 0).all()
+            assert (m2[:, 1:F + 1][at_station | at_depot] == 0).all()
+            open_cust = (m2[:, F + 1:] > 0)
+            assert ((dem[:, F + 1:] > 0) | ~open_cust).all()          # only customers with demand left are offered ...
+            assert ((dem[:, F + 1:] < L[:, None]) | ~open_cust).all() # ... and only if the load strictly exceeds the demand
+            done = (dem == 0).all(1)
+            if done.all():
+                assert (m2 == 0).all()                                # rule 0 is GLOBAL: all-zero only once the whole batch is done
+            else:                                                     # a finished instance idles at the depot (pi = 0 padding)
+                assert (m2[done][:, 0] == 1).all() and (m2[done][:, 1:] == 0).all()
+            assert (m2[~done].sum(1) >= 1).all()                      # unfinished ones always keep a move (rule 8)
+            dyn, now, mask = new, sel, m2
+        assert (dyn[:, 1, F + 1:].sum(1) <= served0).all()
