@@ -232,6 +232,42 @@ def test_cvrplib_parser(tmp_path):
     assert torch.equal(ds.static[0, :, 0], torch.tensor([30., 40.]))
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/EM-EVRP/ExperimentalData/CVRPlib"),
+                    reason="reference data only exists in the build container")
+def test_cvrplib_parser_matches_reference_reader_on_its_own_files():
+    """utils/functions.py:213-231 read_file / parse_file of the (patched-import) reference against
+    evrp_b200.parse_cvrplib on the 8 Augerat P-set instances the reference ships"""
+    import glob
+    from oracle import ref_shim
+    ref_shim.load()
+    from utils.functions import read_file                     # the reference's own reader
+    files = sorted(glob.glob("/root/reference/EM-EVRP/ExperimentalData/CVRPlib/*.txt"))
+    assert len(files) == 8
+    for f in files:
+        coords, dem, cap = evrp_b200.parse_cvrplib(f)
+        rc, rd, rcap = read_file(f)
+        assert [list(c) for c in coords] == [list(c) for c in rc] and list(dem) == list(rd) and cap == rcap, f
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/EM-EVRP/ExperimentalData/CVRPlib"),
+                    reason="reference data only exists in the build container")
+@pytest.mark.parametrize("name,n", [("P-n21-k2.txt", 20), ("P-n51-k10.txt", 50), ("P-n101-k4.txt", 100)])
+def test_cvrplib_dataset_branch_matches_reference(name, n):
+    """problems/EVRP.py:58-66 (CVRP_lib_test): the instance built from a CVRPLIB file -- depot, the 5 random stations
+    (same RNG stream), customers, demands / capacity, distance and slope matrices -- equals the reference's, bit for bit"""
+    import types
+    from oracle import ref_shim
+    _, RefDS = ref_shim.load()
+    path = "/root/reference/EM-EVRP/ExperimentalData/CVRPlib/" + name
+    a = types.SimpleNamespace(CVRP_lib_test=True, CVRP_lib_path=path, Start_SOC=80., t_limit=10., num_nodes=n, charging_num=5)
+    ref = RefDS(1, n, 10., 80., 50., 4, 4, 5, 12345, a)
+    ours = evrp_b200.VehicleRoutingDataset(1, n, 10., 80., 50., 4, 4, 5, 12345, a, device="cpu")
+    assert np.array_equal(ours.static.numpy(), ref.static.cpu().numpy())
+    assert np.array_equal(ours.dynamic.numpy(), ref.dynamic.cpu().numpy())
+    assert np.abs(ours.distances.numpy() - ref.distances.cpu().numpy()).max() <= 1e-5       # ATen's vectorised sqrt: 1 ulp
+    assert np.abs(ours.slope.numpy() - ref.slope.cpu().numpy()).max() <= 1e-6
+
+
 def test_test_set_pickle_round_trip(tmp_path):
     """the reference's test-set file (trainer.py:361-381 writer, :469-482 reader): nested-list 4-tuples"""
     import pickle
