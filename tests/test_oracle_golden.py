@@ -168,3 +168,35 @@ def test_oracle_environment_invariants_on_random_walks():
             assert (m2[~done].sum(1) >= 1).all()                      # unfinished ones always keep a move (rule 8)
             dyn, now, mask = new, sel, m2
         assert (dyn[:, 1, F + 1:].sum(1) <= served0).all()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/EM-EVRP"), reason="the live reference only exists in the build container")
+@pytest.mark.parametrize("N,B,seed,bn", [(30, 6, 777, False), (20, 8, 4242, True)])
+def test_oracle_against_the_live_reference_on_fresh_inputs(N, B, seed, bn):
+    """Beyond the committed fixtures: run the patched reference itself (oracle/ref_shim.py) on a dataset seed and a
+    graph size that no fixture holds, and check the oracle teacher-forced on its tours -- rewards / states / masks
+    bit-exact, log-probs 2e-5 -- plus the oracle's own free-running greedy tours."""
+    import torch
+    from oracle import make_golden as MG, ref_shim
+    ds, args = ref_shim.make_dataset(B, N, seed)
+    m = ref_shim.make_model(ds, args, 0)
+    if bn:
+        m.load_state_dict(MG.perturb_bn(m.state_dict()))
+    m.eval(); m.set_decode_type("greedy")
+    bat = MG.batch_of(ds, B)
+    tr = MG.Tracer(m)
+    with torch.no_grad():
+        pi, ll, R = m(bat)
+    tr.close()
+    t = tr.arrays()
+    W = {k: v.numpy() for k, v in m.state_dict().items()}
+    static, dynamic, D, G = (x.numpy().astype(np.float32) for x in bat)
+    o = O.rollout(W, static, dynamic, D, G, forced=pi.numpy(), trace=True)
+    assert np.array_equal(o["R"], R.numpy())
+    assert np.array_equal(o["dynamic"], t["t_dynamic"])
+    assert np.array_equal(o["mask"].astype(np.uint8), t["t_mask"])
+    live = np.isfinite(t["t_log_p"])
+    assert np.abs(o["log_p"][live] - t["t_log_p"][live]).max() < 2e-5
+    free = O.rollout(W, static, dynamic, D, G)
+    T = min(free["pi"].shape[1], pi.shape[1])
+    assert (free["pi"][:, :T] == pi.numpy()[:, :T]).all(1).mean() >= 0.8
