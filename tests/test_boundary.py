@@ -268,6 +268,53 @@ def test_cvrplib_dataset_branch_matches_reference(name, n):
     assert np.abs(ours.slope.numpy() - ref.slope.cpu().numpy()).max() <= 1e-6
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/EM-EVRP"), reason="the live reference only exists in the build container")
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_training_math_against_the_live_reference_on_fresh_inputs(mode):
+    """policy_math (the differentiable half of the training path, CPU statement) against the patched reference run LIVE
+    on a seed / graph size no fixture holds: sampled rollout of the reference, its REINFORCE gradients with the actions
+    forced, vs encode_torch + teacher_forced_ll on the same weights -- log-probs 2e-5 (6e-5 with batch statistics),
+    gradients of all 50 parameters 1e-4 relative, BatchNorm running statistics updated identically"""
+    from oracle import make_golden as MG, ref_shim
+    N, B = 30, 6
+    ds, rargs = ref_shim.make_dataset(B, N, 999)
+    rm = ref_shim.make_model(ds, rargs, 0)
+    rm.load_state_dict(MG.perturb_bn(rm.state_dict()))
+    bat = MG.batch_of(ds, B)
+    rm.eval(); rm.set_decode_type("sample")
+    torch.manual_seed(5)
+    with torch.no_grad():
+        pi, _, R = rm(bat)
+    adv = (R.sum(1) - R.sum(1).mean()).detach()
+    m = evrp_b200.AttentionModel(128, 128, args_for(N), n_encode_layers=3)
+    m.load_state_dict(rm.state_dict())
+    rm.train(mode == "train"); m.train(mode == "train")
+    ll_ref, _, _, g_ref = MG.teacher_forced_grads(rm, bat, pi, adv)
+    W = {k: v.detach().numpy() for k, v in m.state_dict().items()}
+    static, dynamic, D, G = (x.numpy().astype(np.float32) for x in bat)
+    o = O.rollout(W, static, dynamic, D, G, forced=pi.numpy(), trace=True)
+    T = pi.shape[1]
+    bits = np.zeros((B, T, 4), np.int64)
+    for j in range(N + 6):
+        bits[..., j >> 5] |= o["mask"][..., j].astype(np.int64) << (j & 31)
+    bits = torch.from_numpy(bits.astype(np.uint32).view(np.int32).reshape(B, T, 4))
+    before = np.concatenate([dynamic[:, None], o["dynamic"][:, :-1]], 1)
+    veh = torch.from_numpy(np.stack([before[:, :, 0, 0], before[:, :, 2, 0] / np.float32(80),
+                                     before[:, :, 3, 0] / np.float32(10)], -1).astype(np.float32))
+    emb, kvl, fixed = PM.encode_torch(m, torch.from_numpy(static), torch.from_numpy(dynamic))
+    ll = PM.teacher_forced_ll(m, emb, kvl, fixed, pi, bits, veh, torch.full((B,), T, dtype=torch.int32))
+    assert float((ll.detach() - ll_ref).abs().max()) < (2e-5 if mode == "eval" else 6e-5)
+    (adv * ll.sum(1)).mean().backward()
+    num = den = 0.0
+    for k, p in m.named_parameters():
+        num += float((p.grad - g_ref[k]).norm() ** 2); den += float(g_ref[k].norm() ** 2)
+    assert (num / den) ** 0.5 < 1e-4
+    if mode == "train":
+        for k, v in m.state_dict().items():
+            if "running" in k:
+                assert torch.allclose(v, rm.state_dict()[k], rtol=1e-4, atol=1e-5), k
+
+
 def test_test_set_pickle_round_trip(tmp_path):
     """the reference's test-set file (trainer.py:361-381 writer, :469-482 reader): nested-list 4-tuples"""
     import pickle
