@@ -211,6 +211,8 @@ def main():
     greedy_fixture("greedy_bn_n20.npz", 20, 16, bn=True)
     greedy_fixture("greedy_n50.npz", 50, 8)
     greedy_fixture("greedy_n100.npz", 100, 6)
+    greedy_fixture("greedy_n35.npz", 35, 8, seed=31337)               # a size / seed off the reference's 20 / 50 / 100 grid
+    greedy_fixture("greedy_bn_n50.npz", 50, 6, seed=2024, bn=True)
     sample_fixture("sample_n20.npz", 20, 16)
     dm_fixture("dm_n20.npz", 20, 8)
     am_fixture("am_n20.npz", 20, 16)

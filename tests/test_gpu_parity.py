@@ -82,7 +82,7 @@ def weights():
 # ---------------------------------------------------------------------------------------------
 # a7 / a8: stand-alone environment step kernels, bit-exact against the reference trace
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["greedy_n20.npz", "greedy_n50.npz", "greedy_n100.npz"])
+@pytest.mark.parametrize("name", ["greedy_n20.npz", "greedy_n35.npz", "greedy_n50.npz", "greedy_bn_n50.npz", "greedy_n100.npz"])
 def test_step_kernels_bit_exact(evrp, name):
     g = load(name)
     N = g["static"].shape[2] - 6
@@ -157,7 +157,7 @@ def test_encoder_matches_oracle(evrp, weights, name, bn):
 # a4-a8 fused: teacher-forced rollout against the reference trace
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("ff_mode", [0, 1])      # 0: FF_tour on tcgen05 (default kernel), 1: fp32 FFMA kernel
-@pytest.mark.parametrize("name", ["greedy_n20.npz", "greedy_bn_n20.npz", "greedy_n50.npz", "greedy_n100.npz"])
+@pytest.mark.parametrize("name", ["greedy_n20.npz", "greedy_bn_n20.npz", "greedy_n35.npz", "greedy_n50.npz", "greedy_bn_n50.npz", "greedy_n100.npz"])
 def test_teacher_forced_rollout(evrp, weights, name, ff_mode):
     g = load(name)
     W = bn_perturb_numpy(weights) if bool(g["bn_perturbed"]) else weights
@@ -176,7 +176,7 @@ def test_teacher_forced_rollout(evrp, weights, name, ff_mode):
 
 
 @pytest.mark.parametrize("ff_mode", [0, 1])
-@pytest.mark.parametrize("name", ["greedy_n20.npz", "greedy_n50.npz", "greedy_n100.npz"])
+@pytest.mark.parametrize("name", ["greedy_n20.npz", "greedy_n35.npz", "greedy_n50.npz", "greedy_n100.npz"])
 def test_free_running_greedy_tours(evrp, weights, name, ff_mode):
     g = load(name)
     S = g["static"].shape[2]

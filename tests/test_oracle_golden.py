@@ -40,7 +40,7 @@ def bn_weights(weights):
     return out
 
 
-@pytest.mark.parametrize("name", ["greedy_n20.npz", "greedy_bn_n20.npz", "greedy_n50.npz", "greedy_n100.npz"])
+@pytest.mark.parametrize("name", ["greedy_n20.npz", "greedy_bn_n20.npz", "greedy_n35.npz", "greedy_n50.npz", "greedy_bn_n50.npz", "greedy_n100.npz"])
 def test_teacher_forced_trace(weights, name):
     g = load(name)
     W = bn_weights(weights) if bool(g["bn_perturbed"]) else weights
