@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EVRP_B200_LIB") or os.path.join(_HERE, "libevrp_b200.so")   # override: instrumented debug builds (tools/)
 
 EVRP_MAX_S = 128
-ABI_VERSION = 14
+ABI_VERSION = 15
 EVRP_MAX_LAYERS = 8
 ST_NAN_LOGIT, ST_INFEASIBLE_PICK, ST_STEP_CAP, ST_NONUNIFORM_DYNAMIC, ST_NO_FEASIBLE, ST_STUCK_AT_DEPOT = 1, 2, 4, 8, 16, 32
 DECODE_GREEDY, DECODE_SAMPLE = 0, 1
@@ -38,7 +38,8 @@ class EncoderWeights(C.Structure):
         [("n_layers", C.c_int32), ("layers", LayerWeights * EVRP_MAX_LAYERS),
          ("node_proj", _FP), ("fixed_ctx_w", _FP), ("node_proj_hi", _FP), ("node_proj_lo", _FP),
          ("step_proj", _FP), ("step_proj_hi", _FP), ("step_proj_lo", _FP),
-         ("gemm_mode", C.c_int32), ("attn_mode", C.c_int32)]
+         ("gemm_mode", C.c_int32), ("attn_mode", C.c_int32),
+         ("fused_w", _FP), ("fused_params", _FP), ("fused_node_chunks", C.c_int32)]
 
 
 class DecoderWeights(C.Structure):
@@ -64,6 +65,7 @@ SIGNATURES = {
     "evrp_encoder_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "evrp_encoder_forward": (C.c_int, [C.POINTER(EncoderWeights), _FP, _FP, C.c_int, C.c_int, C.c_int,
                                        _FP, _FP, _FP, _FP, _FP, C.c_size_t, _FP]),
+    "evrp_encoder_fused_debug": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "evrp_rollout": (C.c_int, [C.POINTER(Phys), C.POINTER(DecoderWeights), C.POINTER(RolloutCfg),
                                _FP, _FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int,
                                _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_size_t, _FP]),

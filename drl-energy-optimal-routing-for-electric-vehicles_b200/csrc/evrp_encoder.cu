@@ -269,6 +269,10 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // evrp_attn_tc.cu
 int launch_attn_tc(const float* qkv, int B, int S, float* heads, int sm_count, cudaStream_t st);
 
+// evrp_encoder_fused.cu
+int launch_encoder_fused(const evrp_encoder_weights* w, const float* xy, const float* dyn, int B, int S, int F, float* emb,
+                         float* kvl, float* step_tab, int sm_count, cudaStream_t st);
+
 // evrp_tc_gemm.cu
 int tc_gemm(int epi, const float* A, int lda, const float* Wh, const float* Wl, float* C, int ldc, int M, int N, int K,
             const float* bias, const float* resid, int ldr, const float* scale, const float* shift, int sm_count,
@@ -288,13 +292,23 @@ int evrp_encoder_forward(const evrp_encoder_weights* w, const float* static_xy, 
                          int F, float* emb, float* kvl, float* fixed_ctx, float* step_tab, void* workspace,
                          size_t workspace_bytes, void* stream) {
   using namespace evrp;
-  if (!w || !static_xy || !dynamic || !emb || !kvl || !fixed_ctx || !workspace || B < 0 || S < 2 || F < 1 || F >= S ||
+  if (!w || !static_xy || !dynamic || !emb || !kvl || !fixed_ctx || B < 0 || S < 2 || F < 1 || F >= S ||
       w->n_layers < 0 || w->n_layers > EVRP_MAX_LAYERS)
     return -EVRP_E_BADARG;
   if (S > EVRP_MAX_S) return -EVRP_E_TOO_MANY_NODES;
-  if (workspace_bytes < evrp_encoder_workspace_bytes(B, S)) return -EVRP_E_WORKSPACE;
   if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (w->gemm_mode == 2) {
+    // ONE persistent kernel: init embedding, every layer and the node projection; no activation leaves the SM
+    int dev = 0, sms = 148, rc;
+    EVRP_CUDA_OK(cudaGetDevice(&dev));
+    EVRP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if ((rc = launch_encoder_fused(w, static_xy, dynamic, B, S, F, emb, kvl, step_tab, sms, st))) return rc;
+    fixed_context_kernel<<<B, 128, 0, st>>>(emb, S, w->fixed_ctx_w, fixed_ctx);
+    EVRP_LAUNCH_OK();
+    return 0;
+  }
+  if (!workspace || workspace_bytes < evrp_encoder_workspace_bytes(B, S)) return -EVRP_E_WORKSPACE;
   const int M = B * S;
   const size_t slab = align_up((size_t)M * 128 * 4, 256);
   float* ha = (float*)workspace;

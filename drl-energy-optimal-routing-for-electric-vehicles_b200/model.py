@@ -111,7 +111,7 @@ class AttentionModel(nn.Module):
         self.sample_seed = 0
         self._calls = 0
         self.last_energy = None                   # [B,T] energy of the last rollout (DM trainer's 3rd output)
-        self.gemm_mode = 0                        # encoder GEMMs: 0 = tcgen05 3xTF32 (fp32-faithful), 1 = fp32 FFMA
+        self.gemm_mode = 2                        # encoder: 2 = ONE fused tcgen05 kernel (fp16-pair split), 0 = per-sub-layer tcgen05 3xTF32 launches, 1 = fp32 FFMA
         self.ff_mode = 0                          # FF_tour inside the rollout kernel: 0 = tcgen05 (fp16-pair split), 1 = fp32 FFMA
         self.attn_mode = 0                        # encoder self-attention: 0 = tcgen05 3xTF32 (with gemm_mode 0), 1 = fp32 FFMA2
         self.profile_events = None                # list -> (start, end) CUDA events around each rollout kernel launch
@@ -200,10 +200,13 @@ class AttentionModel(nn.Module):
         emb = torch.empty(B, S, 128, device=dev)
         kvl = torch.empty(B, S, 384, device=dev)
         fixed = torch.empty(B, 128, device=dev)
-        nbytes = L.evrp_encoder_workspace_bytes(B, S)
-        ws = self._enc_ws                                   # scratch activations: reused across calls
-        if ws is None or ws.numel() < nbytes or ws.device != dev:
-            ws = self._enc_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        if self.gemm_mode == 2:                             # fused kernel: activations never leave the SM, no scratch
+            ws, nbytes = None, 0
+        else:
+            nbytes = L.evrp_encoder_workspace_bytes(B, S)
+            ws = self._enc_ws                               # scratch activations: reused across calls
+            if ws is None or ws.numel() < nbytes or ws.device != dev:
+                ws = self._enc_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         tab = torch.empty(B, S, 128, device=dev) if self.policy == 1 else None
         rc = L.evrp_encoder_forward(pk["enc_struct"], _lib.ptr(static), _lib.ptr(dynamic), B, S, self.charging_num,
                                     _lib.ptr(emb), _lib.ptr(kvl), _lib.ptr(fixed), _lib.ptr(tab), _lib.ptr(ws), nbytes,

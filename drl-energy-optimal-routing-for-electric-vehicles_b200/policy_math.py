@@ -65,6 +65,49 @@ def split_f16(w):
     return hi.contiguous(), lo.contiguous(), 2.0 ** (-e)
 
 
+FUSED_LP = 1280          # floats of fused_params per layer (csrc/evrp_encoder_fused.cu)
+
+
+def _fused_blocks(w, chunks, kblocks):
+    """w [N,K] fp32 (nn.Linear layout) -> (list of fp16 [128,64] blocks, 1/scale).  Order: for every (chunk of 128
+    output rows, K block of 64 inputs) in ``order``: hi block then lo block."""
+    hi, lo, inv = split_f16(w)
+    out = []
+    for c, kb in zip(chunks, kblocks):
+        out.append(hi[128 * c:128 * c + 128, 64 * kb:64 * kb + 64])
+        out.append(lo[128 * c:128 * c + 128, 64 * kb:64 * kb + 64])
+    return out, inv
+
+
+def pack_fused_encoder(model, layer_mats, node_mat, bn_folds):
+    """Operand stream of the fused encoder kernel (include/evrp_b200.h ``fused_w`` / ``fused_params``).
+    layer_mats: per layer (Wqkv [384,128], Wo [128,128], W1 [512,128], b1, W2 [128,512], b2) in nn.Linear layout;
+    node_mat [384 or 512, 128]; bn_folds: per layer ((scale1, shift1), (scale2, shift2))."""
+    blocks, params = [], []
+    for (Wqkv, Wo, W1, b1, W2, b2), ((s1, h1), (s2, h2)) in zip(layer_mats, bn_folds):
+        bq, iq = _fused_blocks(Wqkv, [0, 0, 1, 1, 2, 2], [0, 1, 0, 1, 0, 1])
+        bo, io = _fused_blocks(Wo, [0, 0], [0, 1])
+        w1h, w1l, i1 = split_f16(W1)
+        w2h, w2l, i2 = split_f16(W2)
+
+        def ff1(c):
+            return [t[128 * c:128 * c + 128, 64 * kb:64 * kb + 64] for kb in (0, 1) for t in (w1h, w1l)]
+
+        def ff2(j):
+            return [t[:, 64 * kb:64 * kb + 64] for kb in (2 * j, 2 * j + 1) for t in (w2h, w2l)]
+        blocks += bq + bo + ff1(0) + ff1(1) + ff2(0) + ff1(2) + ff2(1) + ff1(3) + ff2(2) + ff2(3)
+        p = torch.zeros(FUSED_LP, dtype=torch.float32, device=Wqkv.device)
+        p[0:128], p[128:256], p[256:768], p[768:896], p[896:1024], p[1024:1152] = s1, h1, b1, b2, s2, h2
+        p[1152:1156] = torch.tensor([iq, io, i1, i2], dtype=torch.float32)
+        params.append(p)
+    n_chunks = node_mat.shape[0] // 128
+    bn, inode = _fused_blocks(node_mat, [c for c in range(n_chunks) for _ in (0, 1)], [0, 1] * n_chunks)
+    blocks += bn
+    params.append(torch.full((1,), inode, dtype=torch.float32, device=node_mat.device))
+    W = torch.stack([b.contiguous() for b in blocks]).contiguous()         # [n_blocks,128,64] fp16
+    return W, torch.cat(params).contiguous(), n_chunks
+
+
 def pack_weights(model):
     keep = {}
     ew = _lib.EncoderWeights()
@@ -82,6 +125,7 @@ def pack_weights(model):
     ew.cust_b = dev("cust_b", model.init_embed.bias)
     layers = model.embedder.layers
     ew.n_layers = len(layers)
+    fused_layers, fused_bn = [], []
     for l, layer in enumerate(layers):
         att, bn1, ff, bn2 = layer[0].module, layer[1].normalizer, layer[2].module, layer[3].normalizer
         Hh, d, dk = att.W_query.shape
@@ -95,6 +139,9 @@ def pack_weights(model):
         lw.ff2_w, lw.ff2_b = dev(f"l{l}.ff2w", ff[2].weight.t()), dev(f"l{l}.ff2b", ff[2].bias)
         s, sh = _bn_fold(bn2)
         lw.bn2_scale, lw.bn2_shift = dev(f"l{l}.bn2s", s), dev(f"l{l}.bn2b", sh)
+        fused_layers.append((torch.cat(cols, 1).t().float(), att.W_out.reshape(Hh * dk, d).t().float(), ff[0].weight.float(),
+                             ff[0].bias.float(), ff[2].weight.float(), ff[2].bias.float()))
+        fused_bn.append((_bn_fold(bn1), (s, sh)))
         # tcgen05 path: [out][in] planes
         for name, mat in (("Wqkv", torch.cat(cols, 1).t()), ("Wo", att.W_out.reshape(Hh * dk, d).t()),
                           ("ff1", ff[0].weight), ("ff2", ff[2].weight)):
@@ -109,6 +156,14 @@ def pack_weights(model):
     ew.fixed_ctx_w = dev("fixed_ctx_w", model.project_fixed_context.weight.t())
     dw = _lib.DecoderWeights()
     dw.policy = int(getattr(model, "policy", 0))
+    node_mat = folded_node_projection(model).float()
+    if dw.policy == 1:                                 # the AM step table rides behind the node projection (4th chunk)
+        node_mat = torch.cat([node_mat, model.project_step_context.weight[:, :128].float()], 0)
+    fw, fp, nchunks = pack_fused_encoder(model, fused_layers, node_mat, fused_bn)
+    keep["fused_w"], keep["fused_params"] = fw, fp
+    ew.fused_w = _lib.ptr(fw) if fw.is_cuda else None
+    ew.fused_params = _lib.ptr(fp) if fp.is_cuda else None
+    ew.fused_node_chunks = nchunks
     if dw.policy == 1:                                 # nets/AM.py:90: project_step_context = [emb columns | load column]
         Ws = model.project_step_context.weight
         ew.step_proj = dev("step_proj", Ws[:, :128].t())

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 14
+#define EVRP_ABI_VERSION 15
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -135,11 +135,25 @@ typedef struct {
      tabulates it per node (step_tab below), so the rollout reads one 512-byte row per step instead of a mat-vec. */
   const float *step_proj;                     /* [128,128] k-major (weight[:, :128]^T), gemm_mode 1            */
   const float *step_proj_hi, *step_proj_lo;   /* [128,128] [out][in] TF32 planes, gemm_mode 0                  */
-  int32_t gemm_mode;                   /* 0: tcgen05 3xTF32 (fp32-faithful, tensor cores); 1: fp32 FFMA GEMM   */
+  int32_t gemm_mode;                   /* 2: ONE fused persistent tcgen05 kernel for the whole encoder (fp16-pair split
+                                          operands, fp32-faithful; needs fused_w / fused_params below); 0: one tcgen05
+                                          3xTF32 GEMM / attention launch per sub-layer; 1: fp32 FFMA GEMMs            */
   int32_t attn_mode;                   /* self-attention core (QK^T, softmax, PV): 0: tcgen05 3xTF32, probabilities as
                                           the TMEM A operand (used when gemm_mode == 0); 1: fp32 FFMA2 kernel          */
+  /* fused encoder kernel (gemm_mode 2, csrc/evrp_encoder_fused.cu): every weight matrix of the encoder and of the node
+     projection as fp16 (hi, lo) operand blocks [128 out][64 in] in the kernel's consumption order, each matrix scaled
+     by a power of two (evrp_b200/policy_math.py::pack_fused_encoder documents the order):
+       per layer: W_qkv chunks Q, K, V x (K block 0 hi, lo, K block 1 hi, lo); W_out; then FF1 chunk 0, FF1 chunk 1,
+       FF2 K blocks 0-1, FF1 chunk 2, FF2 K blocks 2-3, FF1 chunk 3, FF2 K blocks 4-5, FF2 K blocks 6-7;
+       then the node projection chunks (glimpse K, glimpse V, folded logit K[, AM step table])                       */
+  const void *fused_w;                 /* fp16 [n_layers * 48 + fused_node_chunks * 4][128][64]                        */
+  const float *fused_params;           /* fp32 [n_layers][1280]: bn1 scale 128 | bn1 shift 128 | ff1 bias 512 | ff2 bias
+                                          128 | bn2 scale 128 | bn2 shift 128 | 1/scale of W_qkv, W_out, FF1, FF2 | pad;
+                                          then [1]: 1/scale of the node projection                                   */
+  int32_t fused_node_chunks;           /* 3, or 4 when the AM step table is packed behind the node projection         */
 } evrp_encoder_weights;
 
+/* scratch of the per-sub-layer paths (gemm_mode 0 / 1); the fused kernel (gemm_mode 2) needs none (workspace may be NULL) */
 size_t evrp_encoder_workspace_bytes(int B, int S);
 
 /* Eval-mode forward (BatchNorm folded to per-channel affine).  Outputs: emb [B,S,128] node embeddings,
@@ -149,6 +163,10 @@ int evrp_encoder_forward(const evrp_encoder_weights* w, const float* static_xy /
                          const float* dynamic /*[B,4,S]*/, int B, int S, int F,
                          float* emb, float* kvl, float* fixed_ctx, float* step_tab,
                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* diagnostics of the fused encoder kernel (synchronises): returns 1 and fills out8_host = {code of the first barrier
+ * wait that did not complete within ~2 s, CTA, thread, parity, ...} if a launch since the last reset aborted, else 0 */
+int evrp_encoder_fused_debug(int* out8_host, int reset);
 
 /* ------------------------------------------------------------------------------------------------
  * (3) persistent rollout:  AttentionModel._inner        nets/DRLModel.py:240-280
