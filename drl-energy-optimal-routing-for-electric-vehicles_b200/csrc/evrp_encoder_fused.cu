@@ -70,17 +70,37 @@ constexpr size_t SMEM_BYTES = 8 * (size_t)BLK /*K, V^T planes*/ + NSLOT * (size_
 __device__ int g_abort;
 __device__ int g_dbg[8];
 
-__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, int code) {
-  uint32_t ok = 0;
-  const uint32_t addr = smem_u32(bar);
+#ifdef EVRP_FENC_PROF
+// wait-time profile of CTA 0: cycles spent in every wait site (index = code % 100) of the producer lane, the MMA lane
+// and worker thread 0, plus their total run time in slot 99
+__device__ unsigned long long g_prof[3][100];
+#define PROF_DECL long long prof_acc[100]; for (int _i = 0; _i < 100; ++_i) prof_acc[_i] = 0; const long long prof_t0 = clock64(); long long prof_last = prof_t0;
+#define PHASE(i) do { const long long _n = clock64(); prof_acc[i] += _n - prof_last; prof_last = _n; } while (0)
+#define PROF_DUMP(role) do { if (blockIdx.x == 0) { prof_acc[99] = clock64() - prof_t0; for (int _i = 0; _i < 100; ++_i) g_prof[role][_i] = (unsigned long long)prof_acc[_i]; } } while (0)
+#define WAIT(bar, parity, code) do { const long long _t = clock64(); wait_bar(bar, parity, code); prof_acc[(code) % 100] += clock64() - _t; } while (0)
+#else
+#define PROF_DECL
+#define PHASE(i) do { } while (0)
+#define PROF_DUMP(role) do { } while (0)
+#define WAIT(bar, parity, code) wait_bar(bar, parity, code)
+#endif
+
+__device__ __forceinline__ uint32_t try_wait(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  return ok;
+}
+// slow path, out of line (one copy): keeps the ~40 wait sites small -- the kernel's three roles run three different
+// instruction streams, so code size is instruction-cache pressure
+__device__ __noinline__ void wait_slow(uint32_t addr, uint32_t parity, int code) {
   long long t0 = 0;
-  for (uint32_t spin = 0; !ok; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    if (!ok && (spin & 255u) == 255u) {
+  for (uint32_t spin = 1;; ++spin) {
+    if (try_wait(addr, parity)) return;
+    if ((spin & 255u) == 0u) {
       if (*(volatile int*)&g_abort) return;
       const long long now = clock64();
       if (t0 == 0) t0 = now;
@@ -90,6 +110,11 @@ __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, int cod
       }
     }
   }
+}
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity, int code) {
+  const uint32_t addr = smem_u32(bar);
+  if (try_wait(addr, parity)) return;
+  wait_slow(addr, parity, code);
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -130,30 +155,51 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 // one warp = one arrival: every lane has fenced its own tensor-memory / shared-memory writes before the __syncwarp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
   __syncwarp();
   if (lane == 0) mbar_arrive(bar);
 }
+__device__ __forceinline__ void col_group_sync(int q) { asm volatile("bar.sync %0, 128;" ::"r"(5 + q) : "memory"); }
+// bulk tensor store shared -> global (128-byte swizzled [rows x 32 fp32] box), tracked by the issuing thread's bulk group
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void row_group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
 
-// 32 fp32 values -> 16 + 16 packed fp16 (hi, lo) pairs, element 2e in the low half (= the lower K index)
-__device__ __forceinline__ void split32(const float (&v)[32], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
-#pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
-    hi[e] = *reinterpret_cast<const uint32_t*>(&h);
-    lo[e] = *reinterpret_cast<const uint32_t*>(&l);
-  }
+// packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100: one issue slot for two IEEE fp32 operations)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) { return ((uint64_t)__float_as_uint(hi) << 32) | __float_as_uint(lo); }
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+__device__ __forceinline__ float lo_of(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi_of(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+// one fp32 pair -> packed fp16 (hi, lo) planes: x = hi + lo to 22 significant bits (5 instructions per pair)
+__device__ __forceinline__ void split_pair(uint64_t x, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(lo_of(x), hi_of(x));
+  const float2 hf = __half22float2(h);
+  const uint64_t d = sub2(x, pk2(hf.x, hf.y));
+  const __half2 l = __floats2half2_rn(lo_of(d), hi_of(d));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-__device__ __forceinline__ void join32(const uint32_t (&hi)[16], const uint32_t (&lo)[16], float (&x)[32]) {
+// 16 fp32 pairs -> 16 + 16 packed fp16 (hi, lo) words, element 2e in the low half (= the lower K index)
+__device__ __forceinline__ void split32(const uint64_t (&v)[16], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
 #pragma unroll
-  for (int e = 0; e < 16; ++e) {
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hi[e]));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lo[e]));
-    x[2 * e] = a.x + b.x; x[2 * e + 1] = a.y + b.y;
-  }
+  for (int e = 0; e < 16; ++e) split_pair(v[e], hi[e], lo[e]);
+}
+__device__ __forceinline__ uint64_t join_pair(uint32_t hi, uint32_t lo) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+  return add2(pk2(a.x, a.y), pk2(b.x, b.y));
 }
 
 struct Args {
@@ -168,7 +214,8 @@ struct Args {
 };
 
 __global__ void __launch_bounds__(NT, 1)
-encoder_fused_kernel(const __grid_constant__ CUtensorMap mapW, const Args a) {
+encoder_fused_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapEmb,
+                     const __grid_constant__ CUtensorMap mapKvl, const __grid_constant__ CUtensorMap mapTab, const Args a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* KP = smem;                          // [channel block 0..1][plane hi, lo][128 keys x 128 B]
@@ -206,122 +253,148 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap mapW, const Args a) {
   if (warp == NWORK + 1) {
     // =========================== TMA producer: the tile's weight blocks, in consumption order ===========================
     if (lane == 0) {
-      uint32_t it = 0;
+      PROF_DECL
+      uint32_t slot = 0, phase = 1;            // a fresh barrier passes a wait on the phase before its first
+#pragma unroll 1
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int i = 0; i < tile_blocks; ++i, ++it) {
-          const int s = it % NSLOT;
-          wait_bar(&bars->empty[s], ((it / NSLOT) & 1) ^ 1, 100 + s);
-          mbar_expect_tx(&bars->full[s], BLK);
-          tma_load_2d(ring + s * BLK, &mapW, &bars->full[s], 0, i * 128);
+#pragma unroll 1
+        for (int i = 0; i < tile_blocks; ++i) {
+          WAIT(&bars->empty[slot], phase, 100);
+          mbar_expect_tx(&bars->full[slot], BLK);
+          tma_load_2d(ring + slot * BLK, &mapW, &bars->full[slot], 0, i * 128);
+          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
         }
       }
+      PROF_DUMP(0);
     }
   } else if (warp == NWORK) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      uint32_t it = 0;                       // ring position
+    // The whole warp runs the (warp-uniform) program so that descriptors and addresses live in uniform registers; one
+    // elected lane issues the tcgen05 instructions (a divergent `if (lane == 0)` costs an election loop per MMA, and the
+    // single issuing warp is instruction-latency bound: every descriptor below is one add away from a base).
+    {
+      const bool leader = elect_one();
+      PROF_DECL
+      uint32_t slot = 0, phase = 0;            // ring position
       uint32_t n_xp = 0, n_qo = 0, n_kv = 0, n_hp = 0;
-      uint32_t n_acc[2] = {0, 0};            // products written to each accumulator so far
+      uint32_t n_acc0 = 0, n_acc1 = 0;         // products written to each accumulator so far
       const int nks = (rows_per_tile + 15) >> 4;          // 16-key steps of the P V product
+      const uint64_t ring_desc = umma_desc(smem_u32(ring));               // + 1024 per slot, + 2 per 16-element K step
+      const uint64_t kp_desc = umma_desc(smem_u32(KP)), vt_desc = umma_desc(smem_u32(VT));
+      constexpr uint64_t DBLK = BLK >> 4;
       // D[128 x 128] (+)= A[128 x 128] W^T: A planes in TMEM (hi at a_tmem, lo at a_tmem + 64), four ring blocks
       // (K block 0 hi, lo, K block 1 hi, lo)
       auto gemm_k128 = [&](uint32_t d_tmem, uint32_t a_tmem, bool accumulate) {
-#pragma unroll 1
-        for (int kb = 0; kb < 2; ++kb) {
-          const int s0 = it % NSLOT, s1 = (it + 1) % NSLOT;
-          wait_bar(&bars->full[s0], (it / NSLOT) & 1, 200 + s0);
-          wait_bar(&bars->full[s1], ((it + 1) / NSLOT) & 1, 210 + s1);
-          tc_fence_after();
-          const uint32_t wh = smem_u32(ring + s0 * BLK), wl = smem_u32(ring + s1 * BLK);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t ah = a_tmem + (kb * 4 + k) * 8, al = ah + 64;
-            const uint64_t dwh = umma_desc(wh + k * 32), dwl = umma_desc(wl + k * 32);
-            umma_f16_ts(d_tmem, ah, dwh, (accumulate || kb || k) ? 1u : 0u, IDESC_G);
-            umma_f16_ts(d_tmem, al, dwh, 1u, IDESC_G);
-            umma_f16_ts(d_tmem, ah, dwl, 1u, IDESC_G);
+        for (int kb = 0; kb < 2; ++kb) {
+          const uint32_t s0 = slot, p0 = phase;
+          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+          const uint32_t s1 = slot, p1 = phase;
+          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+          WAIT(&bars->full[s0], p0, 200);
+          WAIT(&bars->full[s1], p1, 210);
+          tc_fence_after();
+          const uint64_t dwh = ring_desc + s0 * DBLK, dwl = ring_desc + s1 * DBLK;
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t ah = a_tmem + (kb * 4 + k) * 8, al = ah + 64;
+              umma_f16_ts(d_tmem, ah, dwh + 2 * k, (accumulate || kb || k) ? 1u : 0u, IDESC_G);
+              umma_f16_ts(d_tmem, al, dwh + 2 * k, 1u, IDESC_G);
+              umma_f16_ts(d_tmem, ah, dwl + 2 * k, 1u, IDESC_G);
+            }
+            umma_commit(&bars->empty[s0]);
+            umma_commit(&bars->empty[s1]);
           }
-          umma_commit(&bars->empty[s0]);
-          umma_commit(&bars->empty[s1]);
-          it += 2;
         }
       };
-      auto acquire_acc = [&](int b) {          // the previous product in this accumulator has been read
-        if (n_acc[b] > 0) { wait_bar(&bars->acc_empty[b], (n_acc[b] - 1) & 1, 220 + b); tc_fence_after(); }
-        ++n_acc[b];
-      };
+      // the previous product in an accumulator has been read by the workers
+      auto acquire_acc0 = [&]() { if (n_acc0 > 0) { WAIT(&bars->acc_empty[0], (n_acc0 - 1) & 1, 220); tc_fence_after(); } ++n_acc0; };
+      auto acquire_acc1 = [&]() { if (n_acc1 > 0) { WAIT(&bars->acc_empty[1], (n_acc1 - 1) & 1, 221); tc_fence_after(); } ++n_acc1; };
       const uint32_t tX = tmem_base + TM_X, tS = tmem_base + TM_S, tP = tmem_base + TM_P, tQO = tmem_base + TM_QO;
+#pragma unroll 1
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        wait_bar(&bars->xp_full, n_xp++ & 1, 230); tc_fence_after();
+        WAIT(&bars->xp_full, n_xp++ & 1, 230); tc_fence_after();
+        PHASE(45);
+#pragma unroll 1
         for (int l = 0; l < a.n_layers; ++l) {
           // ---- Q | K | V = x W_qkv^T, three 128-column chunks into accumulators 0, 1, 0 ----
-          for (int c = 0; c < 3; ++c) {
-            const int b = c & 1;
-            acquire_acc(b);
-            gemm_k128(b ? tP : tS, tX, false);
-            umma_commit(&bars->acc_full[b]);
-          }
+          acquire_acc0(); gemm_k128(tS, tX, false); if (leader) umma_commit(&bars->acc_full[0]);
+          acquire_acc1(); gemm_k128(tP, tX, false); if (leader) umma_commit(&bars->acc_full[1]);
+          acquire_acc0(); gemm_k128(tS, tX, false); if (leader) umma_commit(&bars->acc_full[0]);
+          PHASE(40);
           // ---- attention: scores of head h + 1 are issued before the P V product of head h ----
-          wait_bar(&bars->qo_ready, n_qo++ & 1, 231);
-          wait_bar(&bars->kv_ready, n_kv++ & 1, 232);
+          WAIT(&bars->qo_ready, n_qo++ & 1, 231);
+          WAIT(&bars->kv_ready, n_kv++ & 1, 232);
           tc_fence_after();
           auto issue_pv = [&](int h) {
-            wait_bar(&bars->hp_full, n_hp++ & 1, 233); tc_fence_after();
-#pragma unroll 1
-            for (int ks = 0; ks < nks; ++ks) {
-              const uint32_t vb = smem_u32(VT + (ks >> 2) * (2 * BLK)) + h * 2048 + (ks & 3) * 32;
-              const uint64_t dvh = umma_desc(vb), dvl = umma_desc(vb + BLK);
-              const uint32_t ph = tP + ks * 8, pl = ph + 64;
-              umma_f16_ts(tQO + h * 16, ph, dvh, ks ? 1u : 0u, IDESC_PV);
-              umma_f16_ts(tQO + h * 16, pl, dvh, 1u, IDESC_PV);
-              umma_f16_ts(tQO + h * 16, ph, dvl, 1u, IDESC_PV);
+            WAIT(&bars->hp_full, n_hp++ & 1, 233); tc_fence_after();
+            if (leader) {
+              const uint64_t dv = vt_desc + (uint32_t)h * 128u;               // V^T rows 16h.. : 16 x 128 B
+              const uint32_t d_o = tQO + h * 16;
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                if (ks < nks) {
+                  const uint64_t dvh = dv + (ks >> 2) * (2 * DBLK) + (ks & 3) * 2, dvl = dvh + DBLK;
+                  const uint32_t ph = tP + ks * 8, pl = ph + 64;
+                  umma_f16_ts(d_o, ph, dvh, ks ? 1u : 0u, IDESC_PV);
+                  umma_f16_ts(d_o, pl, dvh, 1u, IDESC_PV);
+                  umma_f16_ts(d_o, ph, dvl, 1u, IDESC_PV);
+                }
+              }
+              umma_commit(&bars->hp_empty);
             }
-            umma_commit(&bars->hp_empty);
           };
+#pragma unroll 1
           for (int h = 0; h < H; ++h) {
-            acquire_acc(0);
-            const uint32_t kb = smem_u32(KP + (h >> 2) * (2 * BLK)) + (h & 3) * 32;
-            const uint64_t dkh = umma_desc(kb), dkl = umma_desc(kb + BLK);
-            const uint32_t qh = tQO + h * 16, ql = qh + 8;
-            umma_f16_ts(tS, qh, dkh, 0u, IDESC_G);
-            umma_f16_ts(tS, ql, dkh, 1u, IDESC_G);
-            umma_f16_ts(tS, qh, dkl, 1u, IDESC_G);
-            umma_commit(&bars->acc_full[0]);
+            acquire_acc0();
+            if (leader) {
+              const uint64_t dkh = kp_desc + (uint32_t)(h >> 2) * (2 * DBLK) + (uint32_t)(h & 3) * 2, dkl = dkh + DBLK;
+              const uint32_t qh = tQO + h * 16, ql = qh + 8;
+              umma_f16_ts(tS, qh, dkh, 0u, IDESC_G);
+              umma_f16_ts(tS, ql, dkh, 1u, IDESC_G);
+              umma_f16_ts(tS, qh, dkl, 1u, IDESC_G);
+              umma_commit(&bars->acc_full[0]);
+            }
             if (h > 0) issue_pv(h - 1);
           }
           issue_pv(H - 1);
-          umma_commit(&bars->y_full);
+          if (leader) umma_commit(&bars->y_full);
+          PHASE(41);
           // ---- heads W_out^T ----
-          wait_bar(&bars->qo_ready, n_qo++ & 1, 234); tc_fence_after();
-          acquire_acc(0);
+          WAIT(&bars->qo_ready, n_qo++ & 1, 234); tc_fence_after();
+          acquire_acc0();
           gemm_k128(tS, tQO, false);
-          umma_commit(&bars->acc_full[0]);
+          if (leader) umma_commit(&bars->acc_full[0]);
+          PHASE(42);
           // ---- FF: hidden chunk j+1 (FF1) is issued before the FF2 partial product over chunk j ----
-          wait_bar(&bars->xp_full, n_xp++ & 1, 235); tc_fence_after();
+          WAIT(&bars->xp_full, n_xp++ & 1, 235); tc_fence_after();
+#pragma unroll 1
           for (int j = 0; j < 4; ++j) {
-            acquire_acc(0);
+            acquire_acc0();
             gemm_k128(tS, tX, false);
-            umma_commit(&bars->acc_full[0]);
+            if (leader) umma_commit(&bars->acc_full[0]);
             if (j > 0) {
-              wait_bar(&bars->hp_full, n_hp++ & 1, 236); tc_fence_after();
+              WAIT(&bars->hp_full, n_hp++ & 1, 236); tc_fence_after();
               gemm_k128(tQO, tP, j > 1);
-              umma_commit(&bars->hp_empty);
+              if (leader) umma_commit(&bars->hp_empty);
             }
           }
-          wait_bar(&bars->hp_full, n_hp++ & 1, 237); tc_fence_after();
+          WAIT(&bars->hp_full, n_hp++ & 1, 237); tc_fence_after();
           gemm_k128(tQO, tP, true);
-          umma_commit(&bars->hp_empty);
-          umma_commit(&bars->y_full);
-          wait_bar(&bars->xp_full, n_xp++ & 1, 238); tc_fence_after();      // next layer's input / the embeddings
+          if (leader) { umma_commit(&bars->hp_empty); umma_commit(&bars->y_full); }
+          WAIT(&bars->xp_full, n_xp++ & 1, 238); tc_fence_after();      // next layer's input / the embeddings
+          PHASE(43);
         }
         // ---- node projection (glimpse K | glimpse V | folded logit K [| AM step table]) ----
+#pragma unroll 1
         for (int c = 0; c < a.n_node_chunks; ++c) {
-          const int b = c & 1;
-          acquire_acc(b);
-          gemm_k128(b ? tP : tS, tX, false);
-          umma_commit(&bars->acc_full[b]);
+          if (c & 1) { acquire_acc1(); gemm_k128(tP, tX, false); if (leader) umma_commit(&bars->acc_full[1]); }
+          else { acquire_acc0(); gemm_k128(tS, tX, false); if (leader) umma_commit(&bars->acc_full[0]); }
         }
+        PHASE(44);
       }
+      if (leader) PROF_DUMP(1);
     }
   } else {
     // =========================== workers: thread = (row r of the tile = TMEM lane, column quarter q) ===========================
@@ -331,7 +404,8 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap mapW, const Args a) {
     const uint32_t tX = tmem_base + lane_base + TM_X, tS = tmem_base + lane_base + TM_S,
                    tP = tmem_base + lane_base + TM_P, tQO = tmem_base + lane_base + TM_QO;
     const float c2 = 0.25f * 1.4426950408889634f;         // norm_factor 1/sqrt(16) (nets/GraphEncoder.py:38) and log2(e)
-    uint32_t n_accf[2] = {0, 0}, n_hp = 0, n_y = 0;
+    uint32_t n_accf0 = 0, n_accf1 = 0, n_hp = 0, n_y = 0;
+    PROF_DECL
     // keys this thread's row attends to: the rows of its own instance
     uint32_t kmask = 0;
     {
@@ -341,27 +415,52 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap mapW, const Args a) {
 #pragma unroll
       for (int e = 0; e < 32; ++e) kmask |= ((32 * q + e >= klo && 32 * q + e < khi) ? 1u : 0u) << e;
     }
-    auto wait_acc = [&](int b, int code) { wait_bar(&bars->acc_full[b], n_accf[b]++ & 1, code); tc_fence_after(); };
+    const bool all_keys = __all_sync(0xffffffffu, kmask == 0xffffffffu);      // warp-uniform: no masking needed
+    auto wait_acc0 = [&](int code) { WAIT(&bars->acc_full[0], n_accf0++ & 1, code); tc_fence_after(); };
+    auto wait_acc1 = [&](int code) { WAIT(&bars->acc_full[1], n_accf1++ & 1, code); tc_fence_after(); };
     auto release_acc = [&](int b) { tmem_ld_wait(); tc_fence_before(); warp_arrive(&bars->acc_empty[b], lane); };
     auto wait_p_free = [&](int code) {       // the MMAs that read the previous contents of the P region have retired
-      if (n_hp > 0) { wait_bar(&bars->hp_empty, (n_hp - 1) & 1, code); tc_fence_after(); }
+      if (n_hp > 0) { WAIT(&bars->hp_empty, (n_hp - 1) & 1, code); tc_fence_after(); }
       ++n_hp;
     };
-    auto store_x_planes = [&](const float (&v)[32]) {
+    // 16 fp32 pairs -> (hi, lo) planes at packed columns 16q.. / 64 + 16q.. of a 128-column operand region
+    auto store_planes = [&](uint32_t region, const uint64_t (&v)[16]) {
       uint32_t hi[16], lo[16];
       split32(v, hi, lo);
-      tmem_st16(tX + 16 * q, hi);
-      tmem_st16(tX + 64 + 16 * q, lo);
+      tmem_st16(region + 16 * q, hi);
+      tmem_st16(region + 64 + 16 * q, lo);
       tmem_st_wait(); tc_fence_before();
-      warp_arrive(&bars->xp_full, lane);
     };
 
+    // Output tiles leave through shared memory: the K / V^T plane regions (dead outside the attention phase) alternate
+    // as staging buffers of four [rows x 32 fp32] 128-byte-swizzled boxes; the four warps that own a column quarter
+    // fill box q and one of their threads hands it to TMA (a direct store would touch 32 separate lines per warp
+    // instruction).  A buffer is rewritten only after the bulk store issued two outputs earlier has read it.
+    uint32_t n_out = 0;
+    const bool out_leader = (g == 0 && lane == 0);
+    auto stage_out = [&](const CUtensorMap* map, int col0, int row0, const uint32_t (&u)[32], float scale) {
+      unsigned char* box = (n_out & 1 ? VT : KP) + q * BLK;
+      ++n_out;
+      if (out_leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      col_group_sync(q);
+      unsigned char* row = box + r * 128;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(row + ((i ^ (r & 7)) << 4)) =
+            make_float4(__uint_as_float(u[4 * i]) * scale, __uint_as_float(u[4 * i + 1]) * scale,
+                        __uint_as_float(u[4 * i + 2]) * scale, __uint_as_float(u[4 * i + 3]) * scale);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      col_group_sync(q);
+      if (out_leader) tma_store_2d(map, box, col0 + 32 * q, row0);
+    };
+
+#pragma unroll 1
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int grow = tile * rows_per_tile + r;
       const bool valid = r < rows_per_tile && grow < M;
       // ---- init embedding (nets/DRLModel.py:192-200): depot | stations | customers (x/100, y/100[, demand]) ----
       {
-        float v[32];
+        uint64_t v[16];
         if (valid) {
           const int b = grow / S, j = grow - b * S;
           const float x = __fdiv_rn(__ldg(a.xy + ((size_t)b * 2 + 0) * S + j), 100.f);
@@ -370,32 +469,39 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap mapW, const Args a) {
             const float* w = (j == 0 ? a.depot_w : a.station_w) + 64 * q;
             const float* bb = (j == 0 ? a.depot_b : a.station_b) + 32 * q;
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float4 ww = __ldg(reinterpret_cast<const float4*>(w + 2 * i));
-              const float2 b2 = __ldg(reinterpret_cast<const float2*>(bb + i));
-              v[i] = fmaf(ww.y, y, fmaf(ww.x, x, 0.f)) + b2.x;
-              v[i + 1] = fmaf(ww.w, y, fmaf(ww.z, x, 0.f)) + b2.y;
+            for (int i = 0; i < 16; ++i) {
+              const float4 ww = __ldg(reinterpret_cast<const float4*>(w + 4 * i));
+              const float2 b2 = __ldg(reinterpret_cast<const float2*>(bb + 2 * i));
+              v[i] = pk2(fmaf(ww.y, y, fmaf(ww.x, x, 0.f)) + b2.x, fmaf(ww.w, y, fmaf(ww.z, x, 0.f)) + b2.y);
             }
           } else {
             const float dem = __ldg(a.dyn + ((size_t)b * 4 + 1) * S + j);
             const float* w = a.cust_w + 96 * q;
             const float* bb = a.cust_b + 32 * q;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              v[i] = fmaf(__ldg(w + 3 * i + 2), dem, fmaf(__ldg(w + 3 * i + 1), y, fmaf(__ldg(w + 3 * i), x, 0.f))) + __ldg(bb + i);
+            for (int i = 0; i < 16; ++i) {
+              const float2 w0 = __ldg(reinterpret_cast<const float2*>(w + 6 * i)), w1 = __ldg(reinterpret_cast<const float2*>(w + 6 * i + 2)),
+                           w2 = __ldg(reinterpret_cast<const float2*>(w + 6 * i + 4));
+              const float2 b2 = __ldg(reinterpret_cast<const float2*>(bb + 2 * i));
+              v[i] = pk2(fmaf(w1.x, dem, fmaf(w0.y, y, fmaf(w0.x, x, 0.f))) + b2.x, fmaf(w2.y, dem, fmaf(w2.x, y, fmaf(w1.y, x, 0.f))) + b2.y);
+            }
           }
           if (a.n_layers == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(a.emb + (size_t)grow * D + 32 * q + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            for (int i = 0; i < 16; i += 2)
+              *reinterpret_cast<float4*>(a.emb + (size_t)grow * D + 32 * q + 2 * i) = make_float4(lo_of(v[i]), hi_of(v[i]), lo_of(v[i + 1]), hi_of(v[i + 1]));
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          for (int i = 0; i < 16; ++i) v[i] = 0ull;
         }
-        store_x_planes(v);
+        store_planes(tX, v);
+        if (out_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // K / V^T regions free again
+        warp_arrive(&bars->xp_full, lane);
       }
+      PHASE(90);
 
+#pragma unroll 1
       for (int l = 0; l < a.n_layers; ++l) {
         const float* prm = a.params + (size_t)l * LP;
         const float inv_qkv = __ldg(prm + P_INV), inv_wo = __ldg(prm + P_INV + 1), inv_w1 = __ldg(prm + P_INV + 2),
@@ -403,16 +509,18 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap mapW, const Args a) {
         // ---- Q chunk -> operand planes per head in QO: head 2q at columns 32q (hi 8 | lo 8), head 2q+1 at 32q + 16 ----
         {
           uint32_t u[32];
-          wait_acc(0, 300);
+          wait_acc0(300);
           tmem_ld32(tS + 32 * q, u);
           release_acc(0);
-          float v[32];
+          const uint64_t sc = pk2(inv_qkv, inv_qkv);
+          uint32_t o[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]) * inv_qkv;
-          uint32_t hi[16], lo[16], o[32];
-          split32(v, hi, lo);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { o[i] = hi[i]; o[8 + i] = lo[i]; o[16 + i] = hi[8 + i]; o[24 + i] = lo[8 + i]; }
+          for (int i = 0; i < 16; ++i) {
+            uint32_t hi, lo;
+            split_pair(mul2(pk2u(u[2 * i], u[2 * i + 1]), sc), hi, lo);
+            o[(i >> 3) * 16 + (i & 7)] = hi;
+            o[(i >> 3) * 16 + 8 + (i & 7)] = lo;
+          }
           tmem_st32(tQO + 32 * q, o);
           tmem_st_wait(); tc_fence_before();
           warp_arrive(&bars->qo_ready, lane);
@@ -420,14 +528,13 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap mapW, const Args a) {
         // ---- K chunk -> K planes in shared memory: row = key r, channels 32q..32q+31 = 4 swizzled 16-byte chunks ----
         {
           uint32_t u[32];
-          wait_acc(1, 301);
+          wait_acc1(301);
           tmem_ld32(tP + 32 * q, u);
           release_acc(1);
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]) * inv_qkv;
+          const uint64_t sc = pk2(inv_qkv, inv_qkv);
           uint32_t hi[16], lo[16];
-          split32(v, hi, lo);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) split_pair(mul2(pk2u(u[2 * i], u[2 * i + 1]), sc), hi[i], lo[i]);
           unsigned char* kp = KP + (q >> 1) * (2 * BLK) + r * 128;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -439,34 +546,47 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap mapW, const Args a) {
         // ---- V chunk -> V^T planes: element (channel d, key r) -> key block r / 64, row d, fp16 column r % 64 ----
         {
           uint32_t u[32];
-          wait_acc(0, 302);
+          wait_acc0(302);
           tmem_ld32(tS + 32 * q, u);
           release_acc(0);
+          const uint64_t sc = pk2(inv_qkv, inv_qkv);
           unsigned char* vb = VT + (r >> 6) * (2 * BLK) + (32 * q) * 128 + ((r & 7) << 1);
           const int kc = (r & 63) >> 3;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = __uint_as_float(u[i]) * inv_qkv;
-            const __half hi = __float2half_rn(x);
-            const __half lo = __float2half_rn(x - __half2float(hi));
-            unsigned char* p = vb + i * 128 + ((kc ^ (i & 7)) << 4);
-            *reinterpret_cast<__half*>(p) = hi;
-            *reinterpret_cast<__half*>(p + BLK) = lo;
+          for (int i = 0; i < 16; ++i) {
+            uint32_t hi, lo;
+            split_pair(mul2(pk2u(u[2 * i], u[2 * i + 1]), sc), hi, lo);
+            unsigned char* p0 = vb + (2 * i) * 128 + ((kc ^ ((2 * i) & 7)) << 4);
+            unsigned char* p1 = vb + (2 * i + 1) * 128 + ((kc ^ ((2 * i + 1) & 7)) << 4);
+            *reinterpret_cast<unsigned short*>(p0) = (unsigned short)(hi & 0xffffu);
+            *reinterpret_cast<unsigned short*>(p1) = (unsigned short)(hi >> 16);
+            *reinterpret_cast<unsigned short*>(p0 + BLK) = (unsigned short)(lo & 0xffffu);
+            *reinterpret_cast<unsigned short*>(p1 + BLK) = (unsigned short)(lo >> 16);
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // K and V^T writes -> visible to tcgen05
           warp_arrive(&bars->kv_ready, lane);
         }
+        PHASE(91);
         // ---- softmax of every head: p = 2^(c2 (s - max)) unnormalised, masked keys 0; planes to the P region ----
         float tot0 = 1.f, tot1 = 1.f;                     // softmax denominators of this thread's heads 2q, 2q + 1
+#pragma unroll 1
         for (int h = 0; h < H; ++h) {
           const int par = h & 1;
           uint32_t u[32];
-          wait_acc(0, 310 + h);
+          wait_acc0(310);
           tmem_ld32(tS + 32 * q, u);
           release_acc(0);
-          float mx = -INFINITY;
+          if (!all_keys) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, ((kmask >> e) & 1u) ? __uint_as_float(u[e]) : -INFINITY);
+            for (int e = 0; e < 32; ++e) u[e] = ((kmask >> e) & 1u) ? u[e] : 0xff800000u;      // -inf: p = 0
+          }
+          float m0 = fmaxf(__uint_as_float(u[0]), __uint_as_float(u[1])), m1 = fmaxf(__uint_as_float(u[2]), __uint_as_float(u[3]));
+#pragma unroll
+          for (int e = 4; e < 32; e += 4) {
+            m0 = fmaxf(m0, fmaxf(__uint_as_float(u[e]), __uint_as_float(u[e + 1])));
+            m1 = fmaxf(m1, fmaxf(__uint_as_float(u[e + 2]), __uint_as_float(u[e + 3])));
+          }
+          float mx = fmaxf(m0, m1);
           pmax[(par * 4 + q) * 128 + r] = mx;
           row_group_sync(g);
           mx = fmaxf(fmaxf(pmax[(par * 4 + 0) * 128 + r], pmax[(par * 4 + 1) * 128 + r]),
@@ -476,25 +596,31 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap mapW, const Args a) {
             const float t = (ps[0] + ps[128]) + (ps[256] + ps[384]);
             if (((h - 1) >> 1) == q) { if ((h - 1) & 1) tot1 = t; else tot0 = t; }
           }
-          const float mx2 = mx * c2;
-          float p[32];
-          float sum = 0.f;
+          const float nmx2 = -mx * c2;
+          const uint64_t cc = pk2(c2, c2), mm = pk2(nmx2, nmx2);
+          uint64_t p[16];
+          uint64_t sum0 = 0ull, sum1 = 0ull;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float x = ((kmask >> e) & 1u) ? fmaf(__uint_as_float(u[e]), c2, -mx2) : -INFINITY;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p[e]) : "f"(x));
+          for (int e = 0; e < 16; ++e) {
+            const uint64_t x = fma2(pk2u(u[2 * e], u[2 * e + 1]), cc, mm);
+            float a0, a1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a0) : "f"(lo_of(x)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a1) : "f"(hi_of(x)));
+            p[e] = pk2(a0, a1);
+            if (e & 1) sum1 = add2(sum1, p[e]); else sum0 = add2(sum0, p[e]);
           }
-#pragma unroll
-          for (int e = 0; e < 32; ++e) sum += p[e];
+          const uint64_t sm = add2(sum0, sum1);
+          const float sum = lo_of(sm) + hi_of(sm);
           uint32_t hi[16], lo[16];
           split32(p, hi, lo);
-          wait_p_free(320 + h);
+          wait_p_free(320);
           tmem_st16(tP + 16 * q, hi);
           tmem_st16(tP + 64 + 16 * q, lo);
           tmem_st_wait(); tc_fence_before();
           warp_arrive(&bars->hp_full, lane);
           psum[(par * 4 + q) * 128 + r] = sum;
         }
+        PHASE(92);
         // ---- concatenated heads: O / denominator -> operand planes, in place in QO ----
         {
           row_group_sync(g);                              // the last head's partial denominators are visible
@@ -503,14 +629,15 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap mapW, const Args a) {
             const float t = (ps[0] + ps[128]) + (ps[256] + ps[384]);
             if (((H - 1) >> 1) == q) tot1 = t;
           }
-          wait_bar(&bars->y_full, n_y++ & 1, 330); tc_fence_after();
+          WAIT(&bars->y_full, n_y++ & 1, 330); tc_fence_after();
           uint32_t u[32];
           tmem_ld32(tQO + 32 * q, u);
           tmem_ld_wait();
           const float i0 = 1.f / tot0, i1 = 1.f / tot1;
-          float v[32];
+          const uint64_t s0 = pk2(i0, i0), s1 = pk2(i1, i1);
+          uint64_t v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(u[i]) * i0; v[16 + i] = __uint_as_float(u[16 + i]) * i1; }
+          for (int i = 0; i < 8; ++i) { v[i] = mul2(pk2u(u[2 * i], u[2 * i + 1]), s0); v[8 + i] = mul2(pk2u(u[16 + 2 * i], u[17 + 2 * i]), s1); }
           uint32_t hi[16], lo[16];
           split32(v, hi, lo);
           tc_fence_before();
@@ -521,97 +648,103 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap mapW, const Args a) {
           tmem_st_wait(); tc_fence_before();
           warp_arrive(&bars->qo_ready, lane);
         }
+        PHASE(93);
         // ---- x1 = BN1(x + heads W_out^T)  (nets/GraphEncoder.py:162-169): planes rewritten in place ----
         {
           uint32_t u[32], xh[16], xl[16];
-          wait_acc(0, 340);
+          wait_acc0(340);
           tmem_ld32(tS + 32 * q, u);
           tmem_ld16(tX + 16 * q, xh);
           tmem_ld16(tX + 64 + 16 * q, xl);
           release_acc(0);
-          float x[32], v[32];
-          join32(xh, xl, x);
+          const uint64_t iw = pk2(inv_wo, inv_wo);
+          uint64_t v[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(prm + P_BN1S + 32 * q + i));
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(prm + P_BN1B + 32 * q + i));
-            v[i] = fmaf(fmaf(__uint_as_float(u[i]), inv_wo, x[i]), sc.x, sh.x);
-            v[i + 1] = fmaf(fmaf(__uint_as_float(u[i + 1]), inv_wo, x[i + 1]), sc.y, sh.y);
-            v[i + 2] = fmaf(fmaf(__uint_as_float(u[i + 2]), inv_wo, x[i + 2]), sc.z, sh.z);
-            v[i + 3] = fmaf(fmaf(__uint_as_float(u[i + 3]), inv_wo, x[i + 3]), sc.w, sh.w);
+          for (int i = 0; i < 16; i += 2) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(prm + P_BN1S + 32 * q + 2 * i));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(prm + P_BN1B + 32 * q + 2 * i));
+            v[i] = fma2(fma2(pk2u(u[2 * i], u[2 * i + 1]), iw, join_pair(xh[i], xl[i])), pk2(sc.x, sc.y), pk2(sh.x, sh.y));
+            v[i + 1] = fma2(fma2(pk2u(u[2 * i + 2], u[2 * i + 3]), iw, join_pair(xh[i + 1], xl[i + 1])), pk2(sc.z, sc.w), pk2(sh.z, sh.w));
           }
-          store_x_planes(v);
+          store_planes(tX, v);
+          warp_arrive(&bars->xp_full, lane);
         }
+        PHASE(94);
         // ---- hidden chunk j = relu(x1 W1_j^T + b1_j) -> operand planes in the P region ----
+#pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           uint32_t u[32];
-          wait_acc(0, 350 + j);
+          wait_acc0(350);
           tmem_ld32(tS + 32 * q, u);
           release_acc(0);
-          float v[32];
+          const uint64_t iw = pk2(inv_w1, inv_w1);
+          uint64_t v[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(prm + P_B1 + 128 * j + 32 * q + i));
-            v[i] = fmaxf(fmaf(__uint_as_float(u[i]), inv_w1, bb.x), 0.f);
-            v[i + 1] = fmaxf(fmaf(__uint_as_float(u[i + 1]), inv_w1, bb.y), 0.f);
-            v[i + 2] = fmaxf(fmaf(__uint_as_float(u[i + 2]), inv_w1, bb.z), 0.f);
-            v[i + 3] = fmaxf(fmaf(__uint_as_float(u[i + 3]), inv_w1, bb.w), 0.f);
+          for (int i = 0; i < 16; i += 2) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(prm + P_B1 + 128 * j + 32 * q + 2 * i));
+            const uint64_t t0 = fma2(pk2u(u[2 * i], u[2 * i + 1]), iw, pk2(bb.x, bb.y));
+            const uint64_t t1 = fma2(pk2u(u[2 * i + 2], u[2 * i + 3]), iw, pk2(bb.z, bb.w));
+            v[i] = pk2(fmaxf(lo_of(t0), 0.f), fmaxf(hi_of(t0), 0.f));
+            v[i + 1] = pk2(fmaxf(lo_of(t1), 0.f), fmaxf(hi_of(t1), 0.f));
           }
           uint32_t hi[16], lo[16];
           split32(v, hi, lo);
-          wait_p_free(360 + j);
+          wait_p_free(360);
           tmem_st16(tP + 16 * q, hi);
           tmem_st16(tP + 64 + 16 * q, lo);
           tmem_st_wait(); tc_fence_before();
           warp_arrive(&bars->hp_full, lane);
         }
+        PHASE(95);
         // ---- x2 = BN2(x1 + hidden W2^T + b2): the next layer's input; the last layer's is the node embedding ----
         {
           uint32_t u[32], xh[16], xl[16];
-          wait_bar(&bars->y_full, n_y++ & 1, 370); tc_fence_after();
+          WAIT(&bars->y_full, n_y++ & 1, 370); tc_fence_after();
           tmem_ld32(tQO + 32 * q, u);
           tmem_ld16(tX + 16 * q, xh);
           tmem_ld16(tX + 64 + 16 * q, xl);
           tmem_ld_wait();
-          float x[32], v[32];
-          join32(xh, xl, x);
+          const uint64_t iw = pk2(inv_w2, inv_w2);
+          uint64_t v[16];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(prm + P_B2 + 32 * q + i));
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(prm + P_BN2S + 32 * q + i));
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(prm + P_BN2B + 32 * q + i));
-            v[i] = fmaf(fmaf(__uint_as_float(u[i]), inv_w2, bb.x) + x[i], sc.x, sh.x);
-            v[i + 1] = fmaf(fmaf(__uint_as_float(u[i + 1]), inv_w2, bb.y) + x[i + 1], sc.y, sh.y);
-            v[i + 2] = fmaf(fmaf(__uint_as_float(u[i + 2]), inv_w2, bb.z) + x[i + 2], sc.z, sh.z);
-            v[i + 3] = fmaf(fmaf(__uint_as_float(u[i + 3]), inv_w2, bb.w) + x[i + 3], sc.w, sh.w);
+          for (int i = 0; i < 16; i += 2) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(prm + P_B2 + 32 * q + 2 * i));
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(prm + P_BN2S + 32 * q + 2 * i));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(prm + P_BN2B + 32 * q + 2 * i));
+            v[i] = fma2(add2(fma2(pk2u(u[2 * i], u[2 * i + 1]), iw, pk2(bb.x, bb.y)), join_pair(xh[i], xl[i])), pk2(sc.x, sc.y), pk2(sh.x, sh.y));
+            v[i + 1] = fma2(add2(fma2(pk2u(u[2 * i + 2], u[2 * i + 3]), iw, pk2(bb.z, bb.w)), join_pair(xh[i + 1], xl[i + 1])), pk2(sc.z, sc.w), pk2(sh.z, sh.w));
           }
-          if (l == a.n_layers - 1 && valid) {
+          store_planes(tX, v);
+          warp_arrive(&bars->xp_full, lane);
+          if (l == a.n_layers - 1) {                      // the node embeddings (after the hand-off: the MMAs run meanwhile)
+            uint32_t w[32];
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(a.emb + (size_t)grow * D + 32 * q + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            for (int i = 0; i < 16; ++i) { w[2 * i] = (uint32_t)v[i]; w[2 * i + 1] = (uint32_t)(v[i] >> 32); }
+            stage_out(&mapEmb, 0, tile * rows_per_tile, w, 1.f);
           }
-          store_x_planes(v);
         }
+        PHASE(96);
       }
       // ---- node projection chunks -> kvl (chunks 0..2) / step table (chunk 3) ----
       {
         const float inv_node = __ldg(a.params + (size_t)a.n_layers * LP);
+#pragma unroll 1
         for (int c = 0; c < a.n_node_chunks; ++c) {
           const int b = c & 1;
           uint32_t u[32];
-          wait_acc(b, 380 + c);
+          if (b) wait_acc1(381); else wait_acc0(380);
           tmem_ld32((b ? tP : tS) + 32 * q, u);
           release_acc(b);
-          if (valid) {
-            float* o = c < 3 ? a.kvl + (size_t)grow * 384 + 128 * c + 32 * q : a.step_tab + (size_t)grow * D + 32 * q;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(o + i) = make_float4(__uint_as_float(u[i]) * inv_node, __uint_as_float(u[i + 1]) * inv_node,
-                                                               __uint_as_float(u[i + 2]) * inv_node, __uint_as_float(u[i + 3]) * inv_node);
-          }
+          if (c < 3) stage_out(&mapKvl, 128 * c, tile * rows_per_tile, u, inv_node);
+          else stage_out(&mapTab, 0, tile * rows_per_tile, u, inv_node);
         }
       }
+      PHASE(97);
     }
+    if (out_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#ifdef EVRP_FENC_PROF
+    if (threadIdx.x == 0) PROF_DUMP(2);
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -629,9 +762,14 @@ int launch_encoder_fused(const evrp_encoder_weights* w, const float* xy, const f
   if (step_tab && w->fused_node_chunks < 4) return -EVRP_E_BADARG;
   // the node projection is packed with fused_node_chunks chunks; a 3-chunk call on a 4-chunk pack reads the first three
   const int pack_blocks = w->n_layers * LAYER_BLOCKS + w->fused_node_chunks * 4;
-  CUtensorMap map;
+  CUtensorMap map, mapEmb, mapKvl, mapTab;
   int rc;
   if ((rc = tc::make_weight_map_f16(&map, w->fused_w, pack_blocks * 128, 64, 128))) return rc;
+  const int ipt0 = S > 64 ? 1 : 128 / S;
+  // output maps: box = [32 fp32 x rows of one tile], 128-byte swizzle; rows beyond B*S are clipped by the TMA unit
+  if ((rc = tc::make_weight_map(&mapEmb, emb, B * S, 128, 128, ipt0 * S))) return rc;
+  if ((rc = tc::make_weight_map(&mapKvl, kvl, B * S, 384, 384, ipt0 * S))) return rc;
+  if ((rc = tc::make_weight_map(&mapTab, step_tab ? step_tab : emb, B * S, 128, 128, ipt0 * S))) return rc;
   Args a;
   a.params = w->fused_params;
   a.depot_w = w->depot_w; a.depot_b = w->depot_b; a.station_w = w->station_w; a.station_b = w->station_b;
@@ -642,12 +780,18 @@ int launch_encoder_fused(const evrp_encoder_weights* w, const float* xy, const f
   const int n_tiles = (B + ipt - 1) / ipt;
   EVRP_CUDA_OK(cudaFuncSetAttribute(encoder_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   const int grid = n_tiles < sm_count ? n_tiles : sm_count;
-  encoder_fused_kernel<<<grid, NT, SMEM_BYTES, st>>>(map, a);
+  encoder_fused_kernel<<<grid, NT, SMEM_BYTES, st>>>(map, mapEmb, mapKvl, mapTab, a);
   EVRP_LAUNCH_OK();
   return 0;
 }
 
 }  // namespace evrp
+
+#ifdef EVRP_FENC_PROF
+extern "C" int evrp_encoder_fused_prof(unsigned long long* out300_host) {
+  return cudaMemcpyFromSymbol(out300_host, evrp::fenc::g_prof, sizeof(unsigned long long) * 300) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 // diagnostics of the fused encoder kernel: out8[0] = code of the first wait that timed out (0: none), [1] CTA, [2] thread
 extern "C" int evrp_encoder_fused_debug(int* out8_host, int reset) {
