@@ -144,6 +144,10 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
         "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -201,6 +205,8 @@ __device__ __forceinline__ uint64_t join_pair(uint32_t hi, uint32_t lo) {
   const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lo));
   return add2(pk2(a.x, a.y), pk2(b.x, b.y));
 }
+
+template <int V> struct IC { static constexpr int value = V; };
 
 struct Args {
   const float* params;                 // [n_layers][LP] + [1] inverse scale of the node projection
@@ -416,6 +422,12 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_cons
       for (int e = 0; e < 32; ++e) kmask |= ((32 * q + e >= klo && 32 * q + e < khi) ? 1u : 0u) << e;
     }
     const bool all_keys = __all_sync(0xffffffffu, kmask == 0xffffffffu);      // warp-uniform: no masking needed
+    // blocks of 16 keys (32q.., 32q + 16..) that some row of this warp attends to (warp-uniform): n_live of them, the
+    // first at block blk0; kmask_live = the thread's key mask from that block on
+    const uint32_t half_live = (__any_sync(0xffffffffu, (kmask & 0xffffu) != 0u) ? 1u : 0u) |
+                               (__any_sync(0xffffffffu, (kmask >> 16) != 0u) ? 2u : 0u);
+    const int n_live = (half_live & 1u) + (half_live >> 1), blk0 = half_live == 2u ? 1 : 0;
+    const uint32_t kmask_live = kmask >> (16 * blk0);
     auto wait_acc0 = [&](int code) { WAIT(&bars->acc_full[0], n_accf0++ & 1, code); tc_fence_after(); };
     auto wait_acc1 = [&](int code) { WAIT(&bars->acc_full[1], n_accf1++ & 1, code); tc_fence_after(); };
     auto release_acc = [&](int b) { tmem_ld_wait(); tc_fence_before(); warp_arrive(&bars->acc_empty[b], lane); };
@@ -568,25 +580,32 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_cons
         }
         PHASE(91);
         // ---- softmax of every head: p = 2^(c2 (s - max)) unnormalised, masked keys 0; planes to the P region ----
+        // Of the thread's two blocks of 16 keys only those that some row of the warp attends to are processed (keys
+        // beyond the graph and the other instances of a packed tile cost nothing): NL = 2, 1 or 0 live blocks.
         float tot0 = 1.f, tot1 = 1.f;                     // softmax denominators of this thread's heads 2q, 2q + 1
-#pragma unroll 1
-        for (int h = 0; h < H; ++h) {
+        auto softmax_head = [&](int h, auto nl_tag) {
+          constexpr int NL = decltype(nl_tag)::value;
+          constexpr int NE = NL == 2 ? 32 : 16;
           const int par = h & 1;
-          uint32_t u[32];
+          uint32_t u[NE];
           wait_acc0(310);
-          tmem_ld32(tS + 32 * q, u);
+          if (NL == 2) tmem_ld32(tS + 32 * q, *reinterpret_cast<uint32_t (*)[32]>(&u));
+          else if (NL == 1) tmem_ld16(tS + 32 * q + 16 * blk0, *reinterpret_cast<uint32_t (*)[16]>(&u));
           release_acc(0);
-          if (!all_keys) {
+          float mx = -INFINITY;
+          if (NL > 0) {
+            if (!all_keys) {
 #pragma unroll
-            for (int e = 0; e < 32; ++e) u[e] = ((kmask >> e) & 1u) ? u[e] : 0xff800000u;      // -inf: p = 0
-          }
-          float m0 = fmaxf(__uint_as_float(u[0]), __uint_as_float(u[1])), m1 = fmaxf(__uint_as_float(u[2]), __uint_as_float(u[3]));
+              for (int e = 0; e < NE; ++e) u[e] = ((kmask_live >> e) & 1u) ? u[e] : 0xff800000u;      // -inf: p = 0
+            }
+            float m0 = fmaxf(__uint_as_float(u[0]), __uint_as_float(u[1])), m1 = fmaxf(__uint_as_float(u[2]), __uint_as_float(u[3]));
 #pragma unroll
-          for (int e = 4; e < 32; e += 4) {
-            m0 = fmaxf(m0, fmaxf(__uint_as_float(u[e]), __uint_as_float(u[e + 1])));
-            m1 = fmaxf(m1, fmaxf(__uint_as_float(u[e + 2]), __uint_as_float(u[e + 3])));
+            for (int e = 4; e < NE; e += 4) {
+              m0 = fmaxf(m0, fmaxf(__uint_as_float(u[e]), __uint_as_float(u[e + 1])));
+              m1 = fmaxf(m1, fmaxf(__uint_as_float(u[e + 2]), __uint_as_float(u[e + 3])));
+            }
+            mx = fmaxf(m0, m1);
           }
-          float mx = fmaxf(m0, m1);
           pmax[(par * 4 + q) * 128 + r] = mx;
           row_group_sync(g);
           mx = fmaxf(fmaxf(pmax[(par * 4 + 0) * 128 + r], pmax[(par * 4 + 1) * 128 + r]),
@@ -598,27 +617,54 @@ encoder_fused_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_cons
           }
           const float nmx2 = -mx * c2;
           const uint64_t cc = pk2(c2, c2), mm = pk2(nmx2, nmx2);
-          uint64_t p[16];
+          uint32_t hi[NE / 2], lo[NE / 2];
           uint64_t sum0 = 0ull, sum1 = 0ull;
+          if (NL > 0) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const uint64_t x = fma2(pk2u(u[2 * e], u[2 * e + 1]), cc, mm);
-            float a0, a1;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a0) : "f"(lo_of(x)));
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a1) : "f"(hi_of(x)));
-            p[e] = pk2(a0, a1);
-            if (e & 1) sum1 = add2(sum1, p[e]); else sum0 = add2(sum0, p[e]);
+            for (int hb = 0; hb < NE / 16; ++hb) {          // per block of 16: the exponentials (MUFU), then the split (FMA / ALU)
+              uint64_t p[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const uint64_t x = fma2(pk2u(u[16 * hb + 2 * e], u[16 * hb + 2 * e + 1]), cc, mm);
+                float a0, a1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a0) : "f"(lo_of(x)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a1) : "f"(hi_of(x)));
+                p[e] = pk2(a0, a1);
+              }
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                if (e & 1) sum1 = add2(sum1, p[e]); else sum0 = add2(sum0, p[e]);
+                split_pair(p[e], hi[8 * hb + e], lo[8 * hb + e]);
+              }
+            }
           }
           const uint64_t sm = add2(sum0, sum1);
           const float sum = lo_of(sm) + hi_of(sm);
-          uint32_t hi[16], lo[16];
-          split32(p, hi, lo);
           wait_p_free(320);
-          tmem_st16(tP + 16 * q, hi);
-          tmem_st16(tP + 64 + 16 * q, lo);
+          if (NL == 2) {
+            tmem_st16(tP + 16 * q, *reinterpret_cast<const uint32_t (*)[16]>(&hi));
+            tmem_st16(tP + 64 + 16 * q, *reinterpret_cast<const uint32_t (*)[16]>(&lo));
+          } else {
+            const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if (NL == 1) {
+              tmem_st8(tP + 16 * q + 8 * blk0, *reinterpret_cast<const uint32_t (*)[8]>(&hi));
+              tmem_st8(tP + 64 + 16 * q + 8 * blk0, *reinterpret_cast<const uint32_t (*)[8]>(&lo));
+              tmem_st8(tP + 16 * q + 8 * (blk0 ^ 1), z);
+              tmem_st8(tP + 64 + 16 * q + 8 * (blk0 ^ 1), z);
+            } else {
+              tmem_st8(tP + 16 * q, z); tmem_st8(tP + 16 * q + 8, z);
+              tmem_st8(tP + 64 + 16 * q, z); tmem_st8(tP + 64 + 16 * q + 8, z);
+            }
+          }
           tmem_st_wait(); tc_fence_before();
           warp_arrive(&bars->hp_full, lane);
           psum[(par * 4 + q) * 128 + r] = sum;
+        };
+#pragma unroll 1
+        for (int h = 0; h < H; ++h) {
+          if (n_live == 2) softmax_head(h, IC<2>{});
+          else if (n_live == 1) softmax_head(h, IC<1>{});
+          else softmax_head(h, IC<0>{});
         }
         PHASE(92);
         // ---- concatenated heads: O / denominator -> operand planes, in place in QO ----
