@@ -11,9 +11,17 @@ value      instances/s, whole job, inputs resident in HBM, CUDA-event timed, max
 e2e        the same through the public API call `model((static, dynamic, distances, slope))` with static/dynamic
            in pinned HOST memory (distances/slope live on the device exactly as the reference's dataset keeps
            them, problems/EVRP.py:87-92) and pi / cost read back to the host, copies inside the timed region
-roofline   rollout kernel: algorithmic bytes ((1568*S+2048) B per instance-step x executed
-           instance-steps) / CUDA-event duration of the kernel launch, against MEASURED_PEAKS.json hbm_gbs
-cpu_baseline  the numpy oracle port of the same path on the host cores, bounded sample (rank 0, N=1)
+roofline   rollout kernel, HBM-bound.  `achieved` = the bytes the launch NEEDS (counted live from the recorded
+           feasibility masks of the same rollout: 1,536 B of K / V / logit-K per FEASIBLE node per step + the distance /
+           slope / state rows; masked nodes contribute exactly 0 to the glimpse and the pointer, the kernel never reads
+           them) / CUDA-event duration of the kernel launch; `frac` = achieved / MEASURED_PEAKS.json hbm_gbs.  SURVEY
+           §8d's all-node model ((1568*S+2048) B per instance-step) is printed beside it as `allnode_*` (it counts the
+           masked nodes too and therefore exceeds the peak).  `traffic` = ncu dram bytes of one launch, reported only
+           when profiles/rollout_traffic.json was captured with THIS build (.so hash), batch and graph size.
+cpu_baseline  the PATCHED REFERENCE itself (oracle/_ref, torch on the host cores; kind "reference"), or the numpy
+           oracle port where the copy is absent (kind "port"); bounded sample, child process without CUDA
+reference_gpu  the patched reference as eager PyTorch on the same B200, batch 512
+strong     (N > 1) BASELINE configs[3] as stated: ONE global batch of 8192 sharded B/N per rank
 """
 import argparse
 import json
@@ -76,6 +84,49 @@ def cpu_port_rate(N, sample, threads=None):
     return sample / dt, cores, dt, int(o["pi"].shape[1])
 
 
+def lib_sha256():
+    import hashlib
+    import evrp_b200
+    with open(evrp_b200._lib.LIB_PATH, "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_child(kind, N, B, steps, cuda, timeout=1500):
+    """the patched reference (oracle/ref_runner.py) in a child process: all host threads, CUDA hidden unless `cuda`"""
+    env = dict(os.environ)
+    n = host_threads()
+    env["OMP_NUM_THREADS"] = env["MKL_NUM_THREADS"] = str(n)          # torchrun exports OMP_NUM_THREADS=1
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    if not cuda:
+        env["CUDA_VISIBLE_DEVICES"] = ""
+    out = subprocess.run([sys.executable, "-m", "oracle.ref_runner", kind, str(N), str(B), str(steps)], cwd=ROOT, env=env,
+                         capture_output=True, text=True, timeout=timeout)
+    if out.returncode != 0:
+        raise RuntimeError(out.stderr.strip().splitlines()[-1] if out.stderr.strip() else "reference child failed")
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def needed_bytes(o, S):
+    """bytes one rollout launch needs (tools/needed_bytes.py): per live step 1,536 B per FEASIBLE node (glimpse K, glimpse V,
+    logit K records) + D[c,:], G[c,:], D[0,:], G[0,:], rule-7 rows (6 S floats) + emb[now], emb[c], fixed context, demand
+    row r/w, running-max row r/w (9 x 512 B).  `o` = a rollout with save_trace=True."""
+    import torch
+    from evrp_b200 import policy_math as PM
+    T = o["pi"].shape[1]
+    live = torch.arange(T, device=o["pi"].device)[None] < o["steps"][:, None]
+    feas = int((PM.bits_to_mask(o["mask_bits"], S).sum(-1) * live).sum())
+    steps = int(o["steps"].sum())
+    return feas * 1536 + steps * (6 * S * 4 + 9 * 512), feas / max(steps, 1), steps
+
+
 class ClockSampler:
     """ONE nvidia-smi process (started by rank 0) samples every GPU of the job: 8 ranks each polling NVML at 50 ms
     measurably stall each other's launches on an 8-GPU box."""
@@ -119,26 +170,36 @@ class ClockSampler:
 
 
 def run_reference(a):
-    """The reference's CPU implementation of the path, restated (oracle port), all host threads."""
+    """The reference's own CPU implementation of the path on the host cores: the patched reference (oracle/_ref, torch CPU,
+    all host threads, child process without CUDA) when the copy is present, else the numpy oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sample = a.ref_sample
-    for _ in range(a.warmup if a.warmup < 1 else 1):
-        cpu_port_rate(a.nodes, 16)
-    rates, T, cores, t_all = [], 0, 1, 0.0
-    for _ in range(a.steps):
-        r, cores, dt, T = cpu_port_rate(a.nodes, sample)
-        rates.append(r); t_all += dt
-    v = float(np.mean(rates))
+    from oracle import ref_shim
+    kind, note = "port", "numpy oracle port of the reference path (oracle/_ref absent)"
+    if ref_shim.available():
+        try:
+            r = reference_child("greedy", a.nodes, sample, a.steps, cuda=False)
+            v, T, cores, t_all, kind = r["value"], r["decode_steps"], r["threads"], r["seconds"], "reference"
+            note = "patched reference (oracle/_ref: EM-EVRP nets/DRLModel.py + problems/EVRP.py, torch CPU), actor.forward(batch)"
+        except Exception as ex:
+            note = f"numpy oracle port (reference child failed: {type(ex).__name__}: {ex})"
+    if kind == "port":
+        for _ in range(a.warmup if a.warmup < 1 else 1):
+            cpu_port_rate(a.nodes, 16)
+        rates, T, cores, t_all = [], 0, 1, 0.0
+        for _ in range(a.steps):
+            r, cores, dt, T = cpu_port_rate(a.nodes, sample)
+            rates.append(r); t_all += dt
+        v = float(np.mean(rates))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1e3 * t_all / a.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": min(a.warmup, 1), "ms_per_step": 1e3 * t_all / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"EM-EVRP-{a.nodes} greedy rollout, random-init attention policy (BASELINE configs[3])",
                        "per_step_instances": sample, "nodes": a.nodes, "stations": 5, "decode_steps": T},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{sample} instances per step x {a.steps} steps (numpy oracle port of the "
-                                       f"reference path; the Python reference itself cannot travel to the GPU box)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{sample} instances per step x {a.steps} steps; {note}"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _emit(line)
@@ -161,8 +222,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=8192, help="instances per GPU per step (BASELINE configs[3])")
     ap.add_argument("--nodes", type=int, default=100)
-    ap.add_argument("--cpu-sample", type=int, default=512)
-    ap.add_argument("--ref-sample", type=int, default=512)
+    ap.add_argument("--cpu-sample", type=int, default=256)
+    ap.add_argument("--ref-sample", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-steps", type=int, default=3, help="timed REINFORCE steps (0 = skip)")
     ap.add_argument("--train-batch", type=int, default=1024)
@@ -269,6 +330,40 @@ def main():
     e2e_s = time.perf_counter() - te0
     h2d = st_h.numel() * 4 + dy_h.numel() * 4
     d2h = cost.numel() * 4 + pi_host.numel() * 8
+    # ---------------- bytes the rollout launch needs: one untimed traced rollout of the same (deterministic) batch ------
+    with torch.no_grad():
+        emb, kvl, fixed = model.encode(st, dy)
+        o_tr = model.rollout(emb, kvl, fixed, dy, D, G, save_trace=True)
+    need_b, mean_feasible, steps_tr = needed_bytes(o_tr, S)
+    assert steps_tr * a.steps == inst_steps, "traced rollout differs from the timed ones"
+    del o_tr, emb, kvl, fixed
+    # ---------------- strong scaling (BASELINE configs[3] as stated): ONE global batch of `B` sharded B/N per rank ------
+    strong = None
+    if world > 1:
+        gs, gd, ge = synth(B, N, seed=1000)                          # the same global batch on every rank
+        lo, hi = rank * B // world, (rank + 1) * B // world
+        sst, sdy = torch.from_numpy(gs[lo:hi]).to(dev), torch.from_numpy(gd[lo:hi]).to(dev)
+        sD, sG = evrp_b200.policy_math.pairwise_matrices(sst, torch.from_numpy(ge[lo:hi]).to(dev))
+
+        def step_strong():
+            with torch.no_grad():
+                e_, k_, f_ = model.encode(sst, sdy)
+                return model.rollout(e_, k_, f_, sdy, sD, sG)
+        for _ in range(3):
+            step_strong()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(a.steps):
+            step_strong()
+        s1.record()
+        barrier()
+        sms = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        strong = {"global_batch": B, "per_gpu_batch": hi - lo, "ms_per_step": sms.item() / a.steps,
+                  "value": B * a.steps / (sms.item() * 1e-3), "unit": UNIT, "scaling": "strong",
+                  "note": "the same instances/s metric on ONE global batch sharded over the ranks (device-timed, max over ranks)"}
+        del sst, sdy, sD, sG
     tm = torch.tensor([ms_total, e2e_s * 1e3, float(np.mean(roll_ms)), float(inst_steps)], dtype=torch.float64, device=dev)
     per_rank = None
     if world > 1:
@@ -304,20 +399,36 @@ def main():
         tsec = torch.tensor([time.perf_counter() - tt0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
+        # the rollout kernel inside the step (sampling, trace recorded): needed bytes / its CUDA-event time
+        tm_model.profile_events = []
+        with torch.no_grad():
+            te, tk, tf = tm_model.encode(tbatch[0], tbatch[1])
+            to = tm_model.rollout(te, tk, tf, tbatch[1], tbatch[2], tbatch[3], save_trace=True)
+        torch.cuda.synchronize()
+        t_roll_ms = tm_model.profile_events[-1][0].elapsed_time(tm_model.profile_events[-1][1])
+        tm_model.profile_events = None
+        t_need, _, _ = needed_bytes(to, S)
+        del te, tk, tf, to
         train = {"metric": "REINFORCE train step/sec (EM-EVRP-100)", "value": a.train_steps / tsec.item(),
+                 "roofline": {"bound": "hbm", "kernel": "evrp::dtc::rollout_tc_kernel (sampling, trace recorded)",
+                              "achieved": t_need / (t_roll_ms * 1e-3) / 1e9, "unit": "GB/s", "kernel_ms": t_roll_ms,
+                              "kernel_share_of_step": t_roll_ms / (1e3 * tsec.item() / a.train_steps),
+                              "needed_bytes_per_launch": t_need},
                  "unit": "step/s", "per_gpu_batch": tb, "global_batch": tb * world, "decode_steps": int(out["T"]),
                  "includes": "train-mode encoder (attention core on evrp_attn_train.cu, projections / FF / BatchNorm through "
                              "autograd) + sampled rollout kernel + decoder log-prob forward / backward kernels "
                              "(evrp_logp.cu) + fused loss kernel + flat NCCL gradient all-reduce + clip + Adam"}
     if rank == 0:
         pk, pk_src = peaks()
-        a_step = 1568 * S + 2048                                   # SURVEY §8d algorithmic bytes per instance-step
-        alg_bytes_per_launch = a_step * (inst_steps / a.steps)     # this rank's launch
-        achieved = alg_bytes_per_launch / (roll_avg_ms * 1e-3) / 1e9
-        traffic = None
+        kern_s = roll_avg_ms * 1e-3
+        achieved = need_b / kern_s / 1e9                               # needed bytes of this rank's launch
+        allnode = (1568 * S + 2048) * (inst_steps / a.steps)           # SURVEY §8d all-node model, same launch
+        traffic, traffic_src = None, "no ncu capture of this build / batch / graph size under profiles/rollout_traffic.json"
         try:
             with open(os.path.join(ROOT, "profiles", "rollout_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            if tj.get("lib_sha256") == lib_sha256() and tj.get("batch") == B and tj.get("nodes") == N:
+                traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         except Exception:
             pass
         line = {"metric": METRIC, "value": world * B * a.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -326,49 +437,93 @@ def main():
                 "config": {"workload": f"EM-EVRP-{N} greedy rollout, random-init attention policy (BASELINE configs[3])",
                            "per_gpu_batch": B, "global_batch": B * world, "nodes": N, "stations": F,
                            "decode_steps": T, "mean_steps_per_instance": inst_steps / (a.steps * B),
+                           "mean_feasible_nodes_per_step": mean_feasible,
                            "l2": "inputs_exceed_l2 (distances+slope+kvl = %.0f MB per step)" % ((2 * S * S + 384 * S) * 4 * B / 1e6),
                            "parallelism": f"dp{world} (instances sharded, no data-path collective)"},
                 "e2e": {"value": world * B * a.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h},
-                "gpu_launches": a.steps * (1 + 5 * 3 + 2 + 1),      # init embed, 3 x (QKV, attention, Wo, FF1, FF2), node projection + fixed context, rollout
+                        "d2h_bytes_per_step": d2h,
+                        "note": "static / dynamic from pinned host memory, tours + costs back to pinned host memory; distances / "
+                                "slope stay device-resident exactly as the reference's dataset keeps them (problems/EVRP.py:87-92)"},
+                "gpu_launches": a.steps * 3,                        # fused encoder kernel, fixed-context kernel, rollout kernel
                 "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "evrp::dtc::rollout_tc_kernel", "achieved": achieved,
                              "peak": pk["hbm_gbs"], "peak_source": pk_src, "unit": "GB/s",
-                             "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
-                             "dram_achieved": (traffic / (roll_avg_ms * 1e-3) / 1e9) if traffic else None,
+                             "frac": achieved / pk["hbm_gbs"], "bytes": "needed (feasible nodes only), counted live",
+                             "needed_bytes_per_launch": need_b, "traffic": traffic, "traffic_source": traffic_src,
+                             "dram_achieved": (traffic / kern_s / 1e9) if traffic else None,
                              "kernel_ms": roll_avg_ms, "kernel_share_of_step": roll_avg_ms / (ms_total / a.steps),
-                             "algorithmic_bytes_per_launch": alg_bytes_per_launch}}
-        f_enc = (1278720 * S + 1536 * S * S + 32768) * B               # SURVEY §8d algorithmic encoder FLOPs per launch set
+                             "allnode_bytes_per_launch": allnode, "allnode_over_peak": allnode / kern_s / 1e9 / pk["hbm_gbs"],
+                             "allnode_note": "SURVEY §8d's streaming model counts all S nodes per step; the kernel reads the "
+                                             "feasible ones only, so this ratio is NOT a fraction of peak"}}
+        f_enc = (1278720 * S + 1536 * S * S + 32768) * B               # SURVEY §8d algorithmic encoder FLOPs per launch
         enc_s = float(np.mean(enc_ms)) * 1e-3
-        tf32_peak = pk["bf16_tflops"] / 2.0                            # kind::tf32 runs at half the bf16 rate
-        line["roofline_encoder"] = {"bound": "tensor", "kernels": "init_embed + 3 x (QKV gemm, attention, Wo gemm, FF1, FF2) "
-                                    "+ node projection + fixed context", "achieved": f_enc / enc_s / 1e12,
-                                    "executed": 3 * f_enc / enc_s / 1e12, "peak": tf32_peak, "peak_source": pk_src + " bf16 / 2",
-                                    "unit": "TFLOP/s", "frac": f_enc / enc_s / 1e12 / tf32_peak,
-                                    "frac_executed": 3 * f_enc / enc_s / 1e12 / tf32_peak, "ms": enc_s * 1e3,
-                                    "note": "every product is a 3-MMA error-compensated split (fp32-faithful): executed = 3 x "
-                                            "algorithmic; per-kernel tensor-pipe activity by ncu: profiles/r1_tcgemm_ncu.md"}
+        f16_peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])  # kind::f16 = the bf16 rate; timed inside a long step
+        line["roofline_encoder"] = {"bound": "tensor", "kernels": "evrp::fenc::encoder_fused_kernel (init embedding, 3 layers, node "
+                                    "projection; one launch) + fixed_context_kernel", "achieved": f_enc / enc_s / 1e12,
+                                    "executed": 3 * f_enc / enc_s / 1e12, "peak": f16_peak,
+                                    "peak_source": pk_src + (" bf16 sustained" if "bf16_tflops_sustained" in pk else " bf16"),
+                                    "unit": "TFLOP/s", "frac": f_enc / enc_s / 1e12 / f16_peak,
+                                    "frac_executed": 3 * f_enc / enc_s / 1e12 / f16_peak, "ms": enc_s * 1e3,
+                                    "note": "every product is a 3-MMA fp16-pair split (fp32-faithful): executed = 3 x algorithmic "
+                                            "(padding of the 128-row tiles not counted); tensor-pipe activity by ncu: profiles/"}
         line["breakdown"] = {"encoder_ms": float(np.mean(enc_ms)), "rollout_kernel_ms": float(np.mean(roll_ms)),
                              "note": "rank 0, CUDA events inside the timed region"}
         if per_rank is not None:
             line["per_rank"] = per_rank
+        if strong is not None:
+            strong["efficiency_vs_weak"] = strong["value"] / line["value"]
+            line["strong"] = strong
         if train is not None:
+            train["roofline"]["peak"] = pk["hbm_gbs"]
+            train["roofline"]["frac"] = train["roofline"]["achieved"] / pk["hbm_gbs"]
             line["train"] = train
         if world == 1 and not a.no_cpu_baseline:
-            # a clean child process (no CUDA context, no torch thread pools competing with numpy's BLAS threads)
+            # clean child processes (no CUDA context, no torch thread pools competing with the BLAS threads)
             try:
                 out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2",
                                       "--warmup", "1", "--nodes", str(N), "--ref-sample", str(a.cpu_sample)],
-                                     capture_output=True, text=True, timeout=900).stdout.strip().splitlines()[-1]
+                                     capture_output=True, text=True, timeout=1500).stdout.strip().splitlines()[-1]
                 ref = json.loads(out)
                 line["cpu_baseline"] = {"value": ref["value"], "unit": UNIT, "cores": ref["cpu_baseline"]["cores"],
-                                        "kind": "port", "sample": f"2 x {a.cpu_sample} EM-EVRP-{N} instances, greedy, numpy "
-                                        f"oracle port, {2 * ref['ms_per_step'] / 1e3:.1f} s (child process)"}
-            except Exception as ex:                                   # fall back to timing in this process
+                                        "kind": ref["cpu_baseline"]["kind"],
+                                        "sample": f"2 x {a.cpu_sample} EM-EVRP-{N} instances, greedy, "
+                                        f"{2 * ref['ms_per_step'] / 1e3:.1f} s (child process); " + ref["cpu_baseline"]["sample"]}
+            except Exception as ex:                                   # fall back to timing the numpy port in this process
                 r, cores, dt, Tc = cpu_port_rate(N, a.cpu_sample)
                 line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
                                         "sample": f"{a.cpu_sample} EM-EVRP-{N} instances, greedy, numpy oracle port, "
                                                   f"{dt:.1f} s (in-process: {type(ex).__name__})"}
+            # config 1 of BASELINE.json, the reference's own CPU-runnable case: EM-EVRP-20, batch 256, greedy
+            from oracle import ref_shim
+            if ref_shim.available():
+                try:
+                    r = reference_child("greedy", 20, 256, 2, cuda=False)
+                    line["cpu_config1"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "reference",
+                                           "sample": "EM-EVRP-20, batch 256, greedy, 2 forwards (BASELINE configs[0])"}
+                except Exception as ex:
+                    line["cpu_config1"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
+                # the reference as eager PyTorch on this B200: GPU-vs-GPU context for the headline
+                try:
+                    r = reference_child("greedy", N, 512, 1, cuda=True)
+                    line["reference_gpu"] = {"value": r["value"], "unit": UNIT, "batch": 512, "seconds": r["seconds"],
+                                             "decode_steps": r["decode_steps"], "device": r["device"],
+                                             "what": "patched reference, eager PyTorch CUDA, actor.forward(batch), time.time() "
+                                                     "around the call as trainer.py:430-453"}
+                except Exception as ex:
+                    line["reference_gpu"] = {"unavailable": f"{type(ex).__name__}: {ex}"}
+                if train is not None:
+                    try:
+                        r = reference_child("train", N, 128, 1, cuda=False)
+                        train["cpu_baseline"] = {"value": r["value"], "unit": "step/s", "batch": 128, "cores": r["threads"],
+                                                 "kind": "reference", "equiv_step_per_s_at_batch_%d" % a.train_batch:
+                                                 r["value"] * 128 / a.train_batch,
+                                                 "sample": "patched reference REINFORCE step (trainer.py:112-127), EM-EVRP-%d, batch "
+                                                           "128, 1 step after 1 warm-up, torch CPU" % N}
+                        r = reference_child("train", N, a.train_batch, 2, cuda=True)
+                        train["reference_gpu"] = {"value": r["value"], "unit": "step/s", "batch": a.train_batch,
+                                                  "what": "patched reference REINFORCE step, eager PyTorch CUDA"}
+                    except Exception as ex:
+                        train["cpu_baseline"] = train.get("cpu_baseline") or {"unavailable": f"{type(ex).__name__}: {ex}"}
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
