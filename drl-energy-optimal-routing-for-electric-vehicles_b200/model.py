@@ -154,7 +154,7 @@ class AttentionModel(nn.Module):
         owner = getattr(self.update_dynamic, "__self__", None)
         if owner is not None and getattr(owner, "_evrp_b200_native", False):
             return _lib.make_phys(float(owner.velocity), float(owner.Start_SOC), float(owner.t_limit),
-                                  owner.max_load, owner.objective)
+                                  owner.max_load, owner.objective, div_mode=int(getattr(owner, "div_mode", 0)))
         return _lib.make_phys(self.velocity, float(self.start_soc), float(self.t_limit), self.max_load, self.objective)
 
     def packed_weights(self):

@@ -178,9 +178,14 @@ class VehicleRoutingDataset(Dataset):
         return (self.static[idx], self.dynamic[idx], self.Elevation[idx])
 
     # ------------------------------------------------------------------------------------------
+    # x / python-scalar convention of the state recipe: 0 = IEEE division (what ATen evaluates on the CPU,
+    # pinned by the golden fixtures), 1 = multiplication by fl(1 / scalar); tests/test_reference_gpu.py records which of
+    # the two the reference's CUDA run follows
+    div_mode = 0
+
     def _phys(self):
         return _lib.make_phys(float(self.velocity), float(self.Start_SOC), float(self.t_limit), self.max_load,
-                              self.objective)
+                              self.objective, div_mode=int(self.div_mode))
 
     @staticmethod
     def _cuda(t, dtype):
