@@ -127,6 +127,86 @@ def needed_bytes(o, S):
     return feas * 1536 + steps * (6 * S * 4 + 9 * 512), feas / max(steps, 1), steps
 
 
+def multi_rank_gradient_check(evrp_b200, model, inst, rank, world, dev):
+    """(N > 1) the data-parallel training path against a single-rank recompute: a 256-instance batch is sampled once
+    (rank 0, actions broadcast), every rank takes the REINFORCE gradient of ITS shard teacher-forced on those actions
+    (global-batch BatchNorm statistics + flat gradient all-reduce), rank 0 repeats the step on the whole batch alone.
+    Also: the BatchNorm running statistics and a RolloutBaseline.epoch_callback (CPU statistics through NCCL) agree
+    on every rank."""
+    import torch
+    import torch.distributed as dist
+    from evrp_b200 import policy_math as PM, train as Tr
+    s, d, e = inst
+    st, dy = torch.from_numpy(s).to(dev), torch.from_numpy(d).to(dev)
+    D, G = PM.pairwise_matrices(st, torch.from_numpy(e).to(dev))
+    n = st.shape[0]
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    model.train(); model.set_decode_type("sample")
+    with torch.no_grad(), PM.local_batch_norm():
+        pi, _, _ = model((st, dy, D, G))
+    pi = pi.contiguous()
+    model.load_state_dict(state)
+    tw = torch.tensor([pi.shape[1]], device=dev); dist.broadcast(tw, 0)
+    if rank != 0:
+        pi = torch.zeros(n, int(tw.item()), dtype=torch.int64, device=dev)
+    dist.broadcast(pi, 0)
+    params = [p for p in model.parameters()]
+
+    def grads(lo, hi, local):
+        model.load_state_dict(state)
+        model.zero_grad()
+        if local:
+            with PM.local_batch_norm():
+                _, ll, R = model((st[lo:hi], dy[lo:hi], D[lo:hi], G[lo:hi]), forced_actions=pi[lo:hi])
+        else:
+            _, ll, R = model((st[lo:hi], dy[lo:hi], D[lo:hi], G[lo:hi]), forced_actions=pi[lo:hi])
+        ((R.sum(1) - 4000.0).detach() * ll.sum(1)).sum().div(n).backward()
+        if not local:
+            Tr.allreduce_gradients(params)
+        return torch.cat([p.grad.reshape(-1) for p in params]).clone(), \
+            torch.cat([b.reshape(-1).float() for k, b in model.state_dict().items() if "running" in k]).clone()
+    lo, hi = rank * n // world, (rank + 1) * n // world
+    g_multi, bn_multi = grads(lo, hi, False)
+    out = None
+    bn_all = [torch.zeros_like(bn_multi) for _ in range(world)]
+    dist.all_gather(bn_all, bn_multi)
+    if rank == 0:
+        g_single, bn_single = grads(0, n, True)
+        g_again, _ = grads(0, n, True)                      # run-to-run floor of the single-rank step (fp32 atomics)
+        worst, off, gmax = ("", 0.0), 0, float(g_single.abs().max())
+        for name, p_ in model.named_parameters():
+            k = p_.numel()
+            e_ = float((g_multi[off:off + k] - g_single[off:off + k]).abs().max()) / gmax
+            if e_ > worst[1]:
+                worst = (name, e_)
+            off += k
+        out = {"batch": n, "grad_rel_err": float((g_multi - g_single).abs().max() / g_single.abs().max()),
+               "single_rank_repeat_rel_err": float((g_again - g_single).abs().max() / g_single.abs().max()),
+               "worst_parameter": {"name": worst[0], "max_abs_err_over_global_max": worst[1]},
+               "grad_l2_rel_err": float((g_multi - g_single).norm() / g_single.norm()),
+               "bn_running_stats_max_diff_across_ranks": float(max((b - bn_all[0]).abs().max() for b in bn_all)),
+               "bn_running_stats_vs_single_rank": float((bn_multi - bn_single).abs().max())}
+    model.load_state_dict(state)
+    # the rollout baseline's statistics pass through numpy (CPU tensors) before the NCCL reductions
+    model.eval()
+    class _DS(torch.utils.data.Dataset):
+        def __len__(self): return hi - lo
+        def __getitem__(self, i): return (st[lo + i], dy[lo + i], D[lo + i], G[lo + i])
+    import types as _t
+    bl = Tr.RolloutBaseline(model, _DS(), _t.SimpleNamespace(batch_size=64, bl_alpha=0.05))
+    bl.epoch_callback(model, 1)
+    m_all = torch.tensor([bl.mean], dtype=torch.float64, device=dev)
+    ms = [torch.zeros_like(m_all) for _ in range(world)]
+    dist.all_gather(ms, m_all)
+    if rank == 0:
+        out["rollout_baseline_mean_agrees"] = bool(all(float(x) == float(ms[0]) for x in ms))
+        out["tolerance"] = "1e-3 of the largest gradient entry (north-star gradient bar); the two paths differ by GEMM tile / reduction order, the single-rank step repeats to single_rank_repeat_rel_err"
+        out["ok"] = bool(out["grad_rel_err"] < 1e-3 and out["bn_running_stats_max_diff_across_ranks"] == 0.0
+                         and out["rollout_baseline_mean_agrees"])
+    model.train(); model.set_decode_type("sample")
+    return out
+
+
 class ClockSampler:
     """ONE nvidia-smi process (started by rank 0) samples every GPU of the job: 8 ranks each polling NVML at 50 ms
     measurably stall each other's launches on an 8-GPU box."""
@@ -409,7 +489,11 @@ def main():
         tm_model.profile_events = None
         t_need, _, _ = needed_bytes(to, S)
         del te, tk, tf, to
+        grad_check = None
+        if world > 1:
+            grad_check = multi_rank_gradient_check(evrp_b200, tm_model, synth(256, N, seed=77), rank, world, dev)
         train = {"metric": "REINFORCE train step/sec (EM-EVRP-100)", "value": a.train_steps / tsec.item(),
+                 "grad_check": grad_check,
                  "roofline": {"bound": "hbm", "kernel": "evrp::dtc::rollout_tc_kernel (sampling, trace recorded)",
                               "achieved": t_need / (t_roll_ms * 1e-3) / 1e9, "unit": "GB/s", "kernel_ms": t_roll_ms,
                               "kernel_share_of_step": t_roll_ms / (1e3 * tsec.item() / a.train_steps),

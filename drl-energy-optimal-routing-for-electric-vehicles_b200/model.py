@@ -108,7 +108,7 @@ class AttentionModel(nn.Module):
         self._pack_cache = None
         self._enc_ws = None
         self.max_steps = 1000                     # nets/DRLModel.py:255
-        self.sample_seed = 0
+        self.sample_seed = None                   # None: derived from torch.initial_seed() and the rank at the first rollout
         self._calls = 0
         self.last_energy = None                   # [B,T] energy of the last rollout (DM trainer's 3rd output)
         self.gemm_mode = 2                        # encoder: 2 = ONE fused tcgen05 kernel (fp16-pair split), 0 = per-sub-layer tcgen05 3xTF32 launches, 1 = fp32 FFMA
@@ -138,6 +138,46 @@ class AttentionModel(nn.Module):
 
     def _device(self):
         return self.project_out.weight.device
+
+    # ---- counter-based sampler of the rollout kernel: seed from torch's seed and the data-parallel rank, so that
+    # torch.manual_seed / args.seed steer the sampled actions and ranks draw different streams; part of the checkpoint
+    def _sampler_seed(self):
+        if self.sample_seed is None:
+            import torch.distributed as dist
+            rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+            self.sample_seed = (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + 0xD1B54A32D192ED03 * (rank + 1)) & 0xFFFFFFFFFFFFFFFF
+        return self.sample_seed
+
+    def sampler_state(self):
+        return {"sample_seed": self._sampler_seed(), "calls": self._calls}
+
+    def load_sampler_state(self, st):
+        self.sample_seed, self._calls = int(st["sample_seed"]), int(st["calls"])
+
+    # ---- the packed-weight cache holds ctypes structures with device pointers: never copied or pickled with the module
+    _TRANSIENT = ("_pack_cache", "_enc_ws", "_tensor_list", "profile_events")
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        for k in self._TRANSIENT:
+            if k in st:
+                st[k] = None
+        return st
+
+    def __deepcopy__(self, memo):
+        import copy
+        saved = {k: self.__dict__.get(k) for k in self._TRANSIENT}
+        for k in self._TRANSIENT:
+            self.__dict__[k] = None
+        try:
+            cls = self.__class__
+            new = cls.__new__(cls)
+            memo[id(self)] = new
+            for k, v in self.__dict__.items():
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        finally:
+            self.__dict__.update(saved)
+        return new
 
     def _fused_path_ok(self):
         """The fused kernel is legal only when the injected callbacks are ours (or absent)."""
@@ -235,7 +275,7 @@ class AttentionModel(nn.Module):
         while True:
             cfg = _lib.RolloutCfg(_lib.DECODE_SAMPLE if decode_type == "sample" else _lib.DECODE_GREEDY,
                                   float(self.temp), float(self.tanh_clipping), tcap,
-                                  (self.sample_seed * 0x9E3779B1 + self._calls) & 0xFFFFFFFFFFFFFFFF, n_replicas)
+                                  (self._sampler_seed() + 0x9E3779B1 * self._calls) & 0xFFFFFFFFFFFFFFFF, n_replicas)
             pi = torch.zeros(rows, tcap, dtype=torch.int64, device=dev)
             ll = torch.zeros(rows, tcap, device=dev)
             R = torch.zeros(rows, tcap, device=dev)

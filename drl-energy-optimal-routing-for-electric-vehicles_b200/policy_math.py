@@ -254,9 +254,24 @@ class _GlobalBatchNorm(torch.autograd.Function):
         return gx, gw, gb, None
 
 
+_LOCAL_BN = [False]
+
+
+class local_batch_norm:
+    """context: BatchNorm statistics of THIS rank's rows only even inside a process group (bench.py's single-rank
+    recompute of the multi-rank gradients)"""
+
+    def __enter__(self):
+        _LOCAL_BN[0] = True
+
+    def __exit__(self, *a):
+        _LOCAL_BN[0] = False
+
+
 def _batch_norm(bn, x, training, force_global=False):
     import torch.distributed as dist
-    if training and dist.is_available() and dist.is_initialized() and (dist.get_world_size() > 1 or force_global):
+    if training and not _LOCAL_BN[0] and dist.is_available() and dist.is_initialized() and \
+            (dist.get_world_size() > 1 or force_global):
         if x.is_cuda:
             # CUDA: the same global-batch statistics through PyTorch's fused synchronized-BatchNorm kernels
             # (batch_norm_stats / gather_stats_with_counts / elemt / backward_reduce / backward_elemt): one all-gather

@@ -42,10 +42,28 @@ def shard_bounds(n, rank=None, world_size=None):
 
 
 def allreduce_sum_(t):
+    """in-place sum over ranks.  NCCL reduces device tensors only: a CPU tensor (baseline statistics that went through
+    numpy) is staged on this rank's GPU and copied back."""
     r, w = world()
     if w > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if not t.is_cuda and dist.get_backend() == "nccl":
+            d = t.to(torch.device("cuda", torch.cuda.current_device()))
+            dist.all_reduce(d, op=dist.ReduceOp.SUM)
+            t.copy_(d)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
+
+
+def allreduce_min_int(v):
+    """min over ranks of a Python int (same staging rule)"""
+    r, w = world()
+    if w == 1:
+        return int(v)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([int(v)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return int(t.item())
 
 
 def global_mean(x):
@@ -340,7 +358,9 @@ def checkpoint_state(actor, optimizer, baseline):
     """the reference's checkpoint dictionary, key for key (trainer.py:160-169)"""
     return {'model': actor.state_dict(), 'optimizer': optimizer.state_dict(), 'rng_state': torch.get_rng_state(),
             'cuda_rng_state': torch.cuda.get_rng_state_all() if torch.cuda.is_available() else [],
-            'baseline': baseline.state_dict()}
+            'baseline': baseline.state_dict(),
+            # not in the reference's dictionary (it ignores unknown keys): the counter-based sampler of the rollout kernel
+            'sampler_state': actor.sampler_state() if hasattr(actor, "sampler_state") else None}
 
 
 def load_checkpoint(path, actor, optimizer=None, baseline=None, map_location=None):
@@ -351,6 +371,10 @@ def load_checkpoint(path, actor, optimizer=None, baseline=None, map_location=Non
         optimizer.load_state_dict(ck['optimizer'])
     if 'rng_state' in ck:
         torch.set_rng_state(ck['rng_state'].cpu() if hasattr(ck['rng_state'], "cpu") else ck['rng_state'])
+    if ck.get('cuda_rng_state') and torch.cuda.is_available() and len(ck['cuda_rng_state']) == torch.cuda.device_count():
+        torch.cuda.set_rng_state_all([t.cpu() for t in ck['cuda_rng_state']])
+    if ck.get('sampler_state') is not None and hasattr(actor, "load_sampler_state"):
+        actor.load_sampler_state(ck['sampler_state'])
     if baseline is not None and 'baseline' in ck:
         baseline.load_state_dict(ck['baseline'])
     return ck
@@ -363,10 +387,16 @@ def train_epoch(actor, baseline, optimizer, train_data, batch_size, max_grad_nor
     ``batch_size`` is the PER-RANK batch.  Returns (mean reward, mean loss, steps)."""
     data = baseline.wrap_dataset(rank_shard(train_data))
     loader = DataLoader(data, batch_size, shuffle, num_workers=0)
+    # every REINFORCE step issues collectives (global batch size, BatchNorm statistics, gradient all-reduce): all ranks must
+    # take the SAME number of steps.  Shards differ by at most one instance, so the batch counts can differ by one: stop at
+    # the minimum over ranks (the surplus instances of the longer shards sit out this epoch; shuffling rotates them)
+    n_steps = allreduce_min_int(len(loader))
     actor.train()
     actor.set_decode_type("sample")
     rewards, losses = [], []
     for batch_idx, batch in enumerate(loader):
+        if batch_idx >= n_steps:
+            break
         out = reinforce_step(actor, baseline, optimizer, batch, max_grad_norm)
         rewards.append(float(out["reward"]))
         losses.append(float(out["loss"]))
