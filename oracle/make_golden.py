@@ -201,6 +201,79 @@ def am_fixture(name, N, B, seed=12345):
     print(name, "T=", pi.shape[1], "mean cost", float(R.sum(1).mean()), "sampled T=", spi.shape[1])
 
 
+def greedy_lite_fixture(name, N, B, seed):
+    """many instances at one size, without the per-step state / log-prob trace: inputs, tours, log-likelihoods, rewards
+    and the per-step masks (bit-packed)"""
+    ds, args = ref_shim.make_dataset(B, N, seed)
+    m = ref_shim.make_model(ds, args, 0)
+    m.eval(); m.set_decode_type("greedy")
+    bat = batch_of(ds, B)
+    tr = Tracer(m)
+    with torch.no_grad():
+        pi, ll, R = m(bat)
+    tr.close()
+    d = inputs_dict(ds, bat, B)
+    d.update(pi=pi.numpy(), ll=ll.numpy(), R=R.numpy(), bn_perturbed=np.array(False),
+             t_mask_packed=np.packbits(tr.arrays()["t_mask"].astype(bool), axis=-1), n_nodes=np.array(N + 6))
+    np.savez_compressed(os.path.join(OUT, name), **d)
+    print(name, "T=", pi.shape[1], "mean cost", float(R.sum(1).mean()))
+
+
+def sample_trace_fixture(name, N, B, seed, torch_seed):
+    """SAMPLED rollout of the reference (torch.multinomial stream of `torch_seed`) with the full per-step trace"""
+    ds, args = ref_shim.make_dataset(B, N, seed)
+    m = ref_shim.make_model(ds, args, 0)
+    m.eval(); m.set_decode_type("sample")
+    bat = batch_of(ds, B)
+    tr = Tracer(m)
+    torch.manual_seed(torch_seed)
+    with torch.no_grad():
+        pi, ll, R = m(bat)
+    tr.close()
+    d = inputs_dict(ds, bat, B)
+    d.update(pi=pi.numpy(), ll=ll.numpy(), R=R.numpy(), bn_perturbed=np.array(False), **tr.arrays())
+    np.savez_compressed(os.path.join(OUT, name), **d)
+    print(name, "T=", pi.shape[1], "mean cost", float(R.sum(1).mean()))
+
+
+GRAD_STRIDE = 4
+
+
+def grad_fixture(name, N, B, seed, torch_seed):
+    """REINFORCE gradients at a large graph size (eval- and train-mode BatchNorm) teacher-forced on a sampled rollout.
+    To keep the file small every gradient is stored as its flattened entries [::GRAD_STRIDE] plus its L2 norm."""
+    ds, args = ref_shim.make_dataset(B, N, seed)
+    m = ref_shim.make_model(ds, args, 0)
+    m.load_state_dict(perturb_bn(m.state_dict()))
+    bat = batch_of(ds, B)
+    m.eval(); m.set_decode_type("sample")
+    torch.manual_seed(torch_seed)
+    with torch.no_grad():
+        pi, ll0, R = m(bat)
+    cost = R.sum(1)
+    adv = (cost - cost.mean()).detach()
+    d = inputs_dict(ds, bat, B)
+    d.update(pi=pi.numpy(), R=R.numpy(), adv=adv.numpy(), stride=np.array(GRAD_STRIDE))
+    for mode in ("eval", "train"):
+        m.train(mode == "train")
+        ll, R2, loss, g = teacher_forced_grads(m, bat, pi, adv)
+        assert torch.equal(R2, R)
+        d["ll_" + mode], d["loss_" + mode] = ll.numpy(), np.array(loss)
+        for k, v in g.items():
+            d[f"g_{mode}/" + k] = v.reshape(-1)[::GRAD_STRIDE].numpy().copy()
+            d[f"n_{mode}/" + k] = np.array(float(v.norm()))
+    d.update({"bn_after/" + k: v.numpy() for k, v in m.state_dict().items() if "running" in k or "tracked" in k})
+    np.savez_compressed(os.path.join(OUT, name), **d)
+    print(name, "T=", pi.shape[1], "loss eval/train", float(d["loss_eval"]), float(d["loss_train"]))
+
+
+def main_round2():
+    """fixtures added in round 2 (the round-1 files are left byte-identical)"""
+    greedy_lite_fixture("greedy_n100_64.npz", 100, 64, seed=54321)
+    sample_trace_fixture("sample_n50.npz", 50, 8, seed=4711, torch_seed=5)
+    grad_fixture("sample_grad_n100.npz", 100, 12, seed=2025, torch_seed=7)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ds, args = ref_shim.make_dataset(2, 20, 1)
@@ -219,4 +292,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        main_round2()
+    else:
+        main()

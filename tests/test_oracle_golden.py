@@ -70,6 +70,31 @@ def test_free_running_greedy(weights, name):
         assert gap < 1e-4, f"instance {b} diverges at step {t} with log-prob gap {gap}"
 
 
+def unpack_masks(g):
+    return np.unpackbits(g["t_mask_packed"], axis=-1)[..., :int(g["n_nodes"])]
+
+
+def test_headline_size_64_instances(weights):
+    """round 2: 64 EM-EVRP-100 instances minted from the reference (tours, rewards, per-step masks): oracle teacher-forced
+    bit-exact, log-likelihoods 2e-5"""
+    g = load("greedy_n100_64.npz")
+    o = O.rollout(weights, g["static"], g["dynamic"], g["distances"], g["slope"], forced=g["pi"], trace=True)
+    assert np.array_equal(o["R"], g["R"])
+    assert np.array_equal(o["mask"].astype(np.uint8), unpack_masks(g))
+    assert np.abs(o["ll"] - g["ll"]).max() < LOGP_TOL
+
+
+def test_sampled_trace_n50(weights):
+    """round 2: a SAMPLED reference rollout at N = 50 with its full trace"""
+    g = load("sample_n50.npz")
+    o = O.rollout(weights, g["static"], g["dynamic"], g["distances"], g["slope"], forced=g["pi"], trace=True)
+    assert np.array_equal(o["dynamic"], g["t_dynamic"]) and np.array_equal(o["R"], g["R"])
+    assert np.array_equal(o["mask"].astype(np.uint8), g["t_mask"])
+    fin = np.isfinite(g["t_log_p"])
+    assert np.abs(o["log_p"][fin] - g["t_log_p"][fin]).max() < LOGP_TOL
+    assert np.abs(o["ll"] - g["ll"]).max() < LOGP_TOL
+
+
 def test_dm_objective(weights):
     g = load("dm_n20.npz")
     o = O.rollout(weights, g["static"], g["dynamic"], g["distances"], g["slope"], forced=g["pi"], objective="DM")
