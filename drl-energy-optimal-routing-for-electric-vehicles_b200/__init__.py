@@ -8,7 +8,7 @@ from . import _lib
 from ._lib import EvrpLibraryError, lib
 from .model import AttentionModel, AttentionModelAM
 from .problem import (EVRPDataset, VehicleRoutingDataset, load_dataset, parse_cvrplib, save_dataset,
-                      synthetic_instances)
+                      synthetic_instances, generate_instances)
 
-__all__ = ["AttentionModel", "AttentionModelAM", "VehicleRoutingDataset", "parse_cvrplib", "synthetic_instances", "save_dataset",
+__all__ = ["AttentionModel", "AttentionModelAM", "VehicleRoutingDataset", "parse_cvrplib", "synthetic_instances", "generate_instances", "save_dataset",
            "load_dataset", "EVRPDataset", "EvrpLibraryError", "lib"]

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EVRP_B200_LIB") or os.path.join(_HERE, "libevrp_b200.so")   # override: instrumented debug builds (tools/)
 
 EVRP_MAX_S = 128
-ABI_VERSION = 15
+ABI_VERSION = 16
 EVRP_MAX_LAYERS = 8
 ST_NAN_LOGIT, ST_INFEASIBLE_PICK, ST_STEP_CAP, ST_NONUNIFORM_DYNAMIC, ST_NO_FEASIBLE, ST_STUCK_AT_DEPOT = 1, 2, 4, 8, 16, 32
 DECODE_GREEDY, DECODE_SAMPLE = 0, 1
@@ -50,7 +50,8 @@ class DecoderWeights(C.Structure):
 
 class RolloutCfg(C.Structure):
     _fields_ = [("decode_type", C.c_int32), ("temp", C.c_float), ("tanh_clipping", C.c_float),
-                ("max_steps", C.c_int32), ("seed", C.c_uint64), ("n_replicas", C.c_int32)]
+                ("max_steps", C.c_int32), ("seed", C.c_uint64), ("n_replicas", C.c_int32),
+                ("static_xy", _FP), ("elevations", _FP)]
 
 
 # every symbol include/evrp_b200.h declares, with its ctypes signature
@@ -62,6 +63,8 @@ SIGNATURES = {
                                       _FP, _FP, _FP, _FP]),
     "evrp_update_mask": (C.c_int, [C.POINTER(Phys), _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, _FP, _FP, _FP]),
     "evrp_pairwise_build": (C.c_int, [_FP, _FP, C.c_int, C.c_int, _FP, _FP, _FP]),
+    "evrp_generate_instances": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
+                                          _FP, _FP, _FP, _FP]),
     "evrp_encoder_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "evrp_encoder_forward": (C.c_int, [C.POINTER(EncoderWeights), _FP, _FP, C.c_int, C.c_int, C.c_int,
                                        _FP, _FP, _FP, _FP, _FP, C.c_size_t, _FP]),

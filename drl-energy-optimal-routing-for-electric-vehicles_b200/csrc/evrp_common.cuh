@@ -134,6 +134,39 @@ static __device__ __noinline__ bool reachable_generic(const evrp_phys& p, int j,
   return reachable(p, j, F, load0, load_j, dem_j, soc_j, time_j, d0, g0, D0j, G0j, d3, s3, d4);
 }
 
+// Pairwise geometry of one instance.  Either the caller's [S,S] distance / slope matrices, or -- 3-tuple input
+// (static, dynamic, Elevations), nets/DRLModel.py:124-133 -- the coordinate and elevation rows themselves: the entries
+// are then recomputed where they are needed, with the op order of pairwise_build_kernel (evrp_step.cu), bit for bit:
+//   D[i,j] = sqrt((x_i - x_j)^2 + (y_i - y_j)^2)      G[i,j] = clamp((E_i - E_j) / (D[i,j] + 1e-6), -0.1, 0.1)
+// so that no [B,S,S] tensor (736 MB at B = 8192, N = 100) has to exist at all.
+template <bool COORDS>                   // compile-time: the matrix-mode kernels carry none of the recompute code
+struct Geo {
+  const float* D; const float* G;        // [S,S] of this instance, or nullptr
+  const float* x; const float* y; const float* e;   // [S] rows of this instance (coordinate mode)
+  int S;
+  __device__ __forceinline__ static constexpr bool coords() { return COORDS; }
+  __device__ __forceinline__ void pair(float xi, float yi, float ei, int j, float& d, float& g) const {
+    const float dx = __fsub_rn(xi, __ldg(x + j)), dy = __fsub_rn(yi, __ldg(y + j));
+    d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    g = fminf(fmaxf(__fdiv_rn(__fsub_rn(ei, __ldg(e + j)), __fadd_rn(d, 0.000001f)), -0.10f), 0.10f);
+  }
+  __device__ __forceinline__ void at(int i, int j, float& d, float& g) const {
+    if (coords()) pair(__ldg(x + i), __ldg(y + i), __ldg(e + i), j, d, g);
+    else { d = __ldg(D + (size_t)i * S + j); g = __ldg(G + (size_t)i * S + j); }
+  }
+};
+template <bool COORDS>
+__device__ __forceinline__ Geo<COORDS> make_geo(const float* Dm, const float* Gm, const float* xy, const float* elev, int inst, int S) {
+  Geo<COORDS> g;
+  g.S = S;
+  g.D = COORDS ? nullptr : Dm + (size_t)inst * S * S;
+  g.G = COORDS ? nullptr : Gm + (size_t)inst * S * S;
+  g.x = COORDS ? xy + (size_t)inst * 2 * S : nullptr;
+  g.y = COORDS ? xy + (size_t)inst * 2 * S + S : nullptr;
+  g.e = COORDS ? elev + (size_t)inst * S : nullptr;
+  return g;
+}
+
 // Counter-based RNG for sampling: splitmix64 finaliser over (seed, row, step) -> uniform in [0,1).
 __device__ __forceinline__ float uniform01(uint64_t seed, uint64_t row, uint32_t step) {
   uint64_t z = seed + 0x9E3779B97F4A7C15ull * (row * 1024ull + step + 1ull);

@@ -19,6 +19,7 @@
 //   4. state transition + look-ahead feasibility mask (bit-exact fp32 recipe), state in shared memory.
 // Rows retire individually; the host reads back only t_max and the status word.
 #include <math.h>
+#include <type_traits>
 #include "evrp_common.cuh"
 
 namespace evrp {
@@ -89,11 +90,12 @@ __device__ __forceinline__ T sel4(const T (&a)[4], int i) { return i == 0 ? a[0]
 // POLICY: 0 = the paper's model (route context through FF_tour, nets/DRLModel.py:203-237,394); 1 = nets/AM.py
 // (:336-337,352-377): query = fixed_ctx + project_step_context([emb[now], load]) -- no FF phase at all; `emb` is the
 // encoder's step table (emb @ project_step_context.weight[:, :128]^T), so the step context is one row read + one FMA
-template <int MODE, int POLICY>
+template <int MODE, int POLICY, bool COORDS>
 __global__ void __launch_bounds__(NT, 2)
 rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
                const float* __restrict__ emb, const float* __restrict__ kvl, const float* __restrict__ fixed_ctx,
                const float* __restrict__ dynamic0, const float* __restrict__ Dm, const float* __restrict__ Gm,
+                  const float* __restrict__ xyp, const float* __restrict__ elevp,
                float* station_ws, int B, int S, int F, int rows_total, int rows_per_cta,
                const int64_t* __restrict__ forced, const float* __restrict__ uniforms,
                int64_t* __restrict__ pi, float* __restrict__ ll, float* __restrict__ reward,
@@ -112,8 +114,7 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
     const int row = blockIdx.x * rows_per_cta + lr;
     const bool valid = (lr < rows_per_cta) && (row < rows_total);
     const int inst = valid ? row % B : 0;
-    const float* Db = Dm + (size_t)inst * S * S;
-    const float* Gb = Gm + (size_t)inst * S * S;
+    const Geo<COORDS> geo = make_geo<COORDS>(Dm, Gm, xyp, elevp, inst, S);
     const float* dy = dynamic0 + (size_t)inst * 4 * S;
     const float load = dy[0], soc = dy[2 * S], tim = dy[3 * S];
     bool nonuni = false;
@@ -126,13 +127,18 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       if (j < S) {
         dmv = dy[S + j];
         nonuni |= (dy[j] != load) || (dy[2 * S + j] != soc) || (dy[3 * S + j] != tim);
-        int k = 0; float best = Db[(size_t)1 * S + j];       // rule-7 constants (problems/EVRP.py:196-202)
-        for (int i = 1; i < F; ++i) { const float v = Db[(size_t)(1 + i) * S + j]; if (v < best) { best = v; k = i; } }
+        int k = 0; float best, gk, tmp;                     // rule-7 constants (problems/EVRP.py:196-202)
+        geo.at(1, j, best, gk);
+        for (int i = 1; i < F; ++i) { float v, gv; geo.at(1 + i, j, v, gv); if (v < best) { best = v; gk = gv; k = i; } }
+        float d0v, g0v;
+        geo.at(0, j, d0v, g0v);
         if (valid) {
-          station_ws[((size_t)inst * 2 + 0) * SP + j] = (j == 0) ? 0.f : best;
-          station_ws[((size_t)inst * 2 + 1) * SP + j] = Gb[(size_t)(1 + k) * S + j];
+          station_ws[((size_t)inst * 4 + 0) * SP + j] = (j == 0) ? 0.f : best;
+          station_ws[((size_t)inst * 4 + 1) * SP + j] = gk;
+          station_ws[((size_t)inst * 4 + 2) * SP + j] = d0v;       // D[0,:], G[0,:]: instance constants of the look-ahead
+          station_ws[((size_t)inst * 4 + 3) * SP + j] = g0v;
         }
-        if (j == 0) d4 = Db[(size_t)(1 + k) * S + 0];
+        if (j == 0) geo.at(1 + k, 0, d4, tmp);
       }
       sm.dem[lr][j] = dmv;
       mk[jb] = __ballot_sync(FULL, j < S);                     // mask = ones (:256)
@@ -287,8 +293,7 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       const int row = blockIdx.x * rows_per_cta + lr;
       const int inst = rs.inst;
       const int now = rs.now;
-      const float* Db = Dm + (size_t)inst * S * S;
-      const float* Gb = Gm + (size_t)inst * S * S;
+      const Geo<COORDS> geo = make_geo<COORDS>(Dm, Gm, xyp, elevp, inst, S);
       const float* embb = emb + (size_t)inst * S * D;
       const float* kvlb = kvl + (size_t)inst * S * 384;
       uint32_t mk[4] = {rs.mk[0], rs.mk[1], rs.mk[2], rs.mk[3]};
@@ -493,8 +498,10 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       } else { c_node = -1 - sel_i; lp_sel = -INFINITY; }
 
       // ---- loads for the transition and the new mask, issued together ----
-      const float dist = __ldg(Db + (size_t)now * S + c_node);
-      const float slp = __ldg(Gb + (size_t)now * S + c_node);
+      float dist, slp;
+      geo.at(now, c_node, dist, slp);
+      float xc = 0.f, yc = 0.f, ec_elev = 0.f;                  // coordinate mode: the chosen node, row D[c,:] / G[c,:] on the fly
+      if (geo.coords()) { xc = __ldg(geo.x + c_node); yc = __ldg(geo.y + c_node); ec_elev = __ldg(geo.e + c_node); }
       float4 ec = make_float4(0.f, 0.f, 0.f, 0.f);
       if constexpr (POLICY == 0) ec = ldg4(embb + (size_t)c_node * D + lane * 4);
       float dcj[4], gcj[4], d0j[4], g0j[4], d3j[4], s3j[4], dmj[4];
@@ -502,12 +509,15 @@ rollout_kernel(evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
       for (int jb = 0; jb < 4; ++jb) {
         const int j = jb * 32 + lane;
         const bool in = (jb < nblk) && (j < S);
-        dcj[jb] = in ? __ldg(Db + (size_t)c_node * S + j) : 0.f;
-        gcj[jb] = in ? __ldg(Gb + (size_t)c_node * S + j) : 0.f;
-        d0j[jb] = in ? __ldg(Db + j) : 0.f;
-        g0j[jb] = in ? __ldg(Gb + j) : 0.f;
-        d3j[jb] = in ? station_ws[((size_t)inst * 2 + 0) * SP + j] : 0.f;
-        s3j[jb] = in ? station_ws[((size_t)inst * 2 + 1) * SP + j] : 0.f;
+        dcj[jb] = gcj[jb] = 0.f;
+        if (in) {
+          if (geo.coords()) geo.pair(xc, yc, ec_elev, j, dcj[jb], gcj[jb]);
+          else { dcj[jb] = __ldg(geo.D + (size_t)c_node * S + j); gcj[jb] = __ldg(geo.G + (size_t)c_node * S + j); }
+        }
+        d3j[jb] = in ? station_ws[((size_t)inst * 4 + 0) * SP + j] : 0.f;
+        s3j[jb] = in ? station_ws[((size_t)inst * 4 + 1) * SP + j] : 0.f;
+        d0j[jb] = in ? station_ws[((size_t)inst * 4 + 2) * SP + j] : 0.f;
+        g0j[jb] = in ? station_ws[((size_t)inst * 4 + 3) * SP + j] : 0.f;
       }
       // ---- state transition (problems/EVRP.py:226-280) on warp-uniform scalars ----
       float load = rs.load, soc = rs.soc, tim = rs.tim;
@@ -650,7 +660,8 @@ int debug_row_cycles_tc(unsigned long long* out8, int reset);
 #endif
 int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, const evrp_rollout_cfg* cfg, const float* emb,
                       const float* kvl, const float* fixed_ctx, const float* dynamic0, const float* distances,
-                      const float* slope, int B, int S, int F, const int64_t* forced_actions, const float* uniforms,
+                      const float* slope, const float* static_xy, const float* elevations, int B, int S, int F,
+                      const int64_t* forced_actions, const float* uniforms,
                       int64_t* pi, float* ll, float* reward, float* energy, uint32_t* saved_mask, float* saved_veh,
                       int32_t* steps_used, int32_t* t_max, int32_t* status, float* station_ws, float* dem_ws, float* m_ws,
                       cudaStream_t st);
@@ -662,8 +673,8 @@ extern "C" {
 size_t evrp_rollout_workspace_bytes(int B, int S, int n_replicas) {
   (void)S;
   const size_t rows = (size_t)B * (n_replicas > 0 ? n_replicas : 1);
-  // station constants [B][2][128] | demand rows [rows][128] | exact running-max rows [rows][128]
-  return ((size_t)B * 2 * EVRP_MAX_S + rows * EVRP_MAX_S + rows * EVRP_D) * sizeof(float);
+  // instance constants [B][4][128] (rule-7 d3, s3; D[0,:], G[0,:]) | demand rows [rows][128] | exact running-max rows [rows][128]
+  return ((size_t)B * 4 * EVRP_MAX_S + rows * EVRP_MAX_S + rows * EVRP_D) * sizeof(float);
 }
 
 int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evrp_rollout_cfg* cfg,
@@ -673,7 +684,11 @@ int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evr
                  float* saved_veh, int32_t* steps_used, int32_t* t_max, int32_t* status, void* workspace,
                  size_t workspace_bytes, void* stream) {
   using namespace evrp;
-  if (!phys || !w || !cfg || !emb || !kvl || !fixed_ctx || !dynamic0 || !distances || !slope || !pi || !ll ||
+  // geometry: the [B,S,S] matrices, or (distances == slope == NULL) the coordinate / elevation rows in the configuration
+  const float* static_xy = cfg ? cfg->static_xy : nullptr;
+  const float* elevations = cfg ? cfg->elevations : nullptr;
+  const bool geo_ok = (distances && slope) || (!distances && !slope && static_xy && elevations);
+  if (!phys || !w || !cfg || !emb || !kvl || !fixed_ctx || !dynamic0 || !geo_ok || !pi || !ll ||
       !reward || !steps_used || !t_max || !status || !workspace || B < 0 || S < 2 || F < 1 || F >= S ||
       cfg->max_steps < 1 || cfg->n_replicas < 1 || !(cfg->temp > 0.f))
     return -EVRP_E_BADARG;
@@ -686,16 +701,20 @@ int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evr
   if (w->policy != 1 && (!w->w1_veh || !w->w1_max || !w->b1 || !w->w2 || !w->b2)) return -EVRP_E_BADARG;
   if (w->ff_mode == 0 && w->policy != 1) {
     float* station_ws = (float*)workspace;
-    float* dem_ws = station_ws + (size_t)B * 2 * EVRP_MAX_S;
+    float* dem_ws = station_ws + (size_t)B * 4 * EVRP_MAX_S;
     float* m_ws = dem_ws + (size_t)rows * EVRP_MAX_S;
-    return launch_rollout_tc(phys, w, cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope, B, S, F, forced_actions,
+    return launch_rollout_tc(phys, w, cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope, static_xy, elevations, B, S, F, forced_actions,
                              uniforms, pi, ll, reward, energy, saved_mask, saved_veh, steps_used, t_max, status,
                              station_ws, dem_ws, m_ws, st);
   }
   const size_t smem = sizeof(DecodeSmem);
   const int mode = forced_actions ? 2 : (cfg->decode_type == EVRP_DECODE_SAMPLE ? 1 : 0);
-  auto kern = w->policy == 1 ? (mode == 2 ? rollout_kernel<2, 1> : mode == 1 ? rollout_kernel<1, 1> : rollout_kernel<0, 1>)
-                             : (mode == 2 ? rollout_kernel<2, 0> : mode == 1 ? rollout_kernel<1, 0> : rollout_kernel<0, 0>);
+  auto pick = [&](auto coords_tag) {
+    constexpr bool C = decltype(coords_tag)::value;
+    return w->policy == 1 ? (mode == 2 ? rollout_kernel<2, 1, C> : mode == 1 ? rollout_kernel<1, 1, C> : rollout_kernel<0, 1, C>)
+                          : (mode == 2 ? rollout_kernel<2, 0, C> : mode == 1 ? rollout_kernel<1, 0, C> : rollout_kernel<0, 0, C>);
+  };
+  auto kern = distances ? pick(std::false_type{}) : pick(std::true_type{});
   EVRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // balance: fill whole waves of (2 CTAs x SMs) slots and spread the rows evenly over them (<= RPC rows per CTA)
   int dev = 0, sms = 148;
@@ -708,7 +727,7 @@ int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evr
   if (grid > rows) grid = rows;
   const int rows_per_cta = (rows + grid - 1) / grid;
   grid = (rows + rows_per_cta - 1) / rows_per_cta;
-  kern<<<grid, NT, smem, st>>>(*phys, *w, *cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope,
+  kern<<<grid, NT, smem, st>>>(*phys, *w, *cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope, static_xy, elevations,
                                          (float*)workspace, B, S, F, rows, rows_per_cta, forced_actions, uniforms, pi, ll, reward,
                                          energy, saved_mask, saved_veh, steps_used, t_max, status);
   EVRP_LAUNCH_OK();

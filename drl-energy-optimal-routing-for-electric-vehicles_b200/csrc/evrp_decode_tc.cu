@@ -129,12 +129,13 @@ __device__ __forceinline__ T sel4(const T (&a)[4], int i) { return i == 0 ? a[0]
 
 struct Maps { CUtensorMap w1h, w1l, w2h, w2l; };
 
-// MODE: 0 greedy, 1 sample, 2 teacher-forced
-template <int MODE>
+// MODE: 0 greedy, 1 sample, 2 teacher-forced; COORDS: geometry recomputed from coordinate / elevation rows
+template <int MODE, bool COORDS>
 __global__ void __launch_bounds__(NT, EVRP_CTAS)
 rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
                   const float* __restrict__ emb, const float* __restrict__ kvl, const float* __restrict__ fixed_ctx,
                   const float* __restrict__ dynamic0, const float* __restrict__ Dm, const float* __restrict__ Gm,
+                  const float* __restrict__ xyp, const float* __restrict__ elevp,
                   float* station_ws, float* dem_ws, float* m_ws, int B, int S, int F, int rows_total, int rows_per_cta,
                   int pf_lines, int walkers, const int64_t* __restrict__ forced, const float* __restrict__ uniforms,
                   int64_t* __restrict__ pi, float* __restrict__ ll, float* __restrict__ reward,
@@ -174,8 +175,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
       const int row = blockIdx.x * rows_per_cta + lr;
       const bool valid = (lr < rows_per_cta) && (row < rows_total);
       const int inst = valid ? row % B : 0;
-      const float* Db = Dm + (size_t)inst * S * S;
-      const float* Gb = Gm + (size_t)inst * S * S;
+      const Geo<COORDS> geo = make_geo<COORDS>(Dm, Gm, xyp, elevp, inst, S);
       const float* dy = dynamic0 + (size_t)inst * 4 * S;
       const float load = dy[0], soc = dy[2 * S], tim = dy[3 * S];
       bool nonuni = false;
@@ -188,13 +188,18 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         if (j < S) {
           dmv = dy[S + j];
           nonuni |= (dy[j] != load) || (dy[2 * S + j] != soc) || (dy[3 * S + j] != tim);
-          int k = 0; float best = Db[(size_t)1 * S + j];       // rule-7 constants (problems/EVRP.py:196-202)
-          for (int i = 1; i < F; ++i) { const float v = Db[(size_t)(1 + i) * S + j]; if (v < best) { best = v; k = i; } }
+          int k = 0; float best, gk, tmp;                     // rule-7 constants (problems/EVRP.py:196-202)
+          geo.at(1, j, best, gk);
+          for (int i = 1; i < F; ++i) { float v, gv; geo.at(1 + i, j, v, gv); if (v < best) { best = v; gk = gv; k = i; } }
+          float d0v, g0v;
+          geo.at(0, j, d0v, g0v);
           if (valid) {
-            station_ws[((size_t)inst * 2 + 0) * SP + j] = (j == 0) ? 0.f : best;
-            station_ws[((size_t)inst * 2 + 1) * SP + j] = Gb[(size_t)(1 + k) * S + j];
+            station_ws[((size_t)inst * 4 + 0) * SP + j] = (j == 0) ? 0.f : best;
+            station_ws[((size_t)inst * 4 + 1) * SP + j] = gk;
+            station_ws[((size_t)inst * 4 + 2) * SP + j] = d0v;       // D[0,:], G[0,:]: instance constants of the look-ahead
+            station_ws[((size_t)inst * 4 + 3) * SP + j] = g0v;
           }
-          if (j == 0) d4 = Db[(size_t)(1 + k) * S + 0];
+          if (j == 0) geo.at(1 + k, 0, d4, tmp);
         }
         if (valid) __stcg(dem_ws + (size_t)row * SP + j, dmv);
         mk[jb] = __ballot_sync(FULL, j < S);                     // mask = ones (:256)
@@ -391,8 +396,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         const int row = blockIdx.x * rows_per_cta + lr;
         const int inst = rs.inst;
         const int now = rs.now;
-        const float* Db = Dm + (size_t)inst * S * S;
-        const float* Gb = Gm + (size_t)inst * S * S;
+        const Geo<COORDS> geo = make_geo<COORDS>(Dm, Gm, xyp, elevp, inst, S);
         const float* embb = emb + (size_t)inst * S * D;
         const float* kvlb = kvl + (size_t)inst * S * 384;
         uint32_t mk[4] = {rs.mk[0], rs.mk[1], rs.mk[2], rs.mk[3]};
@@ -623,20 +627,25 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
 
         RT_MARK(5);
         // ---- loads for the transition and the new mask, issued together ----
-        const float dist = __ldg(Db + (size_t)now * S + c_node);
-        const float slp = __ldg(Gb + (size_t)now * S + c_node);
+        float dist, slp;
+        geo.at(now, c_node, dist, slp);
+        float xc = 0.f, yc = 0.f, ec_elev = 0.f;                  // coordinate mode: the chosen node, row D[c,:] / G[c,:] on the fly
+        if (geo.coords()) { xc = __ldg(geo.x + c_node); yc = __ldg(geo.y + c_node); ec_elev = __ldg(geo.e + c_node); }
         const float4 ec = ldg4(embb + (size_t)c_node * D + lane * 4);
         float dcj[4], gcj[4], d0j[4], g0j[4], d3j[4], s3j[4];
 #pragma unroll
         for (int jb = 0; jb < 4; ++jb) {
           const int j = jb * 32 + lane;
           const bool in = (jb < nblk) && (j < S);
-          dcj[jb] = in ? __ldg(Db + (size_t)c_node * S + j) : 0.f;
-          gcj[jb] = in ? __ldg(Gb + (size_t)c_node * S + j) : 0.f;
-          d0j[jb] = in ? __ldg(Db + j) : 0.f;
-          g0j[jb] = in ? __ldg(Gb + j) : 0.f;
-          d3j[jb] = in ? station_ws[((size_t)inst * 2 + 0) * SP + j] : 0.f;
-          s3j[jb] = in ? station_ws[((size_t)inst * 2 + 1) * SP + j] : 0.f;
+          dcj[jb] = gcj[jb] = 0.f;
+          if (in) {
+            if (geo.coords()) geo.pair(xc, yc, ec_elev, j, dcj[jb], gcj[jb]);
+            else { dcj[jb] = __ldg(geo.D + (size_t)c_node * S + j); gcj[jb] = __ldg(geo.G + (size_t)c_node * S + j); }
+          }
+          d3j[jb] = in ? station_ws[((size_t)inst * 4 + 0) * SP + j] : 0.f;
+          s3j[jb] = in ? station_ws[((size_t)inst * 4 + 1) * SP + j] : 0.f;
+          d0j[jb] = in ? station_ws[((size_t)inst * 4 + 2) * SP + j] : 0.f;
+          g0j[jb] = in ? station_ws[((size_t)inst * 4 + 3) * SP + j] : 0.f;
         }
         // ---- state transition (problems/EVRP.py:226-280) on warp-uniform scalars ----
         float load = rs.load, soc = rs.soc, tim = rs.tim;
@@ -792,7 +801,8 @@ int debug_row_cycles_tc(unsigned long long* out8, int reset) {
 // host launcher (called from evrp_rollout in evrp_decode.cu when the decoder weights carry ff_mode == 0)
 int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, const evrp_rollout_cfg* cfg, const float* emb,
                       const float* kvl, const float* fixed_ctx, const float* dynamic0, const float* distances,
-                      const float* slope, int B, int S, int F, const int64_t* forced_actions, const float* uniforms,
+                      const float* slope, const float* static_xy, const float* elevations, int B, int S, int F,
+                      const int64_t* forced_actions, const float* uniforms,
                       int64_t* pi, float* ll, float* reward, float* energy, uint32_t* saved_mask, float* saved_veh,
                       int32_t* steps_used, int32_t* t_max, int32_t* status, float* station_ws, float* dem_ws, float* m_ws,
                       cudaStream_t st) {
@@ -806,7 +816,9 @@ int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, cons
   if ((rc = tc::make_weight_map_f16(&maps.w2l, w->w2_lo, D, FF, 128))) return rc;
   const int rows = B * cfg->n_replicas;
   const int mode = forced_actions ? 2 : (cfg->decode_type == EVRP_DECODE_SAMPLE ? 1 : 0);
-  auto kern = mode == 2 ? rollout_tc_kernel<2> : mode == 1 ? rollout_tc_kernel<1> : rollout_tc_kernel<0>;
+  const bool coords = (distances == nullptr);
+  auto kern = coords ? (mode == 2 ? rollout_tc_kernel<2, true> : mode == 1 ? rollout_tc_kernel<1, true> : rollout_tc_kernel<0, true>)
+                     : (mode == 2 ? rollout_tc_kernel<2, false> : mode == 1 ? rollout_tc_kernel<1, false> : rollout_tc_kernel<0, false>);
   EVRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   int dev = 0, sms = 148;
   EVRP_CUDA_OK(cudaGetDevice(&dev));
@@ -824,7 +836,7 @@ int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, cons
   if (pf_lines < 0) { const char* l = getenv("EVRP_PF_LINES"); pf_lines = l ? atoi(l) : (13 | 0x10000); }
   static int walkers = -1;
   if (walkers < 0) { const char* e = getenv("EVRP_WALKERS"); walkers = e ? atoi(e) : ROW_WARPS + 2; }
-  kern<<<grid, NT, SMEM_BYTES, st>>>(maps, *phys, *w, *cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope, station_ws,
+  kern<<<grid, NT, SMEM_BYTES, st>>>(maps, *phys, *w, *cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope, static_xy, elevations, station_ws,
                                      dem_ws, m_ws, B, S, F, rows, rows_per_cta, pf_lines, walkers, forced_actions, uniforms, pi, ll, reward,
                                      energy, saved_mask, saved_veh, steps_used, t_max, status);
   EVRP_LAUNCH_OK();

@@ -146,9 +146,66 @@ pairwise_build_kernel(const float* __restrict__ xy, const float* __restrict__ el
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// on-device instance generation: the distribution and value grid of problems/EVRP.py:43-92 (with patch P1:
+// layout [depot, F stations, N customers]) from a counter-based generator -- one thread per (instance, node), no host
+// loop, no host->device copy.  depot in [25,75)^2; station i in quadrant i % 4 (x in [0,50) for quadrants 0-1 else
+// [51,101); y in [0,50) for even quadrants else [51,101)); customers on the integer grid [0,100]^2; demand in
+// {1..max_demand} * 0.25 / max_load (0 for depot / stations); elevation in {0..100} / 1000; dynamic0 = [1, demand,
+// Start_SOC, t_limit].
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t draw_below(uint64_t seed, uint64_t inst, uint32_t node, uint32_t stream, uint32_t range) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * ((inst * 256ull + node) * 8ull + stream + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(((z >> 32) * (uint64_t)range) >> 32);          // unbiased to 2^-32
+}
+
+__global__ void __launch_bounds__(256)
+generate_instances_kernel(uint64_t seed, int B, int S, int F, float start_soc, float t_limit, float max_load,
+                          int max_demand, float* __restrict__ xy, float* __restrict__ dyn, float* __restrict__ elev) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * S) return;
+  const long long b = idx / S;
+  const int j = (int)(idx % S);
+  float x, y, dem = 0.f;
+  if (j == 0) {
+    x = 25.f + (float)draw_below(seed, b, j, 0, 50); y = 25.f + (float)draw_below(seed, b, j, 1, 50);
+  } else if (j <= F) {
+    const int q = (j - 1) & 3;
+    const uint32_t rx = draw_below(seed, b, j, 0, 50), ry = draw_below(seed, b, j, 1, 50);
+    x = (q < 2) ? (float)rx : 51.f + (float)rx;
+    y = ((q & 1) == 0) ? (float)ry : 51.f + (float)ry;
+  } else {
+    x = (float)draw_below(seed, b, j, 0, 101); y = (float)draw_below(seed, b, j, 1, 101);
+    dem = __fdiv_rn(__fmul_rn((float)(1 + draw_below(seed, b, j, 2, (uint32_t)max_demand)), 0.25f), max_load);
+  }
+  xy[(b * 2 + 0) * S + j] = x;
+  xy[(b * 2 + 1) * S + j] = y;
+  elev[b * S + j] = __fdiv_rn((float)draw_below(seed, b, j, 3, 101), 1000.f);
+  dyn[(b * 4 + 0) * S + j] = 1.f;
+  dyn[(b * 4 + 1) * S + j] = dem;
+  dyn[(b * 4 + 2) * S + j] = start_soc;
+  dyn[(b * 4 + 3) * S + j] = t_limit;
+}
+
 }  // namespace evrp
 
 extern "C" {
+
+int evrp_generate_instances(uint64_t seed, int B, int N, int F, float start_soc, float t_limit, int max_load, int max_demand,
+                            float* static_xy, float* dynamic, float* elevations, void* stream) {
+  if (!static_xy || !dynamic || !elevations || B < 0 || N < 1 || F < 1 || N + F + 1 > EVRP_MAX_S || max_load < 1 || max_demand < 1)
+    return -EVRP_E_BADARG;
+  if (B == 0) return 0;
+  const int S = N + F + 1;
+  const long long n = (long long)B * S;
+  evrp::generate_instances_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      seed, B, S, F, start_soc, t_limit, (float)max_load, max_demand, static_xy, dynamic, elevations);
+  EVRP_LAUNCH_OK();
+  return 0;
+}
 
 void evrp_phys_default(evrp_phys* p, double velocity, double start_soc, double t_limit, double max_load) {
   const double Cd = 0.7, A = 6.66, Ad = 1.2041;

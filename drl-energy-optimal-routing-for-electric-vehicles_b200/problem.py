@@ -110,6 +110,22 @@ def synthetic_instances(B, N, F=5, seed=0, t_limit=10., Start_SOC=80., max_load=
     return static, dynamic, elevation
 
 
+def generate_instances(B, N, F=5, seed=0, t_limit=10., Start_SOC=80., max_load=4, max_demand=4, device=None):
+    """On-device instance generation: the same distribution and value grid as ``synthetic_instances`` /
+    problems/EVRP.py:43-92, produced by one CUDA kernel from a counter-based generator -- no host loop, no host-to-device
+    copy.  -> CUDA tensors static [B,2,S], dynamic [B,4,S], elevation [B,S]; feed them as the 3-tuple input."""
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    S = N + F + 1
+    static = torch.empty(B, 2, S, device=dev)
+    dynamic = torch.empty(B, 4, S, device=dev)
+    elev = torch.empty(B, S, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().evrp_generate_instances(int(seed) & 0xFFFFFFFFFFFFFFFF, B, N, F, float(Start_SOC), float(t_limit),
+                                                      int(max_load), int(max_demand), _lib.ptr(static), _lib.ptr(dynamic),
+                                                      _lib.ptr(elev), _lib.stream_ptr()), "evrp_generate_instances")
+    return static, dynamic, elev
+
+
 class VehicleRoutingDataset(Dataset):
     _evrp_b200_native = True
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 15
+#define EVRP_ABI_VERSION 16
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -92,6 +92,12 @@ int evrp_update_mask(const evrp_phys* phys, const float* dynamic, const float* d
  * own build problems/EVRP.py:87-92.  static_xy [B,2,S], elevations [B,S] -> distances, slope [B,S,S]. */
 int evrp_pairwise_build(const float* static_xy, const float* elevations, int B, int S, float* distances, float* slope,
                         void* stream);
+
+/* on-device instance generation: B synthetic instances with the distribution and value grid of the dataset
+ * constructor problems/EVRP.py:43-92 (layout [depot, F stations, N customers]) from a counter-based generator: static_xy
+ * [B,2,S], dynamic [B,4,S] = [1, demand, Start_SOC, t_limit], elevations [B,S]; S = 1 + F + N <= EVRP_MAX_S. */
+int evrp_generate_instances(uint64_t seed, int B, int N, int F, float start_soc, float t_limit, int max_load, int max_demand,
+                            float* static_xy, float* dynamic, float* elevations, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (2) encoder + decoder precompute:  AttentionModel._init_embed        nets/DRLModel.py:192-200
@@ -210,11 +216,17 @@ typedef struct {
   uint64_t seed;             /* counter-based RNG seed for sampling                                         */
   int32_t n_replicas;        /* sample_many: rollouts per instance sharing one encoder output (>=1);
                                 rollout row r uses instance r % B (replica-major, nets/DRLModel.py:291-294)   */
+  /* 3-tuple input (static, dynamic, Elevations), nets/DRLModel.py:124-133: when evrp_rollout is called with
+     distances == slope == NULL the kernel recomputes D[i,j] = sqrt((x_i-x_j)^2 + (y_i-y_j)^2) and G[i,j] = clamp((E_i -
+     E_j) / (D + 1e-6), +-0.1) from these rows where it needs them (same separately rounded ops as evrp_pairwise_build,
+     bit-identical results): no [B,S,S] tensor exists at all                                                        */
+  const float *static_xy;    /* [B,2,S] or NULL                                                              */
+  const float *elevations;   /* [B,S] or NULL                                                                */
 } evrp_rollout_cfg;
 
 int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evrp_rollout_cfg* cfg,
                  const float* emb /*[B,S,128]*/, const float* kvl /*[B,S,384]*/, const float* fixed_ctx /*[B,128]*/,
-                 const float* dynamic0 /*[B,4,S]*/, const float* distances /*[B,S,S]*/, const float* slope,
+                 const float* dynamic0 /*[B,4,S]*/, const float* distances /*[B,S,S] or NULL*/, const float* slope /*[B,S,S] or NULL*/,
                  int B, int S, int F,
                  const int64_t* forced_actions /*[B*R,Tcap] or NULL*/, const float* uniforms /*[B*R,Tcap] or NULL*/,
                  int64_t* pi /*[B*R,Tcap]*/, float* ll /*[B*R,Tcap]*/, float* reward /*[B*R,Tcap]*/,

@@ -508,6 +508,76 @@ def test_eval_dataset_width_sweep(evrp, weights, tmp_path):
 
 
 # ---------------------------------------------------------------------------------------------
+# f2: 3-tuple input (static, dynamic, Elevations): distances / slope recomputed inside the rollout kernels
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,B,ff_mode", [(20, 300, 0), (100, 150, 0), (50, 77, 1), (122, 9, 0)])
+def test_three_tuple_input_recomputes_geometry_in_kernel(evrp, weights, N, B, ff_mode):
+    """nets/DRLModel.py:124-133: with (static, dynamic, Elevations) the kernels compute D[i,j] / G[i,j] where they need them
+    (no [B,S,S] tensor); tours, log-likelihoods, rewards and the trace are bit-identical to the 4-tuple call on the matrices
+    of evrp_pairwise_build, greedy and sampled (same counter-based stream), and the oracle replays the costs"""
+    from evrp_b200 import policy_math as PM
+    static, dynamic, elev = O.generate_instances(B, N, seed=900 + N)
+    D, G = O.pairwise_matrices(static, elev)
+    st, dy, el = (torch.from_numpy(x).cuda() for x in (static, dynamic, elev))
+    Dg, Gg = PM.pairwise_matrices(st, el)
+    assert np.array_equal(Dg.cpu().numpy(), D) and np.array_equal(Gg.cpu().numpy(), G)
+    m, _ = make_model(evrp, N, weights)
+    m.ff_mode = ff_mode
+    m.geometry_mode = 1                                             # 3-tuple input -> in-kernel recompute
+    for decode in ("greedy", "sample"):
+        m.set_decode_type(decode)
+        outs = []
+        for batch in ((st, dy, Dg, Gg), (st, dy, el)):
+            m._calls = 0; m.sample_seed = 1234                      # the same sampling stream for both calls
+            with torch.no_grad():
+                outs.append(m(batch))
+        for a, b in zip(*outs):
+            assert torch.equal(a, b), decode
+    pi, ll, R = outs[1]
+    rep = O.rollout(weights, static, dynamic, D, G, forced=pi.cpu().numpy())
+    assert np.array_equal(rep["R"], R.cpu().numpy())
+    # teacher-forced with the trace: masks identical too
+    m.set_decode_type("greedy")
+    o4 = m.forward_forced((st, dy, Dg, Gg), pi, save_trace=True)
+    o3 = m.forward_forced((st, dy, el), pi, save_trace=True)
+    assert torch.equal(o4["mask_bits"], o3["mask_bits"]) and torch.equal(o4["R"], o3["R"]) and torch.equal(o4["ll"], o3["ll"])
+
+
+def test_on_device_instance_generation(evrp, weights):
+    """evrp_generate_instances: value grid and distribution of problems/EVRP.py:43-92, deterministic in the seed; a greedy
+    rollout of the generated 3-tuple serves every customer and the oracle replays its costs"""
+    B, N, F = 4096, 50, 5
+    st, dy, el = evrp.generate_instances(B, N, F, seed=11)
+    st2, dy2, el2 = evrp.generate_instances(B, N, F, seed=11)
+    st3, _, _ = evrp.generate_instances(B, N, F, seed=12)
+    assert torch.equal(st, st2) and torch.equal(dy, dy2) and torch.equal(el, el2) and not torch.equal(st, st3)
+    s, d, e = st.cpu().numpy(), dy.cpu().numpy(), el.cpu().numpy()
+    assert s.shape == (B, 2, N + F + 1) and d.shape == (B, 4, N + F + 1) and e.shape == (B, N + F + 1)
+    assert np.array_equal(s, np.round(s))                                       # integer grid
+    assert s[:, :, 0].min() >= 25 and s[:, :, 0].max() <= 74                    # depot in [25,75)
+    for i in range(F):                                                          # station i in quadrant i % 4
+        q = i % 4
+        x, y = s[:, 0, 1 + i], s[:, 1, 1 + i]
+        assert (x.max() <= 49 and x.min() >= 0) if q < 2 else (x.min() >= 51 and x.max() <= 100)
+        assert (y.max() <= 49 and y.min() >= 0) if q % 2 == 0 else (y.min() >= 51 and y.max() <= 100)
+    c = s[:, :, F + 1:]
+    assert c.min() == 0 and c.max() == 100 and abs(c.mean() - 50) < 0.5
+    dem = d[:, 1]
+    assert np.all(dem[:, :F + 1] == 0) and set(np.unique(dem[:, F + 1:])) == {np.float32(k * 0.25 / 4) for k in (1, 2, 3, 4)}
+    assert np.all(d[:, 0] == 1) and np.all(d[:, 2] == 80) and np.all(d[:, 3] == 10)
+    assert set(np.unique(e)) <= {np.float32(k) / np.float32(1000) for k in range(101)} and abs(e.mean() - 0.05) < 1e-3
+    m, _ = make_model(evrp, N, weights)
+    m.set_decode_type("greedy")
+    with torch.no_grad():
+        pi, ll, R = m((st[:64], dy[:64], el[:64]))
+    D, G = O.pairwise_matrices(s[:64], e[:64])
+    rep = O.rollout(weights, s[:64], d[:64], D, G, forced=pi.cpu().numpy())
+    assert np.array_equal(rep["R"], R.cpu().numpy())
+    for b in range(64):
+        assert set(range(F + 1, N + F + 1)) <= set(pi[b].cpu().numpy().tolist())
+
+
+# ---------------------------------------------------------------------------------------------
 # round 2: wider reference pins -- 64 instances at the headline size, a sampled N = 50 trace, config 3's shape
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("ff_mode", [0, 1])
