@@ -83,7 +83,7 @@ struct __align__(16) Ctl {
   float veh[RPC][4];             // load, soc/Start_SOC, time/t_limit          (:215-222)
   uint64_t full[WSTAGES], empty[WSTAGES];
   uint64_t d1_full[4];           // hidden tile j accumulated (tcgen05.commit)
-  uint64_t b2_full[2];           // hidden tile planes (double-buffered) written by the 512 epilogue threads
+  uint64_t b2_full[2];           // hidden tile planes (double-buffered) written by the 16 epilogue warps
   uint64_t b2_empty[2];          // GEMM2 partial over that buffer retired (tcgen05.commit)
   uint64_t d2_full;              // ctx accumulated
   uint32_t tmem_base;
@@ -159,7 +159,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
   if (tid == 0) {
     for (int s = 0; s < WSTAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
     for (int j = 0; j < 4; ++j) mbar_init(&sm.d1_full[j], 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&sm.b2_full[b], ROW_WARPS * 32); mbar_init(&sm.b2_empty[b], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&sm.b2_full[b], ROW_WARPS); mbar_init(&sm.b2_empty[b], 1); }
     mbar_init(&sm.d2_full, 1);
     sm.next_row = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -361,7 +361,8 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           *reinterpret_cast<__half*>(p + KBLK) = lo;
         }
         fence_async_smem();
-        mbar_arrive(&sm.b2_full[j % NB2]);
+        __syncwarp();                                           // one arrival per warp (512 per-thread arrivals serialise)
+        if (lane == 0) mbar_arrive(&sm.b2_full[j % NB2]);
       }
       PT_MARK(0);
       mbar_wait(&sm.d2_full, t & 1);

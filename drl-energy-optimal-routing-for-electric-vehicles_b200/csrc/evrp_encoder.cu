@@ -276,7 +276,7 @@ int launch_encoder_fused(const evrp_encoder_weights* w, const float* xy, const f
 // evrp_tc_gemm.cu
 int tc_gemm(int epi, const float* A, int lda, const float* Wh, const float* Wl, float* C, int ldc, int M, int N, int K,
             const float* bias, const float* resid, int ldr, const float* scale, const float* shift, int sm_count,
-            cudaStream_t st);
+            cudaStream_t st, const float* aux = nullptr, const float* auxw = nullptr);
 
 }  // namespace evrp
 

@@ -69,11 +69,10 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// fp32 -> TF32 with round-to-nearest, ties away (the result of cvt.rna.tf32.f32 for every finite input) as two integer
+// operations: ptxas expands the cvt into ~5 instructions (NaN / Inf screening), which made the operand converters of
+// the tcgen05 kernels ALU-bound (ncu: profiles/r2_wgrad_ncu.md).  Same expression as policy_math.split_tf32.
+__device__ __forceinline__ uint32_t to_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 
 
 // instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2,

@@ -34,22 +34,23 @@ constexpr int MAX_STAGES = 4;
 #endif
 constexpr int PLANE = BM * BKB * 4;                  // 16 KB: one [128 x 32] fp32 plane
 constexpr int NTHREADS = 320;
-constexpr int EPI_BIAS = 1, EPI_RELU = 2, EPI_RESID = 4, EPI_AFFINE = 8;
+constexpr int EPI_BIAS = 1, EPI_RELU = 2, EPI_RESID = 4, EPI_AFFINE = 8, EPI_AUX = 16;   // AUX: + aux[m][0..2] . auxw[0..2][n] before the ReLU
 
 constexpr uint32_t IDESC = make_idesc_tf32(128, 128);
 
 struct Epilogue {
   const float* bias; const float* resid; int ldr; const float* scale; const float* shift;
+  const float* aux; const float* auxw; int n_cols;      // EPI_AUX: aux [M,3] row-major, auxw [3][n_cols]
 };
 
 struct __align__(8) Barriers {
-  uint64_t full[MAX_STAGES];      // stage filled (128 converter arrivals [+1 producer arrival carrying the TMA bytes])
+  uint64_t full[MAX_STAGES];      // stage filled (4 converter-warp arrivals [+1 producer arrival carrying the TMA bytes])
   uint64_t empty[MAX_STAGES];     // stage consumed (tcgen05.commit)
   uint64_t w_ready;           // resident weights landed
   uint64_t acc_full[2];       // accumulator ready for the epilogue (tcgen05.commit)
-  uint64_t acc_empty[2];      // accumulator drained (128 epilogue arrivals)
+  uint64_t acc_empty[2];      // accumulator drained (4 epilogue-warp arrivals)
   uint64_t raw_full[8];       // raw fp32 activation tile landed (TMA bytes)        [A_TMEM mode]
-  uint64_t raw_empty[8];      // raw tile consumed by the 128 converter threads      [A_TMEM mode]
+  uint64_t raw_empty[8];      // raw tile consumed by the 4 converter warps          [A_TMEM mode]
   uint32_t tmem_base;
 };
 constexpr int RAW_STAGES = EVRP_GEMM_RAW_STAGES;      // raw activation staging ring (16 KB each)
@@ -87,10 +88,10 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
   const int m_tiles = (M + BM - 1) / BM;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars->full[s], RESIDENT ? 128 : 129); mbar_init(&bars->empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars->full[s], RESIDENT ? 4 : 5); mbar_init(&bars->empty[s], 1); }
     mbar_init(&bars->w_ready, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&bars->acc_full[b], 1); mbar_init(&bars->acc_empty[b], 128); }
-    for (int r = 0; r < RAW_STAGES; ++r) { mbar_init(&bars->raw_full[r], 1); mbar_init(&bars->raw_empty[r], 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars->acc_full[b], 1); mbar_init(&bars->acc_empty[b], 4); }
+    for (int r = 0; r < RAW_STAGES; ++r) { mbar_init(&bars->raw_full[r], 1); mbar_init(&bars->raw_empty[r], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {   // TMEM: 2 accumulators x 128 columns
@@ -205,8 +206,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&bars->full[s]);
-      mbar_arrive(&bars->raw_empty[rsg]);                // raw tile consumed (values already pushed to TMEM)
+      __syncwarp();                                      // one arrival per warp: per-thread arrivals serialise on the barrier
+      if (lane == 0) { mbar_arrive(&bars->full[s]); mbar_arrive(&bars->raw_empty[rsg]); }   // raw tile consumed (values already in TMEM)
     }
   } else if (warp >= 4) {
     // ================= A converters: fp32 -> (hi, lo) TF32 planes, swizzled K-major =================
@@ -251,7 +252,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
             *reinterpret_cast<uint4*>(st + PLANE + off) = lo;
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05
-          mbar_arrive(&bars->full[s]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars->full[s]);
           issue(it + PF, v[p]);
         }
       }
@@ -290,12 +292,21 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
           float2 bb = make_float2(0.f, 0.f), sc = make_float2(1.f, 1.f), sh = make_float2(0.f, 0.f);
           if (EPI & EPI_BIAS) bb = __ldg(reinterpret_cast<const float2*>(ep.bias + n));
           if (EPI & EPI_AFFINE) { sc = __ldg(reinterpret_cast<const float2*>(ep.scale + n)); sh = __ldg(reinterpret_cast<const float2*>(ep.shift + n)); }
+          float2 aw0 = bb, aw1 = bb, aw2 = bb;
+          if (EPI & EPI_AUX) {
+            aw0 = __ldg(reinterpret_cast<const float2*>(ep.auxw + n)); aw1 = __ldg(reinterpret_cast<const float2*>(ep.auxw + ep.n_cols + n));
+            aw2 = __ldg(reinterpret_cast<const float2*>(ep.auxw + 2 * ep.n_cols + n));
+          }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int m = mbase + 8 * h;
             if (m < M) {
               float v0 = __uint_as_float(r[4 * i + 2 * h]), v1 = __uint_as_float(r[4 * i + 2 * h + 1]);
               if (EPI & EPI_BIAS) { v0 += bb.x; v1 += bb.y; }
+              if (EPI & EPI_AUX) {                              // vehicle term of FF_tour.0 (nets/DRLModel.py:215-235)
+                const float a0 = __ldg(ep.aux + (size_t)m * 3), a1 = __ldg(ep.aux + (size_t)m * 3 + 1), a2 = __ldg(ep.aux + (size_t)m * 3 + 2);
+                v0 += fmaf(a2, aw2.x, fmaf(a1, aw1.x, a0 * aw0.x)); v1 += fmaf(a2, aw2.y, fmaf(a1, aw1.y, a0 * aw0.y));
+              }
               if (EPI & EPI_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
               if (EPI & EPI_RESID) {
                 const float2 rr = __ldg(reinterpret_cast<const float2*>(ep.resid + (size_t)m * ep.ldr + n));
@@ -308,7 +319,8 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&bars->acc_empty[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty[buf]);
     }
   }
   __syncthreads();
@@ -401,7 +413,7 @@ static int launch(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMa
 // C = epi(A @ W^T) with W given as pre-split TF32 planes Wh, Wl ([N][K]).  K in {128, 512}, N % 128 == 0.
 int tc_gemm(int epi, const float* A, int lda, const float* Wh, const float* Wl, float* C, int ldc, int M, int N, int K,
             const float* bias, const float* resid, int ldr, const float* scale, const float* shift, int sm_count,
-            cudaStream_t st) {
+            cudaStream_t st, const float* aux, const float* auxw) {
   using namespace tc;
   if (N % BN || K % BKB || K < BKB || (K != 128 && K != 512 && epi != 0)) return -EVRP_E_BADARG;
   CUtensorMap mh, ml, ma;
@@ -409,12 +421,13 @@ int tc_gemm(int epi, const float* A, int lda, const float* Wh, const float* Wl, 
   if ((rc = make_weight_map(&mh, Wh, N, K, 0, BN))) return rc;
   if ((rc = make_weight_map(&ml, Wl, N, K, 0, BN))) return rc;
   if ((rc = make_weight_map(&ma, A, M, K, lda, BN))) return rc;
-  Epilogue ep{bias, resid, ldr, scale, shift};
+  Epilogue ep{bias, resid, ldr, scale, shift, aux, auxw, N};
   if (K == 128) {
     switch (epi) {
       case 0: return launch<true, 0>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
       case EPI_BIAS | EPI_RELU: return launch<true, EPI_BIAS | EPI_RELU>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
       case EPI_RESID | EPI_AFFINE: return launch<true, EPI_RESID | EPI_AFFINE>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
+      case EPI_BIAS | EPI_RELU | EPI_AUX: return launch<true, EPI_BIAS | EPI_RELU | EPI_AUX>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
     }
   } else if (epi == (EPI_BIAS | EPI_RESID | EPI_AFFINE)) {
     return launch<false, EPI_BIAS | EPI_RESID | EPI_AFFINE>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
@@ -430,14 +443,15 @@ int tc_gemm(int epi, const float* A, int lda, const float* Wh, const float* Wl, 
 // input-gradient products of the projections / feed-forward layers).
 extern "C" int evrp_gemm_3xtf32(int epilogue, const float* A, int lda, const float* W_hi, const float* W_lo, float* C,
                                 int ldc, int M, int N, int K, const float* bias, const float* resid, int ldr,
-                                const float* scale, const float* shift, void* stream) {
+                                const float* scale, const float* shift, const float* aux, const float* aux_w, void* stream) {
   using namespace evrp::tc;
   if (!A || !W_hi || !W_lo || !C || M < 0 || N < 1 || K < 1 || lda < K || ldc < N) return -EVRP_E_BADARG;
-  if (((epilogue & EPI_BIAS) && !bias) || ((epilogue & EPI_RESID) && !resid) || ((epilogue & EPI_AFFINE) && (!scale || !shift)))
+  if (((epilogue & EPI_BIAS) && !bias) || ((epilogue & EPI_RESID) && !resid) || ((epilogue & EPI_AFFINE) && (!scale || !shift)) ||
+      ((epilogue & EPI_AUX) && (!aux || !aux_w)))
     return -EVRP_E_BADARG;
   if (M == 0) return 0;
   int dev = 0, sms = 148;
   EVRP_CUDA_OK(cudaGetDevice(&dev));
   EVRP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  return evrp::tc_gemm(epilogue, A, lda, W_hi, W_lo, C, ldc, M, N, K, bias, resid, ldr, scale, shift, sms, (cudaStream_t)stream);
+  return evrp::tc_gemm(epilogue, A, lda, W_hi, W_lo, C, ldc, M, N, K, bias, resid, ldr, scale, shift, sms, (cudaStream_t)stream, aux, aux_w);
 }

@@ -212,18 +212,25 @@ class AttentionModel(nn.Module):
                                   owner.max_load, owner.objective, div_mode=int(getattr(owner, "div_mode", 0)))
         return _lib.make_phys(self.velocity, float(self.start_soc), float(self.t_limit), self.max_load, self.objective)
 
-    def packed_weights(self):
+    def packed_weights(self, part="all"):
         """Kernel-side weight layouts (k-major transposes, folded BatchNorm / project_out / tour), rebuilt only
-        when a parameter or buffer changed (tensor version counters)."""
+        when a parameter or buffer changed (tensor version counters).  ``part`` = "encoder" / "decoder" packs (and
+        caches) that half only: a REINFORCE step re-packs just the decoder half after every optimizer step."""
         sd = self.__dict__.get("_tensor_list")
         if sd is None:                               # walking the module tree costs ~0.6 ms: done once (reset by _apply)
             sd = list(self.parameters()) + list(self.buffers())
             self.__dict__["_tensor_list"] = sd
         key = (tuple(t._version for t in sd), tuple(t.data_ptr() for t in sd), self.training, self.gemm_mode, self.ff_mode, self.attn_mode)
-        if self._pack_cache is None or self._pack_cache[0] != key:
-            with torch.no_grad():
-                self._pack_cache = (key, policy_math.pack_weights(self))
-        return self._pack_cache[1]
+        cache = self._pack_cache
+        if cache is None or cache[0] != key:
+            cache = self._pack_cache = (key, {})
+        packed = cache[1]
+        with torch.no_grad():
+            if part in ("all", "encoder") and "enc_struct" not in packed:
+                packed.update(policy_math.pack_encoder_weights(self))
+            if part in ("all", "decoder") and "dec_struct" not in packed:
+                packed.update(policy_math.pack_decoder_weights(self))
+        return packed
 
     def _prepare_inputs(self, input):
         dev = self._device()
@@ -259,7 +266,7 @@ class AttentionModel(nn.Module):
         the paper's model, emb @ project_step_context.weight[:, :128]^T for the nets/AM.py variant."""
         L = _lib.lib()
         B, _, S = static.shape
-        pk = self.packed_weights()
+        pk = self.packed_weights("encoder")
         dev = static.device
         emb = torch.empty(B, S, 128, device=dev)
         kvl = torch.empty(B, S, 384, device=dev)
@@ -288,7 +295,7 @@ class AttentionModel(nn.Module):
         decode_type = decode_type or self.decode_type
         if forced is None and decode_type not in ("greedy", "sample"):
             raise AssertionError("Unknown decode type")           # nets/DRLModel.py:341
-        pk = self.packed_weights()
+        pk = self.packed_weights("decoder")
         phys = self._phys()
         static_xy = elev = None
         if isinstance(slope, _Elevations):            # coordinate mode: no [B,S,S] matrices (3-tuple input)

@@ -109,6 +109,14 @@ def pack_fused_encoder(model, layer_mats, node_mat, bn_folds):
 
 
 def pack_weights(model):
+    """both halves (encoder + decoder) in one dictionary"""
+    keep = pack_encoder_weights(model)
+    keep.update(pack_decoder_weights(model))
+    return keep
+
+
+def pack_encoder_weights(model):
+    """kernel-side layouts of the encoder / precompute weights -> {"enc_struct": EncoderWeights, tensors kept alive}"""
     keep = {}
     ew = _lib.EncoderWeights()
 
@@ -125,6 +133,7 @@ def pack_weights(model):
     ew.cust_b = dev("cust_b", model.init_embed.bias)
     layers = model.embedder.layers
     ew.n_layers = len(layers)
+    gemm_mode = int(getattr(model, "gemm_mode", 0))
     fused_layers, fused_bn = [], []
     for l, layer in enumerate(layers):
         att, bn1, ff, bn2 = layer[0].module, layer[1].normalizer, layer[2].module, layer[3].normalizer
@@ -150,34 +159,51 @@ def pack_weights(model):
             setattr(lw, name + "_lo", dev(f"l{l}.{name}_lo", lo))
     hi, lo = split_tf32(folded_node_projection(model))
     ew.node_proj_hi, ew.node_proj_lo = dev("node_proj_hi", hi), dev("node_proj_lo", lo)
-    ew.gemm_mode = int(getattr(model, "gemm_mode", 0))
+    ew.gemm_mode = gemm_mode
     ew.attn_mode = int(getattr(model, "attn_mode", 0))
     ew.node_proj = dev("node_proj", folded_node_projection(model).t())
     ew.fixed_ctx_w = dev("fixed_ctx_w", model.project_fixed_context.weight.t())
-    dw = _lib.DecoderWeights()
-    dw.policy = int(getattr(model, "policy", 0))
+    policy = int(getattr(model, "policy", 0))
     node_mat = folded_node_projection(model).float()
-    if dw.policy == 1:                                 # the AM step table rides behind the node projection (4th chunk)
+    if policy == 1:                                    # the AM step table rides behind the node projection (4th chunk)
         node_mat = torch.cat([node_mat, model.project_step_context.weight[:, :128].float()], 0)
     fw, fp, nchunks = pack_fused_encoder(model, fused_layers, node_mat, fused_bn)
     keep["fused_w"], keep["fused_params"] = fw, fp
     ew.fused_w = _lib.ptr(fw) if fw.is_cuda else None
     ew.fused_params = _lib.ptr(fp) if fp.is_cuda else None
     ew.fused_node_chunks = nchunks
-    if dw.policy == 1:                                 # nets/AM.py:90: project_step_context = [emb columns | load column]
+    if policy == 1:                                    # nets/AM.py:90: project_step_context = [emb columns | load column]
         Ws = model.project_step_context.weight
         ew.step_proj = dev("step_proj", Ws[:, :128].t())
         hi, lo = split_tf32(Ws[:, :128])
         ew.step_proj_hi, ew.step_proj_lo = dev("step_proj_hi", hi), dev("step_proj_lo", lo)
-        dw.am_w_load = dev("am_w_load", Ws[:, 128])
+    keep["enc_struct"] = ew
+    return keep
+
+
+def pack_decoder_weights(model):
+    """kernel-side layouts of the decoder (FF_tour / step-context) weights -> {"dec_struct": DecoderWeights, tensors}.
+    The REINFORCE step needs only this half every optimizer step (its encoder runs through encode_torch)."""
+    keep = {}
+
+    def dev(name, t):
+        t = t.detach().float().contiguous()
+        keep[name] = t
+        return _lib.ptr(t) if t.is_cuda else None
+
+    dw = _lib.DecoderWeights()
+    dw.policy = int(getattr(model, "policy", 0))
+    if dw.policy == 1:
+        dw.am_w_load = dev("am_w_load", model.project_step_context.weight[:, 128])
         dw.ff_mode = 1
-        keep["enc_struct"], keep["dec_struct"] = ew, dw
+        keep["dec_struct"] = dw
         return keep
     dw.w1_veh = dev("w1_veh", folded_tour_weight(model).t())
     dw.w1_max = dev("w1_max", model.FF_tour[0].weight[:, 128:].t())
     dw.b1 = dev("b1", model.FF_tour[0].bias)
     dw.w2 = dev("w2", model.FF_tour[2].weight.t())
     dw.b2 = dev("b2", model.FF_tour[2].bias)
+
     def dev_raw(name, t):                              # fp16 planes travel as they are
         keep[name] = t
         return _lib.ptr(t) if t.is_cuda else None
@@ -186,7 +212,7 @@ def pack_weights(model):
     hi, lo, inv = split_f16(model.FF_tour[2].weight)
     dw.w2_hi, dw.w2_lo, dw.w2_inv_scale = dev_raw("w2_hi", hi), dev_raw("w2_lo", lo), inv
     dw.ff_mode = int(getattr(model, "ff_mode", 0))
-    keep["enc_struct"], keep["dec_struct"] = ew, dw
+    keep["dec_struct"] = dw
     return keep
 
 
@@ -270,18 +296,11 @@ class local_batch_norm:
 
 def _batch_norm(bn, x, training, force_global=False):
     import torch.distributed as dist
-    if training and not _LOCAL_BN[0] and dist.is_available() and dist.is_initialized() and \
-            (dist.get_world_size() > 1 or force_global):
-        if x.is_cuda:
-            # CUDA: the same global-batch statistics through PyTorch's fused synchronized-BatchNorm kernels
-            # (batch_norm_stats / gather_stats_with_counts / elemt / backward_reduce / backward_elemt): one all-gather
-            # forward, one all-reduce backward, no chain of elementwise passes over [B*S,128]
-            from torch.nn.modules._functions import SyncBatchNorm as _SyncBN
-            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
-            with torch.no_grad():
-                bn.num_batches_tracked += 1
-            return _SyncBN.apply(x.contiguous(), bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, m,
-                                 dist.group.WORLD, dist.get_world_size())
+    multi = dist.is_available() and dist.is_initialized() and (dist.get_world_size() > 1 or force_global) and not _LOCAL_BN[0]
+    if training and x.is_cuda and x.shape[1] == 128 and x.dtype == torch.float32:
+        # product path: the two-phase BatchNorm kernels; one all-reduce of the fp64 sums per pass when sharded over ranks
+        return BatchNormTrain.apply(x, bn.weight, bn.bias, bn, multi)
+    if training and multi:
         return _GlobalBatchNorm.apply(x, bn.weight, bn.bias, bn)
     return bn(x)
 
@@ -333,18 +352,35 @@ def _affine_identity(dev, n):
     return _AFFINE_ID[key]
 
 
-def tc_gemm(x, W, bias=None, resid=None, relu=False):
-    """((x @ W^T + bias) [relu] + resid) on the tcgen05 3xTF32 GEMM of csrc/evrp_tc_gemm.cu (evrp_gemm_3xtf32).
-    x [M,K], W [N,K] (nn.Linear layout), fp32 CUDA.  Epilogues the kernel does not instantiate are finished in torch."""
-    x = x.contiguous(); W = W.detach().contiguous()
+def split_tf32_planes(W):
+    """CUDA weight [rows, cols] with ANY strides (a transposed view for the input-gradient product, a column slice) ->
+    dense TF32 (hi, lo) planes in ONE kernel (evrp_split_tf32; same rounding as split_tf32)."""
+    W = W.detach()
+    assert W.is_cuda and W.dtype == torch.float32 and W.dim() == 2
+    rows, cols = W.shape
+    hi = torch.empty(rows, cols, device=W.device, dtype=torch.float32)
+    lo = torch.empty_like(hi)
+    _lib.check(_lib.lib().evrp_split_tf32(_lib.C.c_void_p(W.data_ptr()), rows, cols, W.stride(0), W.stride(1), _lib.ptr(hi),
+                                          _lib.ptr(lo), _lib.stream_ptr()), "evrp_split_tf32")
+    return hi, lo
+
+
+def tc_gemm(x, W, bias=None, resid=None, relu=False, aux=None, aux_w=None):
+    """((x @ W^T + bias + aux @ aux_w^T) [relu] + resid) on the tcgen05 3xTF32 GEMM of csrc/evrp_tc_gemm.cu
+    (evrp_gemm_3xtf32).  x [M,K], W [N,K] (nn.Linear layout, any strides), aux [M,3], aux_w [N,3], fp32 CUDA.
+    Epilogues the kernel does not instantiate are finished in torch."""
+    x = x.contiguous()
     M, K = x.shape
     N = W.shape[0]
     assert W.shape[1] == K and N % 128 == 0 and K % 32 == 0, (tuple(x.shape), tuple(W.shape))
-    hi, lo = split_tf32(W)
+    hi, lo = split_tf32_planes(W)
     y = torch.empty(M, N, device=x.device, dtype=torch.float32)
     one, zero = _affine_identity(x.device, N)
     epi, post_bias, post_relu, post_resid = 0, None, False, None
-    if bias is not None and relu and resid is None and K == 128:
+    if aux is not None:
+        assert bias is not None and relu and resid is None and K == 128 and aux.shape == (M, 3) and aux_w.shape == (N, 3)
+        epi = 1 | 2 | 16
+    elif bias is not None and relu and resid is None and K == 128:
         epi = 1 | 2
     elif bias is None and not relu and resid is not None and K == 128:
         epi = 4 | 8
@@ -354,9 +390,12 @@ def tc_gemm(x, W, bias=None, resid=None, relu=False):
         post_bias, post_relu, post_resid = bias, relu, resid
     b = bias.detach().contiguous() if (epi & 1) else None
     r = resid.detach().contiguous() if (epi & 4) else None
+    a = aux.detach().contiguous() if (epi & 16) else None
+    aw = aux_w.detach().t().contiguous() if (epi & 16) else None          # [3][N]
     _lib.check(_lib.lib().evrp_gemm_3xtf32(epi, _lib.ptr(x), K, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(y), N, M, N, K,
                                            _lib.ptr(b), _lib.ptr(r), N, _lib.ptr(one) if epi & 8 else None,
-                                           _lib.ptr(zero) if epi & 8 else None, _lib.stream_ptr()), "evrp_gemm_3xtf32")
+                                           _lib.ptr(zero) if epi & 8 else None, _lib.ptr(a), _lib.ptr(aw),
+                                           _lib.stream_ptr()), "evrp_gemm_3xtf32")
     if post_bias is not None:
         y = y + post_bias
     if post_relu:
@@ -366,33 +405,152 @@ def tc_gemm(x, W, bias=None, resid=None, relu=False):
     return y
 
 
+_WGRAD_WS = {}
+
+
+def tc_wgrad(gy, x, want_bias=False, aux=None):
+    """gW [N,K] = gy[M,N]^T @ x[M,K] on the tcgen05 split-K weight-gradient kernel (csrc/evrp_wgrad.cu,
+    evrp_wgrad_3xtf32; fp32-faithful 3xTF32, deterministic reduction).  Also returns gaux [(1 + n_aux), N]: row 0 = the bias
+    gradient gy.sum(0), rows 1.. = aux^T gy for aux [M, n_aux <= 3] (None when neither is wanted)."""
+    gy, x = gy.contiguous(), x.contiguous()
+    M, N = gy.shape
+    K = x.shape[1]
+    L = _lib.lib()
+    key = str(gy.device)
+    ws = _WGRAD_WS.get(key)
+    if ws is None:
+        ws = _WGRAD_WS[key] = torch.empty(L.evrp_wgrad_workspace_bytes(), dtype=torch.uint8, device=gy.device)
+    n_aux = 0 if aux is None else aux.shape[1]
+    gW = torch.empty(N, K, device=gy.device, dtype=torch.float32)
+    gaux = torch.empty(1 + n_aux, N, device=gy.device, dtype=torch.float32) if (want_bias or n_aux) else None
+    a = aux.detach().contiguous() if n_aux else None
+    _lib.check(L.evrp_wgrad_3xtf32(_lib.ptr(gy), N, N, _lib.ptr(x), K, K, M, _lib.ptr(a), n_aux, _lib.ptr(gW), _lib.ptr(gaux), 0,
+                                   _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "evrp_wgrad_3xtf32")
+    return gW, gaux
+
+
 class TCLinear(torch.autograd.Function):
-    """y = ((x @ W^T + bias) [relu] + resid): the forward product and the input-gradient product run on the tcgen05
-    3xTF32 GEMM (fp32-faithful); the weight gradient (contraction over all B*S rows) is a cuBLAS fp32 GEMM."""
+    """y = ((x @ W^T + bias + aux @ aux_w^T) [relu] + resid): forward product and input-gradient product on the tcgen05
+    3xTF32 GEMM, weight / bias / aux_w gradients on the tcgen05 split-K weight-gradient kernel (all fp32-faithful).
+    aux [M,3] (the vehicle scalars of FF_tour.0) carries no gradient."""
 
     @staticmethod
-    def forward(ctx, x, W, bias, resid, relu):
-        y = tc_gemm(x.detach(), W, bias, resid.detach() if resid is not None else None, relu)
-        ctx.save_for_backward(x, W, y if relu else None)
+    def forward(ctx, x, W, bias, resid, relu, aux=None, aux_w=None):
+        y = tc_gemm(x.detach(), W, bias, resid.detach() if resid is not None else None, relu, aux, aux_w)
+        ctx.save_for_backward(x, W, y if relu else None, aux)
         ctx.flags = (bias is not None, resid is not None, relu)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, W, y = ctx.saved_tensors
+        x, W, y, aux = ctx.saved_tensors
         has_bias, has_resid, relu = ctx.flags
         gy = gy.contiguous()
+        g = gy
         if relu:
-            gy = gy * (y > 0)
+            g = torch.empty_like(gy)
+            _lib.check(_lib.lib().evrp_relu_mask(_lib.ptr(gy), _lib.ptr(y), _lib.ptr(g), gy.numel(), _lib.stream_ptr()),
+                       "evrp_relu_mask")
         N, K = W.shape
-        gx = gW = gb = None
+        gx = gW = gb = gaw = None
         if ctx.needs_input_grad[0]:
-            gx = tc_gemm(gy, W.t()) if (K % 128 == 0 and N % 32 == 0) else gy @ W
-        if ctx.needs_input_grad[1]:
-            gW = gy.t() @ x
-        if has_bias and ctx.needs_input_grad[2]:
-            gb = gy.sum(0)
-        return gx, gW, gb, (gy if has_resid else None), None
+            gx = tc_gemm(g, W.t()) if (K % 128 == 0 and N % 32 == 0) else g @ W
+        want_b = has_bias and ctx.needs_input_grad[2]
+        want_aw = aux is not None and ctx.needs_input_grad[6]
+        if ctx.needs_input_grad[1] or want_b or want_aw:
+            if N % 128 == 0 and K % 128 == 0:
+                gW, gaux = tc_wgrad(g, x, want_b, aux if want_aw else None)
+                if want_b:
+                    gb = gaux[0]
+                if want_aw:
+                    gaw = gaux[1:].t()
+            else:
+                gW = g.t() @ x
+                gb = g.sum(0) if want_b else None
+                gaw = g.t() @ aux if want_aw else None
+        return gx, gW, gb, (gy if has_resid else None), None, None, gaw
+
+
+class BatchNormTrain(torch.autograd.Function):
+    """Train-mode BatchNorm1d(128) on the kernels of csrc/evrp_train.cu (nets/GraphEncoder.py:142-150): fp64 sufficient
+    statistics [sum x, sum x^2, n]; when instances are sharded over ranks ONE all-reduce of these 257 doubles makes them the
+    statistics of the GLOBAL batch (backward: one all-reduce of [sum g, sum g * xhat]).  Same outputs, gradients and
+    running-statistics update as nn.BatchNorm1d on the concatenated batch."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, bn, sync):
+        import torch.distributed as dist
+        L = _lib.lib()
+        x = x.contiguous()
+        M = x.shape[0]
+        sums = torch.empty(257, device=x.device, dtype=torch.float64)
+        _lib.check(L.evrp_bn_stats(_lib.ptr(x), M, _lib.ptr(sums), _lib.stream_ptr()), "evrp_bn_stats")
+        if sync:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked + 1)
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+        save = torch.empty(257, device=x.device, dtype=torch.float32)
+        y = torch.empty_like(x)
+        w, b = weight.detach().contiguous(), bias.detach().contiguous()
+        _lib.check(L.evrp_bn_apply(_lib.ptr(x), M, _lib.ptr(sums), _lib.ptr(w), _lib.ptr(b), float(bn.eps), float(m),
+                                   _lib.ptr(bn.running_mean), _lib.ptr(bn.running_var), _lib.ptr(save), _lib.ptr(y),
+                                   _lib.stream_ptr()), "evrp_bn_apply")
+        ctx.save_for_backward(x, w, save)
+        ctx.sync = sync
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        import torch.distributed as dist
+        L = _lib.lib()
+        x, w, save = ctx.saved_tensors
+        g = g.contiguous()
+        M = x.shape[0]
+        sums = torch.empty(256, device=x.device, dtype=torch.float64)
+        _lib.check(L.evrp_bn_backward_reduce(_lib.ptr(x), _lib.ptr(g), M, _lib.ptr(save), _lib.ptr(sums), _lib.stream_ptr()),
+                   "evrp_bn_backward_reduce")
+        local = sums.float()                                   # this rank's share: summed with the other gradients later
+        if ctx.sync:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        gx = torch.empty_like(x)
+        _lib.check(L.evrp_bn_backward_apply(_lib.ptr(x), _lib.ptr(g), M, _lib.ptr(save), _lib.ptr(w), _lib.ptr(sums), _lib.ptr(gx),
+                                            _lib.stream_ptr()), "evrp_bn_backward_apply")
+        return gx, local[128:], local[:128], None, None
+
+
+class RouteContext(torch.autograd.Function):
+    """(run_max [B,T,128], base [B,T,128]) of the teacher-forced decoder: running max of the visited embeddings (zeros before
+    the first pick, nets/DRLModel.py:207-224) and fixed_ctx + emb[now] (:394) for all T recorded steps in one kernel; the
+    backward scatters the gradients to the node holding the running max / the current node (csrc/evrp_train.cu)."""
+
+    @staticmethod
+    def forward(ctx, emb, fixed, pi, want_run_max):
+        emb, fixed, pi = emb.contiguous(), fixed.contiguous(), pi.contiguous()
+        B, S, d = emb.shape
+        T = pi.shape[1]
+        run_max = torch.empty(B, T, d, device=emb.device, dtype=torch.float32)
+        base = torch.empty(B, T, d, device=emb.device, dtype=torch.float32)
+        _lib.check(_lib.lib().evrp_route_context_forward(_lib.ptr(emb), _lib.ptr(fixed), _lib.ptr(pi), B, T, S, _lib.ptr(run_max),
+                                                         _lib.ptr(base), _lib.stream_ptr()), "evrp_route_context_forward")
+        ctx.save_for_backward(emb, pi)
+        ctx.want_run_max = want_run_max
+        return run_max, base
+
+    @staticmethod
+    def backward(ctx, g_rm, g_base):
+        emb, pi = ctx.saved_tensors
+        B, S, d = emb.shape
+        T = pi.shape[1]
+        g_emb = torch.empty_like(emb)
+        g_fixed = torch.empty(B, d, device=emb.device, dtype=torch.float32)
+        grm = g_rm.contiguous() if (ctx.want_run_max and g_rm is not None) else None
+        if g_base is None:
+            g_base = torch.zeros(B, T, d, device=emb.device)
+        _lib.check(_lib.lib().evrp_route_context_backward(_lib.ptr(emb), _lib.ptr(pi), _lib.ptr(grm), _lib.ptr(g_base.contiguous()),
+                                                          B, T, S, _lib.ptr(g_emb), _lib.ptr(g_fixed), _lib.stream_ptr()),
+                   "evrp_route_context_backward")
+        return g_emb, g_fixed, None, None
 
 
 def self_attention_torch(qkv, Hh=8):
@@ -476,22 +634,26 @@ def teacher_forced_ll(model, emb, kvl, fixed, pi, mask_bits, veh, steps):
     evaluated as one batch."""
     B, T = pi.shape
     S, d, Hh = emb.shape[1], emb.shape[2], model.n_heads
-    now = torch.cat([torch.zeros_like(pi[:, :1]), pi[:, :-1]], 1)
-    emb_now = emb.gather(1, now[..., None].expand(B, T, d))
-    if getattr(model, "policy", 0) == 1:                                   # nets/AM.py:336-337,352-377
-        q = fixed[:, None] + model.project_step_context(torch.cat([emb_now, veh[..., 0:1]], -1))
-    else:
-        idx = pi[..., None].expand(B, T, d)
-        visited = emb.gather(1, idx)                                       # emb[pi_t]
-        run_max = torch.cummax(visited, 1)[0]
-        run_max = torch.cat([torch.zeros_like(run_max[:, :1]), run_max[:, :-1]], 1)    # zeros before first pick
+    policy = getattr(model, "policy", 0)
+    if emb.is_cuda and d == 128 and policy == 0:
+        # product path: running max + fixed_ctx + emb[now] of all T steps from ONE kernel (RouteContext), FF_tour on the tcgen05
+        # GEMM with the vehicle term, bias and ReLU in its epilogue
+        run_max, base = RouteContext.apply(emb, fixed, pi, True)
         W1 = model.FF_tour[0]
-        if emb.is_cuda and d == 128:                                       # FF_tour over all B*T steps on the tcgen05 GEMM
-            hm = TCLinear.apply(run_max.reshape(B * T, d), W1.weight[:, 128:], None, None, False)
-            h1 = torch.relu(Fn.linear(veh, folded_tour_weight(model)).view(B * T, -1) + hm + W1.bias)
-            base = (fixed[:, None] + emb_now).reshape(B * T, d)
-            q = TCLinear.apply(h1, model.FF_tour[2].weight, model.FF_tour[2].bias, base, False).view(B, T, d)
+        h1 = TCLinear.apply(run_max.view(B * T, d), W1.weight[:, 128:], W1.bias, None, True,
+                            veh.reshape(B * T, 3), folded_tour_weight(model))
+        q = TCLinear.apply(h1, model.FF_tour[2].weight, model.FF_tour[2].bias, base.view(B * T, d), False).view(B, T, d)
+    else:
+        now = torch.cat([torch.zeros_like(pi[:, :1]), pi[:, :-1]], 1)
+        emb_now = emb.gather(1, now[..., None].expand(B, T, d))
+        if policy == 1:                                                    # nets/AM.py:336-337,352-377
+            q = fixed[:, None] + model.project_step_context(torch.cat([emb_now, veh[..., 0:1]], -1))
         else:
+            idx = pi[..., None].expand(B, T, d)
+            visited = emb.gather(1, idx)                                       # emb[pi_t]
+            run_max = torch.cummax(visited, 1)[0]
+            run_max = torch.cat([torch.zeros_like(run_max[:, :1]), run_max[:, :-1]], 1)    # zeros before first pick
+            W1 = model.FF_tour[0]
             h1 = torch.relu(Fn.linear(veh, folded_tour_weight(model)) + Fn.linear(run_max, W1.weight[:, 128:]) + W1.bias)
             ctx = model.FF_tour[2](h1)
             q = (fixed[:, None] + ctx) + emb_now

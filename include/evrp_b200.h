@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 16
+#define EVRP_ABI_VERSION 17
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -281,12 +281,62 @@ int evrp_self_attention_backward(const float* qkv, const float* heads, const flo
 /* ------------------------------------------------------------------------------------------------
  * (7) the encoder's tcgen05 GEMM on its own (training path):  C[M,N] = epilogue( A[M,K] @ W[N,K]^T ), fp32-faithful
  *     3xTF32 (W given as TF32 hi / lo planes in nn.Linear layout [out][in]).  N % 128 == 0.  epilogue bits: 1 bias,
- *     2 ReLU, 4 residual, 8 per-column affine; supported: 0 (any K % 32 == 0), 1|2 and 4|8 (K == 128), 1|4|8
- *     (K == 512):  C = ((A W^T + bias) [relu] + resid) * scale + shift.
+ *     2 ReLU, 4 residual, 8 per-column affine, 16 auxiliary rank-3 term; supported: 0 (any K % 32 == 0), 1|2, 4|8 and
+ *     1|2|16 (K == 128), 1|4|8 (K == 512):  C = ((A W^T + bias + aux aux_w) [relu] + resid) * scale + shift with
+ *     aux [M,3] row-major and aux_w [3][N] (the vehicle-scalar term of FF_tour.0, nets/DRLModel.py:215-235).
+ *     evrp_split_tf32 builds the planes from a weight with arbitrary strides (a transposed view for the input-gradient
+ *     product): hi = rna_tf32(w), lo = rna_tf32(w - hi), dense [rows][cols].
  * ---------------------------------------------------------------------------------------------- */
 int evrp_gemm_3xtf32(int epilogue, const float* A, int lda, const float* W_hi, const float* W_lo, float* C, int ldc,
                      int M, int N, int K, const float* bias, const float* resid, int ldr, const float* scale,
-                     const float* shift, void* stream);
+                     const float* shift, const float* aux, const float* aux_w, void* stream);
+int evrp_split_tf32(const float* w, int rows, int cols, long long stride_r, long long stride_c, float* hi, float* lo,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (8) weight gradients of the REINFORCE backward (trainer.py:122 loss.backward() through the nn.Linear / W_query /
+ *     W_key / W_val / W_out products of nets/GraphEncoder.py:55-118,153-170 and FF_tour nets/DRLModel.py:233-237):
+ *     gW [N_out, K_in] = gy[M, N_out]^T x[M, K_in], the contraction over all M = B*S (or B*T) rows, on tcgen05 (3xTF32,
+ *     operands transposed on chip: x planes in tensor memory, gy planes swizzled in shared memory), split over M with a
+ *     deterministic second-pass reduction.  gaux [(1 + n_aux), N_out] (optional): row 0 = column sums of gy (the bias
+ *     gradient), row 1 + i = sum_m aux[m][i] * gy[m][:] (gradient of a rank-n_aux side term, n_aux <= 3).
+ *     accumulate != 0 adds to gW / gaux.  N_out and K_in are multiples of 128; ldg, ldx multiples of 4.
+ * ---------------------------------------------------------------------------------------------- */
+size_t evrp_wgrad_workspace_bytes(void);
+int evrp_wgrad_3xtf32(const float* gy, int ldg, int N_out, const float* x, int ldx, int K_in, int M, const float* aux,
+                      int n_aux, float* gW, float* gaux, int accumulate, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (9) train-mode BatchNorm1d(128) of the encoder (nets/GraphEncoder.py:142-150, batch statistics + running-stat update)
+ *     over x [M,128], two phases so that ONE all-reduce between them turns the statistics into those of the global
+ *     batch when instances are sharded over ranks:
+ *       evrp_bn_stats            sums [257] fp64 = sum x | sum x^2 | M        (zeroed by the call)
+ *       evrp_bn_apply            y = (x - mean) * invstd * weight + bias from the (all-reduced) sums; save [257] fp32 =
+ *                                mean | invstd | n for the backward; running_mean / running_var (nullable) updated with
+ *                                `momentum` and the unbiased variance like nn.BatchNorm1d
+ *       evrp_bn_backward_reduce  sums [256] fp64 = sum g | sum g * xhat       (zeroed by the call; the local values are
+ *                                the weight / bias gradients of this rank)
+ *       evrp_bn_backward_apply   gx = weight * invstd * (g - sum_g / n - xhat * sum_gxhat / n) from the (all-reduced) sums
+ * ---------------------------------------------------------------------------------------------- */
+int evrp_bn_stats(const float* x, int M, double* sums, void* stream);
+int evrp_bn_apply(const float* x, int M, const double* sums, const float* weight, const float* bias, float eps,
+                  float momentum, float* running_mean, float* running_var, float* save, float* y, void* stream);
+int evrp_bn_backward_reduce(const float* x, const float* g, int M, const float* save, double* sums, void* stream);
+int evrp_bn_backward_apply(const float* x, const float* g, int M, const float* save, const float* weight,
+                           const double* sums, float* gx, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (10) step-query assembly of the teacher-forced decoder for all T recorded steps (nets/DRLModel.py:203-237,394):
+ *      run_max[b,t,:] = max over the embeddings picked at steps < t (zeros at t = 0), base[b,t,:] = fixed_ctx[b,:] +
+ *      emb[b, now_t, :] with now_0 = 0 (depot), now_t = pi[b,t-1]; and the backward: grad_emb [B,S,128] (written) and
+ *      grad_fixed [B,128] from grad_run_max (nullable) and grad_base.  evrp_relu_mask: out = g * (y > 0), n % 4 == 0.
+ * ---------------------------------------------------------------------------------------------- */
+int evrp_route_context_forward(const float* emb, const float* fixed_ctx, const int64_t* pi, int B, int T, int S,
+                               float* run_max, float* base, void* stream);
+int evrp_route_context_backward(const float* emb, const int64_t* pi, const float* grad_run_max, const float* grad_base,
+                                int B, int T, int S, float* grad_emb, float* grad_fixed, void* stream);
+int evrp_relu_mask(const float* g, const float* y, float* out, long long n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -827,6 +827,112 @@ def test_tc_linear_matches_torch(evrp, M, K, N, bias, resid, relu):
         assert float((g.double() - wv.double()).norm() / wv.double().norm()) < 1e-5     # fp32 noise of contractions up to 2600 long
 
 
+@pytest.mark.parametrize("M,N,K,n_aux", [
+    (1000, 128, 128, 0), (4133, 384, 128, 0), (2600, 512, 128, 3), (515, 128, 512, 0), (31, 128, 128, 1), (20000, 128, 384, 2),
+    (108544, 512, 128, 3)])
+def test_wgrad_kernel_matches_fp64(evrp, M, N, K, n_aux):
+    """csrc/evrp_wgrad.cu (tcgen05 split-K weight gradient, operands transposed on chip, 3xTF32) against the fp64
+    contraction: every tile count the training path uses, ragged M (partial 32-row block, fewer blocks than CTAs), the
+    bias row and the auxiliary rank-3 rows; deterministic (two calls are bit-identical)"""
+    from evrp_b200 import policy_math as PM
+    gen = torch.Generator(device="cpu").manual_seed(M + N)
+    gy = torch.randn(M, N, generator=gen).cuda()
+    x = (torch.randn(M, K, generator=gen) * 1.7 + 0.3).cuda()
+    aux = torch.rand(M, n_aux, generator=gen).cuda() if n_aux else None
+    gW, gaux = PM.tc_wgrad(gy, x, True, aux)
+    gW2, gaux2 = PM.tc_wgrad(gy, x, True, aux)
+    assert torch.equal(gW, gW2) and torch.equal(gaux, gaux2)
+    ref = gy.double().t() @ x.double()
+    assert float((gW.double() - ref).norm() / ref.norm()) < 5e-6          # fp32 accumulation over up to 2,200 rows per slice
+    scale = float((gy.double().abs().t() @ x.double().abs()).max())          # magnitude of the summed terms
+    assert float((gW.double() - ref).abs().max()) < 2e-6 * scale
+    refb = gy.double().sum(0)
+    assert float((gaux[0].double() - refb).abs().max()) < 1e-5 * float(gy.double().abs().sum(0).max())
+    if n_aux:
+        refa = aux.double().t() @ gy.double()
+        assert float((gaux[1:].double() - refa).norm() / refa.norm()) < 1e-5
+
+
+def test_tc_linear_with_vehicle_term_matches_torch(evrp):
+    """FF_tour.0 of the teacher-forced decoder as ONE GEMM (bias + rank-3 vehicle term + ReLU in the epilogue) and its
+    backward (input gradient, weight / bias / vehicle-weight gradients from the weight-gradient kernel) against fp64"""
+    from evrp_b200 import policy_math as PM
+    gen = torch.Generator(device="cpu").manual_seed(11)
+    M = 3001
+    x = torch.randn(M, 128, generator=gen).cuda().requires_grad_(True)
+    Wfull = (torch.randn(512, 256, generator=gen) / 16).cuda().requires_grad_(True)
+    b = torch.randn(512, generator=gen).cuda().requires_grad_(True)
+    aux = torch.rand(M, 3, generator=gen).cuda()
+    aw = torch.randn(512, 3, generator=gen).cuda().requires_grad_(True)
+    w = torch.randn(M, 512, generator=gen).cuda()
+    y = PM.TCLinear.apply(x, Wfull[:, 128:], b, None, True, aux, aw)
+    (y * w).sum().backward()
+    got = [t.grad.clone() for t in (x, Wfull, b, aw)]
+    for t in (x, Wfull, b, aw):
+        t.grad = None
+    ref = torch.relu(x.double() @ Wfull.double()[:, 128:].t() + b.double() + aux.double() @ aw.double().t())
+    (ref * w.double()).sum().backward()
+    assert float((y.double() - ref).abs().max()) < 6e-6 * max(1.0, float(ref.abs().max()))
+    for g, t in zip(got, (x, Wfull, b, aw)):
+        assert float((g.double() - t.grad.double()).norm() / t.grad.double().norm()) < 1e-5
+
+
+@pytest.mark.parametrize("M", [777, 108544])
+def test_batch_norm_train_kernels_match_batchnorm1d(evrp, M):
+    """csrc/evrp_train.cu bn_* (two-phase train-mode BatchNorm, fp64 sufficient statistics) against nn.BatchNorm1d: outputs,
+    input / weight / bias gradients, running statistics, num_batches_tracked"""
+    from evrp_b200 import policy_math as PM
+    torch.manual_seed(3)
+    x = (torch.randn(M, 128, device="cuda") * 2 + 0.5).requires_grad_(True)
+    w = torch.randn(M, 128, device="cuda")
+    a, b = torch.nn.BatchNorm1d(128).cuda().train(), torch.nn.BatchNorm1d(128).cuda().train()
+    with torch.no_grad():
+        for bn in (a, b):
+            bn.weight.copy_(torch.linspace(0.5, 1.5, 128)); bn.bias.copy_(torch.linspace(-0.2, 0.2, 128))
+    for _ in range(2):                                          # two steps: the running statistics accumulate
+        x.grad = None; a.zero_grad(); b.zero_grad()
+        ya = PM._batch_norm(a, x, True)
+        (ya * w).sum().backward()
+        ga, gwa, gba = x.grad.clone(), a.weight.grad.clone(), a.bias.grad.clone()
+        x.grad = None
+        yb = b(x)
+        (yb * w).sum().backward()
+        ref64 = torch.nn.functional.batch_norm(x.detach().double(), None, None, b.weight.double(), b.bias.double(), True)
+        assert float((ya.double() - ref64).abs().max()) <= float((yb.double() - ref64).abs().max()) + 2e-6
+        assert torch.allclose(ya, yb, atol=2e-5) and torch.allclose(ga, x.grad, atol=2e-5, rtol=1e-4)
+        assert float((gwa - b.weight.grad).norm() / b.weight.grad.norm()) < 1e-4
+        assert float((gba - b.bias.grad).norm() / b.bias.grad.norm()) < 1e-4
+        assert torch.allclose(a.running_mean, b.running_mean, atol=1e-6) and torch.allclose(a.running_var, b.running_var, rtol=1e-5)
+    assert int(a.num_batches_tracked) == int(b.num_batches_tracked) == 2
+
+
+@pytest.mark.parametrize("B,T,S", [(5, 37, 26), (64, 157, 106), (3, 300, 128)])
+def test_route_context_kernels_match_torch(evrp, B, T, S):
+    """csrc/evrp_train.cu route_context_* against the plain-PyTorch statement (gather + cummax + shift, nets/DRLModel.py:
+    207-224,394): run_max / base bit-equal, gradients to emb / fixed (scatter to the node holding the running max)"""
+    from evrp_b200 import policy_math as PM
+    gen = torch.Generator(device="cpu").manual_seed(B * T)
+    emb = torch.randn(B, S, 128, generator=gen).cuda().requires_grad_(True)
+    fixed = torch.randn(B, 128, generator=gen).cuda().requires_grad_(True)
+    pi = torch.randint(0, S, (B, T), generator=gen).cuda()
+    pi[:, T // 2:] = torch.where(torch.rand(B, T - T // 2, generator=gen).cuda() < 0.3, 0, pi[:, T // 2:])   # depot revisits
+    w1, w2 = torch.randn(B, T, 128, generator=gen).cuda(), torch.randn(B, T, 128, generator=gen).cuda()
+    rm, base = PM.RouteContext.apply(emb, fixed, pi, True)
+    ((rm * w1).sum() + (base * w2).sum()).backward()
+    ge, gf = emb.grad.clone(), fixed.grad.clone()
+    emb.grad = None; fixed.grad = None
+    now = torch.cat([torch.zeros_like(pi[:, :1]), pi[:, :-1]], 1)
+    emb_now = emb.gather(1, now[..., None].expand(B, T, 128))
+    visited = emb.gather(1, pi[..., None].expand(B, T, 128))
+    rm_ref = torch.cummax(visited, 1)[0]
+    rm_ref = torch.cat([torch.zeros_like(rm_ref[:, :1]), rm_ref[:, :-1]], 1)
+    base_ref = fixed[:, None] + emb_now
+    ((rm_ref * w1).sum() + (base_ref * w2).sum()).backward()
+    assert torch.equal(rm, rm_ref) and torch.equal(base, base_ref)
+    assert float((ge - emb.grad).abs().max()) < 1e-4 * float(emb.grad.abs().max())
+    assert float((gf - fixed.grad).abs().max()) < 1e-4 * float(fixed.grad.abs().max())
+
+
 def test_global_batch_norm_cuda_path_matches_batchnorm1d(evrp):
     """the multi-rank BatchNorm path of the training forward (global-batch statistics) on CUDA, exercised through a
     one-rank NCCL group: outputs, gradients and running statistics equal nn.BatchNorm1d on the same batch"""
