@@ -17,7 +17,7 @@ roofline   rollout kernel, HBM-bound.  `achieved` = the bytes the launch NEEDS (
            them) / CUDA-event duration of the kernel launch; `frac` = achieved / MEASURED_PEAKS.json hbm_gbs.  SURVEY
            §8d's all-node model ((1568*S+2048) B per instance-step) is printed beside it as `allnode_*` (it counts the
            masked nodes too and therefore exceeds the peak).  `traffic` = ncu dram bytes of one launch, reported only
-           when profiles/rollout_traffic.json was captured with THIS build (.so hash), batch and graph size.
+           when profiles/rollout_traffic.json was captured with THIS kernel source (hash), batch and graph size.
 cpu_baseline  the PATCHED REFERENCE itself (oracle/_ref, torch on the host cores; kind "reference"), or the numpy
            oracle port where the copy is absent (kind "port"); bounded sample, child process without CUDA
 reference_gpu  the patched reference as eager PyTorch on the same B200, batch 512
@@ -84,11 +84,19 @@ def cpu_port_rate(N, sample, threads=None):
     return sample / dt, cores, dt, int(o["pi"].shape[1])
 
 
-def lib_sha256():
+ROLLOUT_SOURCES = ("evrp_decode_tc.cu", "evrp_tc.cuh", "evrp_common.cuh")
+
+
+def rollout_source_sha256():
+    """hash of the rollout kernel's SOURCE files (the ncu traffic figure under profiles/ is tied to this: it stays valid when
+    other kernels of the library change and goes stale when this kernel does)"""
     import hashlib
-    import evrp_b200
-    with open(evrp_b200._lib.LIB_PATH, "rb") as f:
-        return hashlib.sha256(f.read()).hexdigest()
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "drl-energy-optimal-routing-for-electric-vehicles_b200", "csrc")
+    for name in ROLLOUT_SOURCES:
+        with open(os.path.join(d, name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
 
 
 def host_threads():
@@ -499,9 +507,11 @@ def main():
                               "kernel_share_of_step": t_roll_ms / (1e3 * tsec.item() / a.train_steps),
                               "needed_bytes_per_launch": t_need},
                  "unit": "step/s", "per_gpu_batch": tb, "global_batch": tb * world, "decode_steps": int(out["T"]),
-                 "includes": "train-mode encoder (attention core on evrp_attn_train.cu, projections / FF / BatchNorm through "
-                             "autograd) + sampled rollout kernel + decoder log-prob forward / backward kernels "
-                             "(evrp_logp.cu) + fused loss kernel + flat NCCL gradient all-reduce + clip + Adam"}
+                 "includes": "train-mode encoder (projections / FF: tcgen05 3xTF32 GEMM forward + input gradient, tcgen05 split-K "
+                             "weight-gradient kernel evrp_wgrad.cu; attention core evrp_attn_train.cu; two-phase BatchNorm "
+                             "kernels evrp_train.cu) + sampled rollout kernel + step-query assembly kernels + decoder "
+                             "log-prob forward / backward kernels (evrp_logp.cu) + fused loss kernel + flat NCCL gradient "
+                             "all-reduce + clip + Adam"}
     if rank == 0:
         pk, pk_src = peaks()
         kern_s = roll_avg_ms * 1e-3
@@ -511,7 +521,7 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "rollout_traffic.json")) as f:
                 tj = json.load(f)
-            if tj.get("lib_sha256") == lib_sha256() and tj.get("batch") == B and tj.get("nodes") == N:
+            if tj.get("source_sha256") == rollout_source_sha256() and tj.get("batch") == B and tj.get("nodes") == N:
                 traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
         except Exception:
             pass

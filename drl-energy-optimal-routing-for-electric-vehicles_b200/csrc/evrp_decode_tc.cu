@@ -830,7 +830,12 @@ int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, cons
   const int waves = (min_ctas + slots - 1) / slots;
   int grid = waves * slots;
   if (grid > rows) grid = rows;
-  const int rows_per_cta = (rows + grid - 1) / grid;
+  int rows_per_cta = (rows + grid - 1) / grid;
+  // Small batches: every CTA streams the whole FF_tour weight set (512 KB) from L2 every step whatever its row count, and
+  // one warp walks one row, so up to `walkers` rows per CTA cost one row latency: fewer, fuller CTAs shorten the FF phase.
+  static int min_rpc = -1;
+  if (min_rpc < 0) { const char* e = getenv("EVRP_MIN_RPC"); min_rpc = e ? atoi(e) : 1; }
+  if (rows_per_cta < min_rpc) rows_per_cta = min_rpc < RPC ? min_rpc : RPC;
   grid = (rows + rows_per_cta - 1) / rows_per_cta;
   static int pf_lines = -1;              // tuning knob: bit 0 K, bit 2 V, bit 3 logit-K just-in-time prefetch,
                                          // bit 16 record loads with L2::evict_first

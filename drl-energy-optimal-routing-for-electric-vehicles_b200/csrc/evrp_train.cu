@@ -41,8 +41,10 @@ __global__ void relu_mask_kernel(const float4* __restrict__ g, const float4* __r
 // ------------------------------------------------------------------------------------------------
 constexpr int BN_C = 128;
 
-__device__ __forceinline__ void block_channel_sums(float4 a, float4 b, double* __restrict__ out_a, double* __restrict__ out_b) {
-  __shared__ float4 sa[8][32], sb[8][32];
+struct D4 { double x, y, z, w; };
+
+__device__ __forceinline__ void block_channel_sums(const D4& a, const D4& b, double* __restrict__ out_a, double* __restrict__ out_b) {
+  __shared__ D4 sa[8][32], sb[8][32];
   const int c4 = threadIdx.x & 31, rsub = threadIdx.x >> 5;
   sa[rsub][c4] = a; sb[rsub][c4] = b;
   __syncthreads();
@@ -50,7 +52,7 @@ __device__ __forceinline__ void block_channel_sums(float4 a, float4 b, double* _
     double ax = 0, ay = 0, az = 0, aw = 0, bx = 0, by = 0, bz = 0, bw = 0;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      const float4 u = sa[r][c4], v = sb[r][c4];
+      const D4 u = sa[r][c4], v = sb[r][c4];
       ax += u.x; ay += u.y; az += u.z; aw += u.w; bx += v.x; by += v.y; bz += v.z; bw += v.w;
     }
     atomicAdd(out_a + 4 * c4 + 0, ax); atomicAdd(out_a + 4 * c4 + 1, ay); atomicAdd(out_a + 4 * c4 + 2, az); atomicAdd(out_a + 4 * c4 + 3, aw);
@@ -58,14 +60,18 @@ __device__ __forceinline__ void block_channel_sums(float4 a, float4 b, double* _
   }
 }
 
-// sums [257] fp64, zeroed by the caller: sum x [128] | sum x^2 [128] | n
+// sums [257] fp64, zeroed by the caller: sum x [128] | sum x^2 [128] | n.  Every addition is fp64 (products exact in fp64), so
+// the statistics do not depend on how the rows are split over threads, blocks or RANKS beyond fp64 rounding: a sharded batch
+// normalises bit-identically to the same batch on one GPU (a 1e-7 difference in the mean flips ReLU gates of the layer
+// behind and shows up as 1e-3 noise in single weight-gradient entries)
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, int M, double* __restrict__ sums) {
   const int c4 = threadIdx.x & 31, rsub = threadIdx.x >> 5;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = s;
+  D4 s = {0, 0, 0, 0}, ss = {0, 0, 0, 0};
   for (int row = blockIdx.x * 8 + rsub; row < M; row += gridDim.x * 8) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * BN_C) + c4);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    ss.x = fmaf(v.x, v.x, ss.x); ss.y = fmaf(v.y, v.y, ss.y); ss.z = fmaf(v.z, v.z, ss.z); ss.w = fmaf(v.w, v.w, ss.w);
+    const double a = v.x, b = v.y, c = v.z, d = v.w;
+    s.x += a; s.y += b; s.z += c; s.w += d;
+    ss.x += a * a; ss.y += b * b; ss.z += c * c; ss.w += d * d;
   }
   block_channel_sums(s, ss, sums, sums + BN_C);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(sums + 2 * BN_C, (double)M);
@@ -114,13 +120,13 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
                                                             const float* __restrict__ save, double* __restrict__ sums) {
   const int c4 = threadIdx.x & 31, rsub = threadIdx.x >> 5;
   const float4 mu = __ldg(reinterpret_cast<const float4*>(save) + c4), is = __ldg(reinterpret_cast<const float4*>(save + BN_C) + c4);
-  float4 sg = make_float4(0.f, 0.f, 0.f, 0.f), sx = sg;
+  D4 sg = {0, 0, 0, 0}, sx = {0, 0, 0, 0};
   for (int row = blockIdx.x * 8 + rsub; row < M; row += gridDim.x * 8) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(x + (size_t)row * BN_C) + c4);
     const float4 d = __ldg(reinterpret_cast<const float4*>(g + (size_t)row * BN_C) + c4);
-    sg.x += d.x; sg.y += d.y; sg.z += d.z; sg.w += d.w;
-    sx.x = fmaf(d.x, (v.x - mu.x) * is.x, sx.x); sx.y = fmaf(d.y, (v.y - mu.y) * is.y, sx.y);
-    sx.z = fmaf(d.z, (v.z - mu.z) * is.z, sx.z); sx.w = fmaf(d.w, (v.w - mu.w) * is.w, sx.w);
+    sg.x += (double)d.x; sg.y += (double)d.y; sg.z += (double)d.z; sg.w += (double)d.w;
+    sx.x += (double)d.x * (double)((v.x - mu.x) * is.x); sx.y += (double)d.y * (double)((v.y - mu.y) * is.y);
+    sx.z += (double)d.z * (double)((v.z - mu.z) * is.z); sx.w += (double)d.w * (double)((v.w - mu.w) * is.w);
   }
   block_channel_sums(sg, sx, sums, sums + BN_C);
 }
