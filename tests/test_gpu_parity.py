@@ -140,17 +140,45 @@ def test_encoder_matches_oracle(evrp, weights, name, bn):
     m.gemm_mode = 1                                   # fp32 FFMA GEMMs: fp32-rounding-level agreement
     emb1, _, _ = m.encode(static, dynamic)
     assert np.abs(emb1.cpu().numpy() - ref).max() < 1e-5
-    m.gemm_mode = 0                                   # tcgen05 3xTF32 (default): TMEM accumulation truncates, ~1e-5
-    emb, kvl, fixed = m.encode(static, dynamic)
-    assert np.abs(emb.cpu().numpy() - ref).max() < 5e-5
     fc, gK, gV, lK = O.precompute(W, ref)
     B, S = ref.shape[:2]
+    lK_fold = lK @ W["project_out.weight"]            # (Wout^T Wl) emb = lK @ Wout
+    # 2: ONE fused tcgen05 kernel, fp16-pair split operands (the default); 0: per-sub-layer tcgen05 3xTF32 launches.
+    # TMEM accumulation truncates: ~1e-5
+    for mode in (2, 0):
+        m.gemm_mode = mode
+        emb, kvl, fixed = m.encode(static, dynamic)
+        assert np.abs(emb.cpu().numpy() - ref).max() < 5e-5, mode
+        kv = kvl.cpu().numpy()
+        assert np.abs(kv[..., :128] - gK.transpose(0, 2, 1, 3).reshape(B, S, 128)).max() < 5e-5, mode
+        assert np.abs(kv[..., 128:256] - gV.transpose(0, 2, 1, 3).reshape(B, S, 128)).max() < 5e-5, mode
+        assert np.abs(kv[..., 256:] - lK_fold).max() < 1e-4, mode
+        assert np.abs(fixed.cpu().numpy() - fc).max() < 5e-5, mode
+    assert m.__class__(128, 128, args_for(N)).gemm_mode == 2          # the fused kernel is what a new model runs
+
+
+@pytest.mark.parametrize("N,B", [(20, 37), (50, 9), (58, 5), (100, 3), (122, 2)])
+def test_fused_encoder_packed_tiles_match_oracle(evrp, weights, N, B):
+    """the fused encoder kernel on fresh instances at graph sizes that pack 4 / 2 / 2 / 1 / 1 instances into a 128-row tile
+    (S = 26, 56, 64, 106, 128 = the kernel maximum), batch sizes that leave a ragged last tile: emb / kvl / fixed context
+    against the numpy oracle (5e-5) and against the fp32 FFMA path of the library"""
+    m, _ = make_model(evrp, N, weights)
+    s, d, e = O.generate_instances(B, N, seed=500 + N)
+    st, dy = torch.from_numpy(s).cuda(), torch.from_numpy(d).cuda()
+    ref = O.encoder(weights, O.init_embed(weights, s, d, 5))
+    fc, gK, gV, lK = O.precompute(weights, ref)
+    S = ref.shape[1]
+    m.gemm_mode = 2
+    emb, kvl, fixed = m.encode(st, dy)
+    m.gemm_mode = 1
+    emb1, kvl1, fixed1 = m.encode(st, dy)
+    assert np.abs(emb.cpu().numpy() - ref).max() < 5e-5
     kv = kvl.cpu().numpy()
     assert np.abs(kv[..., :128] - gK.transpose(0, 2, 1, 3).reshape(B, S, 128)).max() < 5e-5
     assert np.abs(kv[..., 128:256] - gV.transpose(0, 2, 1, 3).reshape(B, S, 128)).max() < 5e-5
-    lK_fold = lK @ W["project_out.weight"]            # (Wout^T Wl) emb = lK @ Wout
-    assert np.abs(kv[..., 256:] - lK_fold).max() < 1e-4
+    assert np.abs(kv[..., 256:] - lK @ weights["project_out.weight"]).max() < 1e-4
     assert np.abs(fixed.cpu().numpy() - fc).max() < 5e-5
+    assert float((emb - emb1).abs().max()) < 5e-5 and float((kvl - kvl1).abs().max()) < 1e-4
 
 
 # ---------------------------------------------------------------------------------------------
