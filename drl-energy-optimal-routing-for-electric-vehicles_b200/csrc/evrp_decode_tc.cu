@@ -42,11 +42,16 @@ using namespace tc;
 #define EVRP_CTAS 1          // CTAs per SM
 #define EVRP_TMEM_COLS 512
 #endif
+#ifndef EVRP_EXTRA_WALKERS
+#define EVRP_EXTRA_WALKERS 2 // warps that only walk rows (idle in the FF phase): 56 rows per CTA over 20 walkers = at most 3 rows per warp
+#endif
 constexpr int RPC = EVRP_RPC;
 constexpr int ROW_WARPS = EVRP_ROW_WARPS;
 constexpr int NB2 = EVRP_NB2;
 static_assert(RPC == 4 * ROW_WARPS, "epilogue mapping: 16 rows per (quadrant, column group) warp");
-constexpr int NT = (ROW_WARPS + 2) * 32;     // 576
+constexpr int XW = EVRP_EXTRA_WALKERS;
+constexpr int NWALK = ROW_WARPS + 2 + XW;    // row warps + the TMA / MMA warps + walker-only warps
+constexpr int NT = NWALK * 32;               // 640
 constexpr int SP = EVRP_MAX_S;               // padded node count (128)
 constexpr int PSTR = SP + 4;                 // head stride of the compat buffer
 constexpr int KBLK = RPC * 128;              // 8 KB: [64 rows x 64 fp16], 128B-swizzled, one plane of one K block
@@ -74,7 +79,7 @@ struct WarpScratch {
   unsigned char list[SP];        // feasible node indices, ascending
 };
 
-constexpr int SCRATCH_BYTES = (ROW_WARPS + 2) * (int)sizeof(WarpScratch);   // the two FF-phase warps walk rows as well
+constexpr int SCRATCH_BYTES = NWALK * (int)sizeof(WarpScratch);   // the two FF-phase warps and the extra warps walk rows as well
 constexpr int RING_BYTES = WSTAGES * WSTAGE;
 constexpr int RS_BYTES = ((SCRATCH_BYTES > RING_BYTES ? SCRATCH_BYTES : RING_BYTES) + 1023) / 1024 * 1024;
 
@@ -329,7 +334,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         }
         umma_commit(&sm.d2_full);
       }
-    } else {
+    } else if (wid < ROW_WARPS) {
       // ---- epilogue / converters: thread = (TMEM lane = feature 32q + lane, 16 rows 16cg..16cg+15) ----
       const int q = wid & 3, cg = wid >> 2;
       const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -841,7 +846,7 @@ int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, cons
                                          // bit 16 record loads with L2::evict_first
   if (pf_lines < 0) { const char* l = getenv("EVRP_PF_LINES"); pf_lines = l ? atoi(l) : (13 | 0x10000); }
   static int walkers = -1;
-  if (walkers < 0) { const char* e = getenv("EVRP_WALKERS"); walkers = e ? atoi(e) : ROW_WARPS + 2; }
+  if (walkers < 0) { const char* e = getenv("EVRP_WALKERS"); walkers = e ? atoi(e) : NWALK; if (walkers > NWALK) walkers = NWALK; }
   kern<<<grid, NT, SMEM_BYTES, st>>>(maps, *phys, *w, *cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope, static_xy, elevations, station_ws,
                                      dem_ws, m_ws, B, S, F, rows, rows_per_cta, pf_lines, walkers, forced_actions, uniforms, pi, ll, reward,
                                      energy, saved_mask, saved_veh, steps_used, t_max, status);

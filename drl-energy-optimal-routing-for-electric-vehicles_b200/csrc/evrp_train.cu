@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(128) route_context_bwd_kernel(const float* __r
   const float* gb = g_base + (size_t)b * T * D + c;
   float dfx = 0.f;
   int now = 0;
-#pragma unroll 4
+#pragma unroll 8
   for (int t = 0; t < T; ++t) {                             // base[t] = fixed + emb[now_t]
     const float g = __ldg(gb + (size_t)t * D);
     dfx += g;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(128) route_context_bwd_kernel(const float* __r
     const float* gr = g_rm + (size_t)b * T * D + c;
     float cur = 0.f, pend = 0.f;
     int arg = -1;
-#pragma unroll 4
+#pragma unroll 8
     for (int u = 0; u + 1 < T; ++u) {                       // pick u feeds run_max[t] for t > u while it holds the maximum
       const int j = s_pi[u];
       const float v = __ldg(e + (size_t)j * D);

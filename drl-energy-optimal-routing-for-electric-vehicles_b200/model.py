@@ -378,7 +378,10 @@ class AttentionModel(nn.Module):
             self.last_energy = o["E"]
             return o["pi"], o["ll"], o["R"]
         # training / grad path: differentiable encoder (train-mode BatchNorm uses batch statistics and updates the
-        # running buffers, nets/GraphEncoder.py:144-145), kernel rollout, teacher-forced differentiable log-probs
+        # running buffers, nets/GraphEncoder.py:144-145), kernel rollout, teacher-forced differentiable log-probs.
+        # The decoder weights are packed FIRST: the power-of-two scales of the fp16 planes are read back on the host, and
+        # here the stream is still empty (behind the encoder the same read would stall the host for the encoder's run time)
+        self.packed_weights("decoder")
         emb, kvl, fixed = policy_math.encode_torch(self, static, dynamic)
         with torch.no_grad():
             tab = emb.detach() if self.policy == 0 else emb.detach() @ self.project_step_context.weight[:, :128].t()

@@ -293,10 +293,11 @@ class ReinforceLoss(torch.autograd.Function):
 # one optimisation step
 # ------------------------------------------------------------------------------------------------
 def clip_grad_norms(param_groups, max_norm=math.inf):
-    """trainer.py:53-70"""
+    """trainer.py:53-70.  The clipped norms stay on the device (torch.clamp, not Python's min(): comparing a CUDA tensor
+    with a float would stall the host until the whole backward has run)."""
     grad_norms = [torch.nn.utils.clip_grad_norm_(g['params'], max_norm if max_norm > 0 else math.inf, norm_type=2)
                   for g in param_groups]
-    clipped = [min(g, max_norm) for g in grad_norms] if max_norm > 0 else grad_norms
+    clipped = [torch.clamp(g, max=max_norm) for g in grad_norms] if max_norm > 0 else grad_norms
     return grad_norms, clipped
 
 
@@ -311,10 +312,13 @@ def reinforce_step(actor, baseline, optimizer, batch, max_grad_norm=2.0, forced_
         bl_val, bl_loss = baseline.eval(x, reward)
     else:
         bl_val, bl_loss = bl_val.to(reward.device), 0
-    n_global = torch.tensor(float(reward.numel()), device=reward.device)
-    allreduce_sum_(n_global)
+    n_global = float(reward.numel())
+    if w > 1:                                    # ranks may hold different batch sizes: the mean is over the GLOBAL batch
+        n_t = torch.tensor(n_global, device=reward.device)
+        allreduce_sum_(n_t)
+        n_global = float(n_t)
     # fused kernel: reward / advantage / loss and d loss / d ll; each rank holds its share of the GLOBAL mean
-    loss, reward, advantage = ReinforceLoss.apply(ll, R, bl_val, 1.0 / float(n_global))
+    loss, reward, advantage = ReinforceLoss.apply(ll, R, bl_val, 1.0 / n_global)
     loss = loss + bl_loss
     optimizer.zero_grad()
     loss.backward()
