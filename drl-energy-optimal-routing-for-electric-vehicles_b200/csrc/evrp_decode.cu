@@ -657,6 +657,7 @@ sample_min_kernel(const float* __restrict__ reward, const int64_t* __restrict__ 
 #ifdef EVRP_PHASE_TIMING
 int debug_phase_cycles_tc(unsigned long long* out4, int reset);
 int debug_row_cycles_tc(unsigned long long* out8, int reset);
+int debug_ff_cycles_tc(unsigned long long* out12, int reset);
 #endif
 int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, const evrp_rollout_cfg* cfg, const float* emb,
                       const float* kvl, const float* fixed_ctx, const float* dynamic0, const float* distances,
@@ -737,6 +738,7 @@ int evrp_rollout(const evrp_phys* phys, const evrp_decoder_weights* w, const evr
 #ifdef EVRP_PHASE_TIMING
 int evrp_debug_phase_cycles_tc(unsigned long long* out4, int reset) { return evrp::debug_phase_cycles_tc(out4, reset); }
 int evrp_debug_row_cycles_tc(unsigned long long* out8, int reset) { return evrp::debug_row_cycles_tc(out8, reset); }
+int evrp_debug_ff_cycles_tc(unsigned long long* out12, int reset) { return evrp::debug_ff_cycles_tc(out12, reset); }
 int evrp_debug_phase_cycles(unsigned long long* out4, int reset) {
   if (cudaMemcpyFromSymbol(out4, evrp::g_phase_cycles, sizeof(unsigned long long) * 4) != cudaSuccess) return -1;
   if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(evrp::g_phase_cycles, z, sizeof(z)); }

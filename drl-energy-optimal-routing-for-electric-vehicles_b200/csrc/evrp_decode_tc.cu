@@ -101,11 +101,14 @@ constexpr size_t SMEM_BYTES = (1 + NB2) * (size_t)ACT_BYTES + RS_BYTES + sizeof(
 // debug build only (tools/phase_timing.py): cycles of warp 0 in [FF hidden tiles, FF ctx + sync, row phase busy, barrier wait]
 __device__ unsigned long long g_phase_cycles_tc[4];
 __device__ unsigned long long g_row_cycles_tc[8];   // per-pass cycles of warp 0 inside the row phase
+__device__ unsigned long long g_ff_cycles_tc[12];   // FF phase of warp 0: [2j] wait for hidden tile j, [2j+1] convert + store, [8] ctx wait, [9] ctx store, [10] sync
+#define FT_MARK(i) do { if (tid == 0) { const long long _n = clock64(); ft_acc[i] += _n - ft_t; ft_t = _n; } } while (0)
 #define RT_MARK(i) do { if (tid == 0) { const long long _n = clock64(); rt_acc[i] += _n - rt_t; rt_t = _n; } } while (0)
 #define PT_MARK(i) do { if (tid == 0) { const long long _n = clock64(); pt_acc[i] += _n - pt_t; pt_t = _n; } } while (0)
 #else
 #define PT_MARK(i) do { } while (0)
 #define RT_MARK(i) do { } while (0)
+#define FT_MARK(i) do { } while (0)
 #endif
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -249,6 +252,8 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
   long long pt_t = clock64();
   long long rt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long rt_t = 0;
+  long long ft_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long ft_t = 0;
 #endif
 
   // ---------------- step loop ----------------
@@ -338,12 +343,16 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
       // ---- epilogue / converters: thread = (TMEM lane = feature 32q + lane, 16 rows 16cg..16cg+15) ----
       const int q = wid & 3, cg = wid >> 2;
       const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+#ifdef EVRP_PHASE_TIMING
+      if (tid == 0) ft_t = clock64();
+#endif
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
         const int f = j * 128 + q * 32 + lane;
         const float bb = __ldg(w.b1 + f), wv0 = __ldg(w.w1_veh + f), wv1 = __ldg(w.w1_veh + FF + f), wv2 = __ldg(w.w1_veh + 2 * FF + f);
         mbar_wait(&sm.d1_full[j], t & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        FT_MARK(2 * j);
         uint32_t v[16];
         tmem_ld16(tmem_base + lane_base + j * RPC + cg * 16, v);
         if (j >= NB2) {                                         // GEMM2 over tile j - NB2 has drained this buffer
@@ -353,8 +362,12 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         // feature 32q + lane of the tile = element (q & 1) * 32 + lane of K block q >> 1: 2 bytes at k * 2
         unsigned char* pb = B2 + (j % NB2) * ACT_BYTES + (q >> 1) * (2 * KBLK) + ((lane & 7) << 1);
         const int chunk = (q & 1) * 4 + (lane >> 3);
+        // rows beyond this CTA's row count are never read back: their operand rows keep whatever they hold (each output
+        // column of the MMA depends on its own operand row only).  At 7 rows per CTA this is 9 of 10 conversions.
+        const int n_i = min(16, rows_per_cta - cg * 16);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
+          if (i >= n_i) break;
           const int r = cg * 16 + i;
           const float4 vh = *reinterpret_cast<const float4*>(&sm.veh[r][0]);
           float x = fmaf(__uint_as_float(v[i]), w.w1_inv_scale, fmaf(wv2, vh.z, fmaf(wv1, vh.y, fmaf(wv0, vh.x, bb))));
@@ -368,20 +381,25 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         fence_async_smem();
         __syncwarp();                                           // one arrival per warp (512 per-thread arrivals serialise)
         if (lane == 0) mbar_arrive(&sm.b2_full[j % NB2]);
+        FT_MARK(2 * j + 1);
       }
       PT_MARK(0);
       mbar_wait(&sm.d2_full, t & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      FT_MARK(8);
       {
         uint32_t v[16];
         tmem_ld16(tmem_base + lane_base + TM_D2 + cg * 16, v);
+        const int n_i = min(16, rows_per_cta - cg * 16);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) ctx[cg * 16 + i][q * 32 + lane] = __uint_as_float(v[i]) * w.w2_inv_scale;
+        for (int i = 0; i < 16; ++i) if (i < n_i) ctx[cg * 16 + i][q * 32 + lane] = __uint_as_float(v[i]) * w.w2_inv_scale;
       }
       if (tid == 0) sm.next_row = 0;
+      FT_MARK(9);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    FT_MARK(10);
     PT_MARK(1);
 
     // =========================== per-row phase: each row warp walks rows ===========================
@@ -783,6 +801,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
 #ifdef EVRP_PHASE_TIMING
   if (tid == 0) for (int i = 0; i < 4; ++i) atomicAdd(&g_phase_cycles_tc[i], (unsigned long long)pt_acc[i]);
   if (tid == 0) for (int i = 0; i < 8; ++i) atomicAdd(&g_row_cycles_tc[i], (unsigned long long)rt_acc[i]);
+  if (tid == 0) for (int i = 0; i < 12; ++i) atomicAdd(&g_ff_cycles_tc[i], (unsigned long long)ft_acc[i]);
 #endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -795,6 +814,11 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
 int debug_phase_cycles_tc(unsigned long long* out4, int reset) {
   if (cudaMemcpyFromSymbol(out4, dtc::g_phase_cycles_tc, sizeof(unsigned long long) * 4) != cudaSuccess) return -1;
   if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(dtc::g_phase_cycles_tc, z, sizeof(z)); }
+  return 0;
+}
+int debug_ff_cycles_tc(unsigned long long* out12, int reset) {
+  if (cudaMemcpyFromSymbol(out12, dtc::g_ff_cycles_tc, sizeof(unsigned long long) * 12) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[12] = {0}; cudaMemcpyToSymbol(dtc::g_ff_cycles_tc, z, sizeof(z)); }
   return 0;
 }
 int debug_row_cycles_tc(unsigned long long* out8, int reset) {

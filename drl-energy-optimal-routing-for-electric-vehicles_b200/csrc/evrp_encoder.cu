@@ -53,6 +53,51 @@ init_embed_kernel(const float* __restrict__ xy, const float* __restrict__ dyn, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// init embedding on its own (training path) and its backward: the three tiny nn.Linear layers of
+// nets/DRLModel.py:192-200 have K = 2 / 2 / 3 inputs, so their weight gradients are 10 column reductions of
+// g [B*S,128] weighted by (x, y, 1 | x, y, 1 | x, y, demand, 1) per node class.  One CTA = 128 channels x a stride of
+// rows, partial sums per CTA, second kernel sums the CTAs in a fixed order (deterministic).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+init_embed_bwd_kernel(const float* __restrict__ xy, const float* __restrict__ dyn, const float* __restrict__ g, int B, int S,
+                      int F, float* __restrict__ partial /*[grid][10][128]*/) {
+  const int c = threadIdx.x;
+  float a[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const size_t rows = (size_t)B * S;
+#pragma unroll 4
+  for (size_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int j = (int)(row % S);
+    const size_t b = row / S;
+    const float gv = __ldg(g + row * D + c);
+    const float x = __fdiv_rn(__ldg(xy + (b * 2 + 0) * S + j), 100.f), y = __fdiv_rn(__ldg(xy + (b * 2 + 1) * S + j), 100.f);
+    if (j == 0) { a[0] = fmaf(gv, x, a[0]); a[1] = fmaf(gv, y, a[1]); a[2] += gv; }
+    else if (j <= F) { a[3] = fmaf(gv, x, a[3]); a[4] = fmaf(gv, y, a[4]); a[5] += gv; }
+    else {
+      const float dem = __ldg(dyn + (b * 4 + 1) * S + j);
+      a[6] = fmaf(gv, x, a[6]); a[7] = fmaf(gv, y, a[7]); a[8] = fmaf(gv, dem, a[8]); a[9] += gv;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 10; ++k) partial[((size_t)blockIdx.x * 10 + k) * D + c] = a[k];
+}
+
+__global__ void init_embed_bwd_reduce_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ gw0, float* __restrict__ gb0,
+                                             float* __restrict__ gw1, float* __restrict__ gb1, float* __restrict__ gw2,
+                                             float* __restrict__ gb2) {
+  const int k = blockIdx.x, c = threadIdx.x;           // 10 blocks x 128 threads
+  float acc = 0.f;
+  for (int i = 0; i < nblk; ++i) acc += partial[((size_t)i * 10 + k) * D + c];
+  switch (k) {                                         // nn.Linear layouts: weight [128][in], bias [128]
+    case 0: case 1: gw0[c * 2 + k] = acc; break;
+    case 2: gb0[c] = acc; break;
+    case 3: case 4: gw1[c * 2 + (k - 3)] = acc; break;
+    case 5: gb1[c] = acc; break;
+    case 6: case 7: case 8: gw2[c * 3 + (k - 6)] = acc; break;
+    default: gb2[c] = acc; break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // SGEMM  C[M,N] = epi(A[M,K] @ Bm[K,N]);  A row-major (lda), Bm k-major (ldb), N % 128 == 0, K % 8 == 0
 // epilogue: v = acc (+bias[n]) ; relu ; (+resid[m,n]) ; (*scale[n] + shift[n])
 // ------------------------------------------------------------------------------------------------
@@ -382,6 +427,47 @@ int evrp_encoder_forward(const evrp_encoder_weights* w, const float* static_xy, 
     }
   }
   fixed_context_kernel<<<B, 128, 0, st>>>(emb, S, w->fixed_ctx_w, fixed_ctx);
+  EVRP_LAUNCH_OK();
+  return 0;
+}
+
+// init embedding alone (training forward): weights in nn.Linear layout (depot [128,2], station [128,2], customer [128,3])
+int evrp_init_embed_forward(const float* static_xy, const float* dynamic, int B, int S, int F, const float* depot_w,
+                            const float* depot_b, const float* station_w, const float* station_b, const float* cust_w,
+                            const float* cust_b, float* h, void* stream) {
+  using namespace evrp;
+  if (!static_xy || !dynamic || !depot_w || !depot_b || !station_w || !station_b || !cust_w || !cust_b || !h || B < 1 || S < 2 ||
+      F < 1 || F >= S)
+    return -EVRP_E_BADARG;
+  int dev = 0, sms = 148;
+  EVRP_CUDA_OK(cudaGetDevice(&dev));
+  EVRP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long want = ((long long)B * S + 7) / 8;
+  const unsigned grid = (unsigned)(want < (long long)sms * 16 ? want : (long long)sms * 16);
+  init_embed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(static_xy, dynamic, B, S, F, depot_w, depot_b, station_w, station_b,
+                                                            cust_w, cust_b, h);
+  EVRP_LAUNCH_OK();
+  return 0;
+}
+
+size_t evrp_init_embed_backward_workspace_bytes(void) { return (size_t)592 * 10 * 128 * sizeof(float); }
+
+// gradients of the six init-embedding parameters from grad_h [B,S,128]
+int evrp_init_embed_backward(const float* static_xy, const float* dynamic, const float* grad_h, int B, int S, int F,
+                             float* g_depot_w, float* g_depot_b, float* g_station_w, float* g_station_b, float* g_cust_w,
+                             float* g_cust_b, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace evrp;
+  if (!static_xy || !dynamic || !grad_h || !g_depot_w || !g_depot_b || !g_station_w || !g_station_b || !g_cust_w || !g_cust_b ||
+      !workspace || B < 1 || S < 2 || F < 1 || F >= S)
+    return -EVRP_E_BADARG;
+  const long long rows = (long long)B * S;
+  const int grid = (int)(rows < 592 ? rows : 592);
+  if (workspace_bytes < (size_t)grid * 10 * 128 * sizeof(float)) return -EVRP_E_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  init_embed_bwd_kernel<<<grid, 128, 0, st>>>(static_xy, dynamic, grad_h, B, S, F, (float*)workspace);
+  EVRP_LAUNCH_OK();
+  init_embed_bwd_reduce_kernel<<<10, 128, 0, st>>>((const float*)workspace, grid, g_depot_w, g_depot_b, g_station_w, g_station_b,
+                                                   g_cust_w, g_cust_b);
   EVRP_LAUNCH_OK();
   return 0;
 }

@@ -243,6 +243,37 @@ def init_embed_torch(model, static, dynamic):
                       model.init_embed(torch.cat((xy[:, F + 1:], dem[:, F + 1:]), 2))), 1)
 
 
+class InitEmbed(torch.autograd.Function):
+    """nets/DRLModel.py:192-200 on the init-embedding kernel (csrc/evrp_encoder.cu) and its backward: the six parameter
+    gradients as weighted column reductions of grad_h (K = 2 / 2 / 3: no GEMM)."""
+
+    @staticmethod
+    def forward(ctx, static, dynamic, wd, bd, ws, bs, wc, bc, F):
+        static, dynamic = static.contiguous(), dynamic.contiguous()
+        B, _, S = static.shape
+        h = torch.empty(B, S, 128, device=static.device, dtype=torch.float32)
+        p = [t.detach().contiguous() for t in (wd, bd, ws, bs, wc, bc)]
+        _lib.check(_lib.lib().evrp_init_embed_forward(_lib.ptr(static), _lib.ptr(dynamic), B, S, F, *[_lib.ptr(t) for t in p],
+                                                      _lib.ptr(h), _lib.stream_ptr()), "evrp_init_embed_forward")
+        ctx.save_for_backward(static, dynamic)
+        ctx.F = F
+        return h
+
+    @staticmethod
+    def backward(ctx, g):
+        static, dynamic = ctx.saved_tensors
+        B, _, S = static.shape
+        L = _lib.lib()
+        dev = static.device
+        out = [torch.empty(128, 2, device=dev), torch.empty(128, device=dev), torch.empty(128, 2, device=dev),
+               torch.empty(128, device=dev), torch.empty(128, 3, device=dev), torch.empty(128, device=dev)]
+        ws = torch.empty(L.evrp_init_embed_backward_workspace_bytes(), dtype=torch.uint8, device=dev)
+        _lib.check(L.evrp_init_embed_backward(_lib.ptr(static), _lib.ptr(dynamic), _lib.ptr(g.contiguous()), B, S, ctx.F,
+                                              *[_lib.ptr(t) for t in out], _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                   "evrp_init_embed_backward")
+        return (None, None) + tuple(out) + (None,)
+
+
 class _GlobalBatchNorm(torch.autograd.Function):
     """Train-mode BatchNorm1d over the GLOBAL batch when instances are sharded over ranks: the batch statistics of
     nets/GraphEncoder.py:144-145 couple every instance of the batch, so each rank contributes [sum x, sum x^2, n]
@@ -309,7 +340,12 @@ def encode_torch(model, static, dynamic):
     """Differentiable restatement of the encoder kernels' math (nets/GraphEncoder.py:55-118,142-179).
     BatchNorm follows ``model.training`` (batch statistics + running-stat update in train mode; with instances
     sharded over ranks the statistics are those of the global batch, see _GlobalBatchNorm)."""
-    h = init_embed_torch(model, static, dynamic)
+    if static.is_cuda and model.init_embed.weight.shape[0] == 128:
+        h = InitEmbed.apply(static.float(), dynamic.float(), model.init_embed_depot_and_station.weight,
+                            model.init_embed_depot_and_station.bias, model.init_embed_station.weight, model.init_embed_station.bias,
+                            model.init_embed.weight, model.init_embed.bias, int(model.charging_num))
+    else:
+        h = init_embed_torch(model, static, dynamic)
     B, S, d = h.shape
     for layer in model.embedder.layers:
         att, bn1, ff, bn2 = layer[0].module, layer[1].normalizer, layer[2].module, layer[3].normalizer
@@ -338,7 +374,10 @@ def encode_torch(model, static, dynamic):
         kvl = TCLinear.apply(h.reshape(B * S, d), folded_node_projection(model), None, None, False).view(B, S, 3 * d)
     else:
         kvl = Fn.linear(h, folded_node_projection(model))
-    fixed = model.project_fixed_context(h.mean(1))
+    if h.is_cuda and d == 128:
+        fixed = TCLinear.apply(h.mean(1), model.project_fixed_context.weight, None, None, False)
+    else:
+        fixed = model.project_fixed_context(h.mean(1))
     return h, kvl, fixed
 
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 17
+#define EVRP_ABI_VERSION 18
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -337,6 +337,19 @@ int evrp_route_context_forward(const float* emb, const float* fixed_ctx, const i
 int evrp_route_context_backward(const float* emb, const int64_t* pi, const float* grad_run_max, const float* grad_base,
                                 int B, int T, int S, float* grad_emb, float* grad_fixed, void* stream);
 int evrp_relu_mask(const float* g, const float* y, float* out, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (11) init embedding on its own and its backward (training path): nets/DRLModel.py:192-200 `_init_embed` with the three
+ *      parameters in nn.Linear layout (depot / station [128,2] + [128], customer [128,3] + [128]); the backward produces the
+ *      six parameter gradients from grad_h [B,S,128] (10 weighted column reductions, deterministic two-pass sum).
+ * ---------------------------------------------------------------------------------------------- */
+int evrp_init_embed_forward(const float* static_xy, const float* dynamic, int B, int S, int F, const float* depot_w,
+                            const float* depot_b, const float* station_w, const float* station_b, const float* cust_w,
+                            const float* cust_b, float* h, void* stream);
+size_t evrp_init_embed_backward_workspace_bytes(void);
+int evrp_init_embed_backward(const float* static_xy, const float* dynamic, const float* grad_h, int B, int S, int F,
+                             float* g_depot_w, float* g_depot_b, float* g_station_w, float* g_station_b, float* g_cust_w,
+                             float* g_cust_b, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -961,6 +961,28 @@ def test_route_context_kernels_match_torch(evrp, B, T, S):
     assert float((gf - fixed.grad).abs().max()) < 1e-4 * float(fixed.grad.abs().max())
 
 
+def test_init_embed_kernels_match_torch(evrp, weights):
+    """training-path init embedding (evrp_init_embed_forward / _backward, nets/DRLModel.py:192-200) against the plain PyTorch
+    statement: values and the six parameter gradients"""
+    from evrp_b200 import policy_math as PM
+    m, _ = make_model(evrp, 50, weights)
+    s, d, e = O.generate_instances(33, 50, seed=77)
+    st, dy = torch.from_numpy(s).cuda(), torch.from_numpy(d).cuda()
+    ps = [m.init_embed_depot_and_station.weight, m.init_embed_depot_and_station.bias, m.init_embed_station.weight,
+          m.init_embed_station.bias, m.init_embed.weight, m.init_embed.bias]
+    w = torch.randn(33, 56, 128, generator=torch.Generator().manual_seed(5)).cuda()
+    h = PM.InitEmbed.apply(st, dy, *ps, 5)
+    (h * w).sum().backward()
+    got = [p.grad.clone() for p in ps]
+    for p in ps:
+        p.grad = None
+    ref = PM.init_embed_torch(m, st, dy)
+    (ref * w).sum().backward()
+    assert float((h - ref).abs().max()) < 2e-6
+    for g, p in zip(got, ps):
+        assert float((g - p.grad).norm() / p.grad.norm()) < 1e-5
+
+
 def test_global_batch_norm_cuda_path_matches_batchnorm1d(evrp):
     """the multi-rank BatchNorm path of the training forward (global-batch statistics) on CUDA, exercised through a
     one-rank NCCL group: outputs, gradients and running statistics equal nn.BatchNorm1d on the same batch"""

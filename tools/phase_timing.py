@@ -43,6 +43,17 @@ if not FFM:
     r = np.array(list(rb), dtype=np.float64)
     rn = ["list + K prefetch + query", "compat pass (K)", "softmax (+V prefetch)", "heads pass (V, + logit-K prefetch)",
           "logits pass (logit-K)", "log-softmax + pick", "transition loads + state + running max", "look-ahead mask + bookkeeping"]
+    fb = (C.c_ulonglong * 12)()
+    L.evrp_debug_ff_cycles_tc.argtypes = [C.POINTER(C.c_ulonglong), C.c_int]
+    L.evrp_debug_ff_cycles_tc(fb, 0)
+    f = np.array(list(fb), dtype=np.float64)
+    T = o['pi'].shape[1]
+    ncta = min(148, (B + 63) // 64 * 148 // 148) if False else None
+    fn = ["wait tile 0", "convert 0", "wait tile 1", "convert 1", "wait tile 2", "convert 2", "wait tile 3", "convert 3",
+          "ctx wait", "ctx store", "sync", "-"]
+    print("  FF phase of warp 0 (share of the FF phase; cycles per CTA-step over all CTAs):")
+    for n, x in zip(fn[:11], f[:11]):
+        print(f"    {n:14s} {100 * x / f[:11].sum():5.1f} %")
     print("  row phase of warp 0 by pass:")
     for n, x in zip(rn, r):
         print(f"    {n:40s} {100 * x / r.sum():5.1f} %")
