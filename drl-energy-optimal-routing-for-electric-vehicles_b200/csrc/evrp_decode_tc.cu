@@ -27,6 +27,7 @@
 // Rows retire individually; the host reads back only t_max and the status word.
 #include <math.h>
 #include <stdlib.h>
+#include <type_traits>
 #include <cuda_fp16.h>
 #include "evrp_tc.cuh"
 
@@ -132,13 +133,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// the two warps of a row team (TEAM == 2) meet here; orders their shared-memory traffic
+__device__ __forceinline__ void team_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
 template <typename T>
 __device__ __forceinline__ T sel4(const T (&a)[4], int i) { return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : a[3]; }
 
 struct Maps { CUtensorMap w1h, w1l, w2h, w2l; };
 
-// MODE: 0 greedy, 1 sample, 2 teacher-forced; COORDS: geometry recomputed from coordinate / elevation rows
-template <int MODE, bool COORDS>
+// MODE: 0 greedy, 1 sample, 2 teacher-forced; COORDS: geometry recomputed from coordinate / elevation rows;
+// TEAM: warps per row in the row phase.  2 (small batches, at most 10 rows per CTA): an owner warp and a helper warp split
+// the feasible nodes of the three record passes (K, V, logit-K) by batch parity and meet on a named barrier; one row then
+// costs ~2/3 of the single-warp latency.  The partial sums of the even and the odd batches are kept apart and added once
+// in BOTH modes, so the results do not depend on the mode (a batch and its shards decode bit-identically).
+template <int MODE, bool COORDS, int TEAM>
 __global__ void __launch_bounds__(NT, EVRP_CTAS)
 rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decoder_weights w, evrp_rollout_cfg cfg,
                   const float* __restrict__ emb, const float* __restrict__ kvl, const float* __restrict__ fixed_ctx,
@@ -404,16 +412,32 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
 
     // =========================== per-row phase: each row warp walks rows ===========================
     if (wid < walkers) {                                   // (the TMA / MMA warps are idle in this phase and walk rows too)
-      WarpScratch& ws = reinterpret_cast<WarpScratch*>(ring)[wid];
+      constexpr bool TEAMED = (TEAM == 2);
+      const int tw = TEAMED ? (wid & 1) : 0;               // 0: the row's owner, 1: its helper
+      WarpScratch* scr = reinterpret_cast<WarpScratch*>(ring);
+      WarpScratch& ws = scr[TEAMED ? (wid & ~1) : wid];    // the owner's scratch, shared by the team
+      WarpScratch& wx = scr[wid | 1];                      // (TEAM == 2) the helper's scratch: exchange area of the team
+      const int team_bar = 1 + (wid >> 1);                 // named barrier of the team (0 is __syncthreads)
+      int* team_slot = reinterpret_cast<int*>(&wx.list[0]);    // [0], [1]: claimed row (ping-pong), [2]: feasible count
+      int iter = 0;
+      (void)iter; (void)team_slot; (void)team_bar;
       const int hd = lane >> 2, sub = lane & 3;
 #pragma unroll 1
       while (true) {
         int lr = 0;
-        if (lane == 0) lr = atomicAdd(&sm.next_row, 1);
-        lr = __shfl_sync(FULL, lr, 0);
+        if (tw == 0) {
+          if (lane == 0) lr = atomicAdd(&sm.next_row, 1);
+          lr = __shfl_sync(FULL, lr, 0);
+        }
+        if (TEAMED) {
+          if (tw == 0 && lane == 0) team_slot[iter & 1] = lr;
+          team_sync(team_bar);
+          lr = *reinterpret_cast<volatile int*>(&team_slot[iter & 1]);
+          ++iter;
+        }
         if (lr >= rows_per_cta) break;
         RowState& rs = sm.rs[lr];
-        if (rs.done) continue;                             // warp-uniform
+        if (rs.done) continue;                             // uniform over the warp and the team
 #ifdef EVRP_PHASE_TIMING
         if (tid == 0) rt_t = clock64();
 #endif
@@ -425,12 +449,15 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         const float* kvlb = kvl + (size_t)inst * S * 384;
         uint32_t mk[4] = {rs.mk[0], rs.mk[1], rs.mk[2], rs.mk[3]};
         // demand row and exact running max of this row (L2; written by this CTA only): issued early
-        float dmj[4];
+        float dmj[4] = {0.f, 0.f, 0.f, 0.f};
+        float4 mm = make_float4(0.f, 0.f, 0.f, 0.f);
+        int nf = 0;
+        float q[4] = {0.f, 0.f, 0.f, 0.f};
+        if (tw == 0) {
 #pragma unroll
         for (int jb = 0; jb < 4; ++jb) dmj[jb] = __ldcg(dem_ws + (size_t)row * SP + jb * 32 + lane);
-        float4 mm = __ldcg(reinterpret_cast<const float4*>(m_ws + (size_t)row * D) + lane);
+        mm = __ldcg(reinterpret_cast<const float4*>(m_ws + (size_t)row * D) + lane);
         // ---- feasible list (ascending node index) ----
-        int nf = 0;
 #pragma unroll
         for (int jb = 0; jb < 4; ++jb) {
           const uint32_t bits = mk[jb];
@@ -454,7 +481,6 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           }
         }
         // ---- query (:394): (fixed_ctx + ctx) + emb[now] ; lane holds 4 channels of head lane/4 ----
-        float q[4];
         {
           const float4 fc = ldg4(fixed_ctx + (size_t)inst * D + lane * 4);
           const float4 en = ldg4(embb + (size_t)now * D + lane * 4);
@@ -465,11 +491,24 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           q[2] = (fc.z + (cx.z + b2.z)) + en.z;
           q[3] = (fc.w + (cx.w + b2.w)) + en.w;
         }
+        if (TEAMED) {                                      // hand the query and the list length to the helper
+          *reinterpret_cast<float4*>(&ws.heads[lane * 4]) = make_float4(q[0], q[1], q[2], q[3]);
+          if (lane == 0) team_slot[2] = nf;
+        }
+        }                                                  // (tw == 0)
+        if (TEAMED) {
+          team_sync(team_bar);
+          if (tw == 1) {
+            nf = *reinterpret_cast<volatile int*>(&team_slot[2]);
+            const float4 qq = *reinterpret_cast<const float4*>(&ws.heads[lane * 4]);
+            q[0] = qq.x; q[1] = qq.y; q[2] = qq.z; q[3] = qq.w;
+          }
+        }
         RT_MARK(0);
         // ---- compat[h][i] = q_h . K[j_i, h] / 4 ; CH rows (CH x 512 B) in flight per warp ----
         constexpr int CH = 8;
         float cmx = -INFINITY;                             // per-head maximum, tracked by all four lanes of the head
-        for (int i0 = 0; i0 < nf; i0 += CH) {
+        for (int i0 = tw * CH; i0 < nf; i0 += CH * TEAM) {
           float4 kv[CH];
 #pragma unroll
           for (int a = 0; a < CH; ++a) kv[a] = ldg4_pol(kvlb + (size_t)ws.list[i0 + a] * 384 + lane * 4, pol);
@@ -483,36 +522,54 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
             if (sub == 0) ws.pc[hd][i0 + a] = p;
           }
         }
-        __syncwarp();
+        if (TEAMED) {                                      // the maximum is over both halves of the list
+          wx.logit[tw * 32 + lane] = cmx;
+          team_sync(team_bar);
+          cmx = fmaxf(cmx, wx.logit[(tw ^ 1) * 32 + lane]);
+        } else {
+          __syncwarp();
+        }
         RT_MARK(1);
         // ---- per-head softmax over the list; lane (hd, sub) strides i = sub, sub+4, ... ----
-        float sum = 0.f;
+        float sum = 0.f, sum_b = 0.f;                      // partial sums of the even / odd batches (see TEAM above)
         {
-          if (pf_lines & 4) {
+          if ((pf_lines & 4) && tw == 0) {
             for (int i = lane; i < nf; i += 32) {
               const float* p = kvlb + (size_t)ws.list[i] * 384 + 128;
 #pragma unroll
               for (int c = 0; c < 4; ++c) prefetch_l2(p + c * 32);
             }
           }
-          for (int i = sub; i < nf; i += 4) { const float e = expf(ws.pc[hd][i] - cmx); ws.pc[hd][i] = e; sum += e; }
+          for (int i0 = tw * CH; i0 < nf; i0 += CH * TEAM) {   // this warp's batches; padded entries weigh nothing
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int i = i0 + sub + 4 * k;
+              const float e = (i < nf) ? expf(ws.pc[hd][i] - cmx) : 0.f;
+              ws.pc[hd][i] = e;
+              sum += e;
+            }
+            if (!TEAMED) { const float tmp = sum; sum = sum_b; sum_b = tmp; }      // one warp: alternate the two partial sums
+          }
           sum += __shfl_xor_sync(FULL, sum, 1);
-          sum += __shfl_xor_sync(FULL, sum, 2);               // the division by `sum` is applied to the 4 head outputs below
-          if (sub == 0) { for (int i = nf; i < ((nf + 7) & ~7); ++i) ws.pc[hd][i] = 0.f; }   // padded entries weigh nothing
+          sum += __shfl_xor_sync(FULL, sum, 2);               // the division by the sum is applied to the 4 head outputs below
+          if (!TEAMED) {
+            sum_b += __shfl_xor_sync(FULL, sum_b, 1);
+            sum_b += __shfl_xor_sync(FULL, sum_b, 2);
+          }
         }
         __syncwarp();
         RT_MARK(2);
         // ---- heads = attn @ V ; lane owns 4 channels ----
         {
-          if (pf_lines & 8) {
+          if ((pf_lines & 8) && tw == 0) {
             for (int i = lane; i < nf; i += 32) {
               const float* p = kvlb + (size_t)ws.list[i] * 384 + 256;
 #pragma unroll
               for (int c = 0; c < 4; ++c) prefetch_l2(p + c * 32);
             }
           }
-          float hv[4] = {0.f, 0.f, 0.f, 0.f};
-          for (int i0 = 0; i0 < nf; i0 += CH) {
+          float hv[4] = {0.f, 0.f, 0.f, 0.f}, hb[4] = {0.f, 0.f, 0.f, 0.f};     // even / odd batches
+          for (int i0 = tw * CH; i0 < nf; i0 += CH * TEAM) {
             float4 vv[CH]; float pr[CH];
 #pragma unroll
             for (int a = 0; a < CH; ++a) {
@@ -524,11 +581,31 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
               hv[0] = fmaf(pr[a], vv[a].x, hv[0]); hv[1] = fmaf(pr[a], vv[a].y, hv[1]);
               hv[2] = fmaf(pr[a], vv[a].z, hv[2]); hv[3] = fmaf(pr[a], vv[a].w, hv[3]);
             }
+            if (!TEAMED) {                                   // one warp: alternate the two accumulators
+#pragma unroll
+              for (int c = 0; c < 4; ++c) { const float tmp = hv[c]; hv[c] = hb[c]; hb[c] = tmp; }
+            }
           }
-          const float inv = div_generic(1.f, sum);           // one IEEE division per head, then 4 multiplies
-          *reinterpret_cast<float4*>(&ws.heads[lane * 4]) = make_float4(hv[0] * inv, hv[1] * inv, hv[2] * inv, hv[3] * inv);
+          if (TEAMED) {                                      // the helper's partial sums reach the owner through its scratch
+            if (tw == 1) {
+              *reinterpret_cast<float4*>(&wx.heads[lane * 4]) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+              wx.logit[64 + lane] = sum;
+            }
+            team_sync(team_bar);
+            if (tw == 0) {
+              const float4 o = *reinterpret_cast<const float4*>(&wx.heads[lane * 4]);
+              hb[0] = o.x; hb[1] = o.y; hb[2] = o.z; hb[3] = o.w;
+              sum_b = wx.logit[64 + lane];
+            }
+          }
+          if (tw == 0) {
+            // x + y is commutative, so which accumulator held the even batches does not matter
+            const float inv = div_generic(1.f, sum + sum_b);   // one IEEE division per head, then 4 multiplies
+            *reinterpret_cast<float4*>(&ws.heads[lane * 4]) =
+                make_float4((hv[0] + hb[0]) * inv, (hv[1] + hb[1]) * inv, (hv[2] + hb[2]) * inv, (hv[3] + hb[3]) * inv);
+          }
         }
-        __syncwarp();
+        if (TEAMED) team_sync(team_bar); else __syncwarp();
         RT_MARK(3);
         // ---- logits[i] = heads . lK[j_i] / sqrt(128) -> tanh clip -> / temp  (project_out folded into lK).
         //      8 lanes per node: lane (grp, s8) covers channels 4*s8 + 32*c, c = 0..3; 4 nodes per pass ----
@@ -537,7 +614,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           float4 hq[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) hq[c] = *reinterpret_cast<const float4*>(&ws.heads[s8 * 4 + c * 32]);
-          for (int i0 = 0; i0 < nf; i0 += 16) {            // 4 nodes per sub-pass, 4 sub-passes in flight
+          for (int i0 = tw * 16; i0 < nf; i0 += 16 * TEAM) {   // 4 nodes per sub-pass, 4 sub-passes in flight
             float4 lv[4][4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -566,7 +643,8 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
             }
           }
         }
-        __syncwarp();
+        if (TEAMED) { team_sync(team_bar); if (tw == 1) continue; }     // the helper is done with this row
+        else __syncwarp();
         RT_MARK(4);
         // ---- log_softmax over the list (:403) ----
         float zl[4];
@@ -847,9 +925,6 @@ int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, cons
   const int rows = B * cfg->n_replicas;
   const int mode = forced_actions ? 2 : (cfg->decode_type == EVRP_DECODE_SAMPLE ? 1 : 0);
   const bool coords = (distances == nullptr);
-  auto kern = coords ? (mode == 2 ? rollout_tc_kernel<2, true> : mode == 1 ? rollout_tc_kernel<1, true> : rollout_tc_kernel<0, true>)
-                     : (mode == 2 ? rollout_tc_kernel<2, false> : mode == 1 ? rollout_tc_kernel<1, false> : rollout_tc_kernel<0, false>);
-  EVRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   int dev = 0, sms = 148;
   EVRP_CUDA_OK(cudaGetDevice(&dev));
   EVRP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -871,8 +946,21 @@ int launch_rollout_tc(const evrp_phys* phys, const evrp_decoder_weights* w, cons
   if (pf_lines < 0) { const char* l = getenv("EVRP_PF_LINES"); pf_lines = l ? atoi(l) : (13 | 0x10000); }
   static int walkers = -1;
   if (walkers < 0) { const char* e = getenv("EVRP_WALKERS"); walkers = e ? atoi(e) : NWALK; if (walkers > NWALK) walkers = NWALK; }
+  // two warps per row when every row of the CTA can have its own team (small batches: latency-bound, most warps idle)
+  static int team_knob = -1;             // tuning knob: 1 forces one warp per row
+  if (team_knob < 0) { const char* e = getenv("EVRP_TEAM"); team_knob = e ? atoi(e) : 2; }
+  const bool team2 = team_knob >= 2 && 2 * rows_per_cta <= (walkers & ~1) && walkers >= 2;
+  auto pick = [&](auto coords_c, auto team_c) {
+    constexpr bool C = decltype(coords_c)::value;
+    constexpr int T = decltype(team_c)::value;
+    return mode == 2 ? rollout_tc_kernel<2, C, T> : mode == 1 ? rollout_tc_kernel<1, C, T> : rollout_tc_kernel<0, C, T>;
+  };
+  auto kern = coords ? (team2 ? pick(std::true_type{}, std::integral_constant<int, 2>{}) : pick(std::true_type{}, std::integral_constant<int, 1>{}))
+                     : (team2 ? pick(std::false_type{}, std::integral_constant<int, 2>{}) : pick(std::false_type{}, std::integral_constant<int, 1>{}));
+  EVRP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  const int walkers_l = team2 ? (walkers & ~1) : walkers;
   kern<<<grid, NT, SMEM_BYTES, st>>>(maps, *phys, *w, *cfg, emb, kvl, fixed_ctx, dynamic0, distances, slope, static_xy, elevations, station_ws,
-                                     dem_ws, m_ws, B, S, F, rows, rows_per_cta, pf_lines, walkers, forced_actions, uniforms, pi, ll, reward,
+                                     dem_ws, m_ws, B, S, F, rows, rows_per_cta, pf_lines, walkers_l, forced_actions, uniforms, pi, ll, reward,
                                      energy, saved_mask, saved_veh, steps_used, t_max, status);
   EVRP_LAUNCH_OK();
   return 0;
