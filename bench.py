@@ -99,6 +99,15 @@ def rollout_source_sha256():
     return h.hexdigest()
 
 
+def static_config(N, F, B, world):
+    """the `config` object of both arms (repo and --impl reference): the workload as BASELINE.json states it, nothing measured"""
+    S = N + F + 1
+    return {"workload": f"EM-EVRP-{N} greedy rollout, random-init attention policy (BASELINE configs[3])",
+            "per_gpu_batch": B, "global_batch": B * world, "nodes": N, "stations": F,
+            "l2": "inputs_exceed_l2 (distances+slope+kvl = %.0f MB per step)" % ((2 * S * S + 384 * S) * 4 * B / 1e6),
+            "parallelism": f"dp{world} (instances sharded, no data-path collective)"}
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -284,8 +293,8 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": min(a.warmup, 1), "ms_per_step": 1e3 * t_all / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"EM-EVRP-{a.nodes} greedy rollout, random-init attention policy (BASELINE configs[3])",
-                       "per_step_instances": sample, "nodes": a.nodes, "stations": 5, "decode_steps": T},
+            "config": static_config(a.nodes, 5, a.batch, a.gpus),      # the repo arm's config, key for key
+            "workload_stats": {"decode_steps": T, "per_step_instances": sample},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": f"{sample} instances per step x {a.steps} steps; {note}"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -528,12 +537,9 @@ def main():
         line = {"metric": METRIC, "value": world * B * a.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"EM-EVRP-{N} greedy rollout, random-init attention policy (BASELINE configs[3])",
-                           "per_gpu_batch": B, "global_batch": B * world, "nodes": N, "stations": F,
-                           "decode_steps": T, "mean_steps_per_instance": inst_steps / (a.steps * B),
-                           "mean_feasible_nodes_per_step": mean_feasible,
-                           "l2": "inputs_exceed_l2 (distances+slope+kvl = %.0f MB per step)" % ((2 * S * S + 384 * S) * 4 * B / 1e6),
-                           "parallelism": f"dp{world} (instances sharded, no data-path collective)"},
+                "config": static_config(N, F, B, world),
+                "workload_stats": {"decode_steps": T, "mean_steps_per_instance": inst_steps / (a.steps * B),
+                                   "mean_feasible_nodes_per_step": mean_feasible},
                 "e2e": {"value": world * B * a.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h,
                         "note": "static / dynamic from pinned host memory, tours + costs back to pinned host memory; distances / "
