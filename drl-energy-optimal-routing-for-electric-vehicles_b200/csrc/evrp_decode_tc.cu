@@ -8,10 +8,11 @@
 //   _calc_log_likelihood             nets/DRLModel.py:182-190
 //   update_dynamic / update_mask     problems/EVRP.py:105-280   (fused, bit-exact recipe of evrp_common.cuh)
 //
-// Layout: ONE CTA per SM (576 threads) owns up to RPC = 64 rollout rows for their whole life.
+// Layout: ONE CTA per SM (640 threads) owns up to RPC = 64 rollout rows for their whole life.
 //   warps 0-15   row warps: per-row decode phase; in the FF phase they are the TMEM epilogue / operand converters
-//   warp  16     TMA producer: streams the pre-split fp16 weight planes of FF_tour from L2 (4-stage ring, 32 KB stages)
+//   warp  16     TMA producer: streams the pre-split fp16 weight planes of FF_tour from L2 (3-slot ring, 32 KB stages)
 //   warp  17     MMA issuer: one lane issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = 64, K = 16)
+//   warps 18-19  walk rows only (idle in the FF phase): 56 rows per CTA at batch 8192 = at most 3 rows per warp
 // Per step
 //   1. FF_tour, transposed so that the ROWS are the MMA N dimension (any row count <= 64 costs N/256 of a full tile):
 //        h1^T [512 x rows] = W1max [512 x 128] . m^T      4 M-tiles, A = weight tile (smem, TMA), B = running-max planes
