@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EVRP_B200_LIB") or os.path.join(_HERE, "libevrp_b200.so")   # override: instrumented debug builds (tools/)
 
 EVRP_MAX_S = 128
-ABI_VERSION = 18
+ABI_VERSION = 19
 EVRP_MAX_LAYERS = 8
 ST_NAN_LOGIT, ST_INFEASIBLE_PICK, ST_STEP_CAP, ST_NONUNIFORM_DYNAMIC, ST_NO_FEASIBLE, ST_STUCK_AT_DEPOT = 1, 2, 4, 8, 16, 32
 DECODE_GREEDY, DECODE_SAMPLE = 0, 1
@@ -74,10 +74,11 @@ SIGNATURES = {
                                _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_size_t, _FP]),
     "evrp_rollout_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "evrp_sample_min": (C.c_int, [_FP, _FP, C.c_int, C.c_int, C.c_int, _FP, _FP, _FP, _FP]),
+    "evrp_pointer_logp_saved_floats": (C.c_int, []),
     "evrp_pointer_logp_forward": (C.c_int, [_FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
-                                            _FP, _FP]),
+                                            _FP, _FP, _FP]),
     "evrp_pointer_logp_backward": (C.c_int, [_FP, _FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_float,
-                                             C.c_float, _FP, _FP, _FP]),
+                                             C.c_float, _FP, _FP, _FP, _FP]),
     "evrp_self_attention_forward": (C.c_int, [_FP, C.c_int, C.c_int, _FP, _FP, _FP]),
     "evrp_self_attention_backward": (C.c_int, [_FP, _FP, _FP, _FP, C.c_int, C.c_int, _FP, _FP]),
     "evrp_gemm_3xtf32": (C.c_int, [C.c_int, _FP, C.c_int, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, _FP, _FP,

@@ -25,6 +25,7 @@ namespace lp {
 constexpr int NW_FWD = 8;        // warps per CTA, forward
 constexpr int NW_BWD = 8;        // warps per CTA, backward
 constexpr int CH = 4;            // node records in flight per warp and pass
+constexpr int SAVED = 196;       // floats of saved statistics per (instance, step): heads 128 | (m, l) x 32 lanes | lse | pad
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
@@ -113,7 +114,7 @@ __device__ __forceinline__ int build_list(const uint32_t* __restrict__ mk, unsig
 __global__ void __launch_bounds__(NW_FWD * 32)
 pointer_logp_fwd_kernel(const float* __restrict__ q, const float* __restrict__ kvl, const uint32_t* __restrict__ mask_bits,
                         const int64_t* __restrict__ pi, const int32_t* __restrict__ steps, int T, int S, float clip,
-                        float inv_temp, float* __restrict__ ll) {
+                        float inv_temp, float* __restrict__ ll, float* __restrict__ saved /*[B*T,193] or null*/) {
   __shared__ unsigned char lists[NW_FWD][EVRP_MAX_S];
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* kv = kvl + (size_t)b * S * 384;
@@ -130,6 +131,12 @@ pointer_logp_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k
     const float4 q4 = ldg4(q + bt * D + lane * 4);
     const StepFwd r = step_forward(kv, lists[warp], nf, lane, q4, (int)pi[bt], clip, inv_temp);
     if (lane == 0) ll[bt] = r.z_sel - r.lse;
+    if (saved) {                                   // per-step statistics for the backward: heads | (m, l) per lane | lse
+      float* sv = saved + bt * SAVED;
+      *reinterpret_cast<float4*>(sv + lane * 4) = r.heads;
+      *reinterpret_cast<float2*>(sv + 128 + lane * 2) = make_float2(r.m, r.l);
+      if (lane == 0) sv[192] = r.lse;
+    }
   }
 }
 
@@ -140,7 +147,8 @@ __device__ __forceinline__ void red4(float* p, float x, float y, float z, float 
 __global__ void __launch_bounds__(NW_BWD * 32)
 pointer_logp_bwd_kernel(const float* __restrict__ q, const float* __restrict__ kvl, const uint32_t* __restrict__ mask_bits,
                         const int64_t* __restrict__ pi, const int32_t* __restrict__ steps, const float* __restrict__ grad_ll,
-                        int T, int S, float clip, float inv_temp, float* __restrict__ grad_q, float* __restrict__ grad_kvl) {
+                        int T, int S, float clip, float inv_temp, float* __restrict__ grad_q, float* __restrict__ grad_kvl,
+                        const float* __restrict__ saved /*forward statistics or null (recompute)*/) {
   __shared__ unsigned char lists[NW_BWD][EVRP_MAX_S];
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* kv = kvl + (size_t)b * S * 384;
@@ -161,7 +169,15 @@ pointer_logp_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k
       if (nf > 0) {
         const float4 q4 = ldg4(q + bt * D + lane * 4);
         const int sel = (int)pi[bt];
-        const StepFwd r = step_forward(kv, list, nf, lane, q4, sel, clip, inv_temp);
+        StepFwd r;
+        if (saved) {                               // the forward kept heads / m / l / lse of this step: no recompute passes
+          const float* sv = saved + bt * SAVED;
+          r.heads = ldg4(sv + lane * 4);
+          const float2 ml = __ldg(reinterpret_cast<const float2*>(sv + 128 + lane * 2));
+          r.m = ml.x; r.l = ml.y; r.lse = __ldg(sv + 192); r.z_sel = 0.f;
+        } else {
+          r = step_forward(kv, list, nf, lane, q4, sel, clip, inv_temp);
+        }
         // ---- logits backward: d z_j = g (1[j = sel] - p_j);  through temp, tanh clip, 1/sqrt(d) ----
         float4 dh = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int i0 = 0; i0 < nf; i0 += CH) {
@@ -221,21 +237,23 @@ pointer_logp_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k
 
 extern "C" {
 
+int evrp_pointer_logp_saved_floats(void) { return evrp::lp::SAVED; }
+
 int evrp_pointer_logp_forward(const float* q, const float* kvl, const uint32_t* mask_bits, const int64_t* pi,
                               const int32_t* steps, int B, int T, int S, float tanh_clipping, float temp, float* ll,
-                              void* stream) {
+                              float* saved_stats, void* stream) {
   if (!q || !kvl || !mask_bits || !pi || !steps || !ll || B < 0 || T < 1 || S < 2 || !(temp > 0.f)) return -EVRP_E_BADARG;
   if (S > EVRP_MAX_S) return -EVRP_E_TOO_MANY_NODES;
   if (B == 0) return 0;
   evrp::lp::pointer_logp_fwd_kernel<<<B, evrp::lp::NW_FWD * 32, 0, (cudaStream_t)stream>>>(
-      q, kvl, mask_bits, pi, steps, T, S, tanh_clipping, 1.f / temp, ll);
+      q, kvl, mask_bits, pi, steps, T, S, tanh_clipping, 1.f / temp, ll, saved_stats);
   EVRP_LAUNCH_OK();
   return 0;
 }
 
 int evrp_pointer_logp_backward(const float* q, const float* kvl, const uint32_t* mask_bits, const int64_t* pi,
                                const int32_t* steps, const float* grad_ll, int B, int T, int S, float tanh_clipping,
-                               float temp, float* grad_q, float* grad_kvl, void* stream) {
+                               float temp, float* grad_q, float* grad_kvl, const float* saved_stats, void* stream) {
   if (!q || !kvl || !mask_bits || !pi || !steps || !grad_ll || !grad_q || !grad_kvl || B < 0 || T < 1 || S < 2 ||
       !(temp > 0.f))
     return -EVRP_E_BADARG;
@@ -243,7 +261,7 @@ int evrp_pointer_logp_backward(const float* q, const float* kvl, const uint32_t*
   if (B == 0) return 0;
   EVRP_CUDA_OK(cudaMemsetAsync(grad_kvl, 0, (size_t)B * S * 384 * sizeof(float), (cudaStream_t)stream));
   evrp::lp::pointer_logp_bwd_kernel<<<B, evrp::lp::NW_BWD * 32, 0, (cudaStream_t)stream>>>(
-      q, kvl, mask_bits, pi, steps, grad_ll, T, S, tanh_clipping, 1.f / temp, grad_q, grad_kvl);
+      q, kvl, mask_bits, pi, steps, grad_ll, T, S, tanh_clipping, 1.f / temp, grad_q, grad_kvl, saved_stats);
   EVRP_LAUNCH_OK();
   return 0;
 }

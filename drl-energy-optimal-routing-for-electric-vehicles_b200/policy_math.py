@@ -637,24 +637,29 @@ class PointerLogProb(torch.autograd.Function):
     def forward(ctx, q, kvl, mask_bits, pi, steps, tanh_clipping, temp):
         B, T, _ = q.shape
         S = kvl.shape[1]
+        L = _lib.lib()
         ll = torch.empty(B, T, device=q.device, dtype=torch.float32)
-        _lib.check(_lib.lib().evrp_pointer_logp_forward(
+        # the forward keeps each step's heads / softmax statistics for the backward (193 floats per step: ~120 MB at batch
+        # 1024), which then skips its recompute passes over the K / V / logit-K records
+        saved = torch.empty(B * T, L.evrp_pointer_logp_saved_floats(), device=q.device, dtype=torch.float32) \
+            if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) else None
+        _lib.check(L.evrp_pointer_logp_forward(
             _lib.ptr(q), _lib.ptr(kvl), _lib.ptr(mask_bits), _lib.ptr(pi), _lib.ptr(steps), B, T, S, tanh_clipping, temp,
-            _lib.ptr(ll), _lib.stream_ptr()), "evrp_pointer_logp_forward")
-        ctx.save_for_backward(q, kvl, mask_bits, pi, steps)
+            _lib.ptr(ll), _lib.ptr(saved), _lib.stream_ptr()), "evrp_pointer_logp_forward")
+        ctx.save_for_backward(q, kvl, mask_bits, pi, steps, saved)
         ctx.consts = (tanh_clipping, temp)
         return ll
 
     @staticmethod
     def backward(ctx, g):
-        q, kvl, mask_bits, pi, steps = ctx.saved_tensors
+        q, kvl, mask_bits, pi, steps, saved = ctx.saved_tensors
         B, T, _ = q.shape
         S = kvl.shape[1]
         gq = torch.empty_like(q)
         gk = torch.empty_like(kvl)
         _lib.check(_lib.lib().evrp_pointer_logp_backward(
             _lib.ptr(q), _lib.ptr(kvl), _lib.ptr(mask_bits), _lib.ptr(pi), _lib.ptr(steps), _lib.ptr(g.contiguous()),
-            B, T, S, ctx.consts[0], ctx.consts[1], _lib.ptr(gq), _lib.ptr(gk), _lib.stream_ptr()),
+            B, T, S, ctx.consts[0], ctx.consts[1], _lib.ptr(gq), _lib.ptr(gk), _lib.ptr(saved), _lib.stream_ptr()),
             "evrp_pointer_logp_backward")
         return gq, gk, None, None, None, None, None
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 18
+#define EVRP_ABI_VERSION 19
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -260,14 +260,17 @@ int evrp_reinforce_loss(const float* ll /*[B,T]*/, const float* R /*[B,T]*/, con
  *     glimpse(q) . lK / sqrt(128)) / temp)[pi[b,t]], 0 on padded steps.  backward: d ll -> d q, d kvl.
  *     No [B,H,T,S] tensor is materialised; one CTA per instance, d kvl accumulated in shared memory.
  * ---------------------------------------------------------------------------------------------- */
+/* `saved_stats` (nullable): [B*T, evrp_pointer_logp_saved_floats()] floats where the forward keeps the per-step heads /
+ * softmax maxima and sums / log-sum-exp; handed to the backward it replaces the recompute passes over the records. */
+int evrp_pointer_logp_saved_floats(void);
 int evrp_pointer_logp_forward(const float* q /*[B,T,128]*/, const float* kvl /*[B,S,384]*/,
                               const uint32_t* mask_bits /*[B,T,4]*/, const int64_t* pi /*[B,T]*/,
                               const int32_t* steps /*[B]*/, int B, int T, int S, float tanh_clipping, float temp,
-                              float* ll /*[B,T]*/, void* stream);
+                              float* ll /*[B,T]*/, float* saved_stats, void* stream);
 int evrp_pointer_logp_backward(const float* q, const float* kvl, const uint32_t* mask_bits, const int64_t* pi,
                                const int32_t* steps, const float* grad_ll /*[B,T]*/, int B, int T, int S,
                                float tanh_clipping, float temp, float* grad_q /*[B,T,128]*/,
-                               float* grad_kvl /*[B,S,384]*/, void* stream);
+                               float* grad_kvl /*[B,S,384]*/, const float* saved_stats, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (6) encoder self-attention for the TRAINING path (nets/GraphEncoder.py:81-102 and its autograd backward): fp32 SIMT,
