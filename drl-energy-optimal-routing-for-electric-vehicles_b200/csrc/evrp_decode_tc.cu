@@ -172,6 +172,8 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
   const int nblk = (S + 31) >> 5;
   const float sqrt_d = sqrtf((float)D);
   const bool fastdiv = (phys.div_mode == 0) && (phys.velocity == 50.f);   // call-free look-ahead arithmetic is exact
+  const float w1_inv_scale = w.inv_scales ? __ldg(w.inv_scales) : w.w1_inv_scale;      // device-side packing keeps the scales on the device
+  const float w2_inv_scale = w.inv_scales ? __ldg(w.inv_scales + 1) : w.w2_inv_scale;
 
   if (tid == 0) {
     for (int s = 0; s < WSTAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
@@ -379,7 +381,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           if (i >= n_i) break;
           const int r = cg * 16 + i;
           const float4 vh = *reinterpret_cast<const float4*>(&sm.veh[r][0]);
-          float x = fmaf(__uint_as_float(v[i]), w.w1_inv_scale, fmaf(wv2, vh.z, fmaf(wv1, vh.y, fmaf(wv0, vh.x, bb))));
+          float x = fmaf(__uint_as_float(v[i]), w1_inv_scale, fmaf(wv2, vh.z, fmaf(wv1, vh.y, fmaf(wv0, vh.x, bb))));
           x = fmaxf(x, 0.f);
           const __half hi = __float2half_rn(x);
           const __half lo = __float2half_rn(x - __half2float(hi));
@@ -401,7 +403,7 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
         tmem_ld16(tmem_base + lane_base + TM_D2 + cg * 16, v);
         const int n_i = min(16, rows_per_cta - cg * 16);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) if (i < n_i) ctx[cg * 16 + i][q * 32 + lane] = __uint_as_float(v[i]) * w.w2_inv_scale;
+        for (int i = 0; i < 16; ++i) if (i < n_i) ctx[cg * 16 + i][q * 32 + lane] = __uint_as_float(v[i]) * w2_inv_scale;
       }
       if (tid == 0) sm.next_row = 0;
       FT_MARK(9);

@@ -10,6 +10,7 @@
 //                                  fixed_ctx + emb[now] for all T steps, and their backward (scatter of the gradients to
 //                                  the node that holds the running max / the current node), no [B,T,128] gathers
 //   relu_mask_kernel               g * (y > 0)
+#include <cuda_fp16.h>
 #include "evrp_common.cuh"
 
 namespace evrp {
@@ -236,6 +237,61 @@ __global__ void __launch_bounds__(128) route_context_bwd_kernel(const float* __r
   d_fixed[(size_t)b * D + c] = dfx;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// decoder weight packing on the device (evrp_pack_decoder)
+// ------------------------------------------------------------------------------------------------
+// scratch[0] = max |W1[:, 128:]|, scratch[1] = max |W2| (as float bit patterns: non-negative floats order like unsigned ints)
+__global__ void pack_decoder_amax_kernel(const float* __restrict__ w1, const float* __restrict__ w2, unsigned int* __restrict__ scratch) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;                 // 0 .. 65535 twice
+  float a = 0.f, b = 0.f;
+  if (i < 512 * 128) { a = fabsf(w1[(i >> 7) * 256 + 128 + (i & 127)]); b = fabsf(w2[i]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a = fmaxf(a, __shfl_xor_sync(FULL, a, o)); b = fmaxf(b, __shfl_xor_sync(FULL, b, o)); }
+  if ((threadIdx.x & 31) == 0) { atomicMax(scratch, __float_as_uint(a)); atomicMax(scratch + 1, __float_as_uint(b)); }
+}
+
+__device__ __forceinline__ float pow2_scale(float amax, float& inv) {
+  int e = 0;
+  if (amax > 0.f) { int ex; frexpf(amax, &ex); e = 12 - ex; }
+  e = max(-14, min(24, e));
+  inv = ldexpf(1.f, -e);
+  return ldexpf(1.f, e);
+}
+
+__global__ void pack_decoder_kernel(const float* __restrict__ tour_w, const float* __restrict__ w1, const float* __restrict__ w2,
+                                    const float* __restrict__ scratch, float* __restrict__ w1_veh, float* __restrict__ w1_max,
+                                    float* __restrict__ w2_t, __half* __restrict__ w1h, __half* __restrict__ w1l,
+                                    __half* __restrict__ w2h, __half* __restrict__ w2l, float* __restrict__ inv_scales) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;                 // one thread per element of a 512 x 128 matrix
+  if (i >= 512 * 128) return;
+  float inv1, inv2;
+  const float s1 = pow2_scale(scratch[0], inv1), s2 = pow2_scale(scratch[1], inv2);
+  if (i == 0) { inv_scales[0] = inv1; inv_scales[1] = inv2; }
+  {                                                                    // W1[:, 128:]  [512 out][128 in]
+    const int f = i >> 7, k = i & 127;
+    const float v = w1[f * 256 + 128 + k];
+    w1_max[k * 512 + f] = v;                                           // k-major copy (FFMA kernel)
+    const float ws = v * s1;                                           // exact (power of two)
+    const __half hi = __float2half_rn(ws);
+    w1h[i] = hi; w1l[i] = __float2half_rn(ws - __half2float(hi));
+  }
+  {                                                                    // W2  [128 out][512 in]
+    const int o = i >> 9, k = i & 511;
+    const float v = w2[i];
+    w2_t[k * 128 + o] = v;
+    const float ws = v * s2;
+    const __half hi = __float2half_rn(ws);
+    w2h[i] = hi; w2l[i] = __float2half_rn(ws - __half2float(hi));
+  }
+  if (i < 512 * 3) {                                                   // fold: (W1[:, :128] @ tour.weight)[f][c], fp64 like the host fold
+    const int f = i / 3, c = i % 3;
+    double acc = 0.0;
+    for (int k = 0; k < 128; ++k) acc += (double)w1[f * 256 + k] * (double)tour_w[k * 3 + c];
+    w1_veh[c * 512 + f] = (float)acc;
+  }
+}
+
 }  // namespace trn
 }  // namespace evrp
 
@@ -323,6 +379,21 @@ extern "C" int evrp_route_context_backward(const float* emb, const int64_t* pi, 
   EVRP_CUDA_OK(cudaFuncSetAttribute(trn::route_context_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   trn::route_context_bwd_kernel<<<B, 128, smem, (cudaStream_t)stream>>>(emb, pi, grad_run_max, grad_base, T, S, grad_emb,
                                                                         grad_fixed);
+  EVRP_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int evrp_pack_decoder(const float* tour_w, const float* w1, const float* w2, float* w1_veh, float* w1_max, float* w2_t,
+                                 void* w1max_hi, void* w1max_lo, void* w2_hi, void* w2_lo, float* inv_scales, float* scratch,
+                                 void* stream) {
+  if (!tour_w || !w1 || !w2 || !w1_veh || !w1_max || !w2_t || !w1max_hi || !w1max_lo || !w2_hi || !w2_lo || !inv_scales || !scratch)
+    return -EVRP_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  EVRP_CUDA_OK(cudaMemsetAsync(scratch, 0, 2 * sizeof(float), st));
+  trn::pack_decoder_amax_kernel<<<256, 256, 0, st>>>(w1, w2, reinterpret_cast<unsigned int*>(scratch));
+  EVRP_LAUNCH_OK();
+  trn::pack_decoder_kernel<<<256, 256, 0, st>>>(tour_w, w1, w2, scratch, w1_veh, w1_max, w2_t, (__half*)w1max_hi, (__half*)w1max_lo,
+                                              (__half*)w2_hi, (__half*)w2_lo, inv_scales);
   EVRP_LAUNCH_OK();
   return 0;
 }

@@ -212,25 +212,41 @@ class AttentionModel(nn.Module):
                                   owner.max_load, owner.objective, div_mode=int(getattr(owner, "div_mode", 0)))
         return _lib.make_phys(self.velocity, float(self.start_soc), float(self.t_limit), self.max_load, self.objective)
 
+    def _decoder_tensors(self):
+        """the parameters the decoder half of the packing reads (policy_math.pack_decoder_weights)"""
+        if self.policy == 1:
+            return [self.project_step_context.weight]
+        return [self.tour.weight, self.FF_tour[0].weight, self.FF_tour[0].bias, self.FF_tour[2].weight, self.FF_tour[2].bias]
+
     def packed_weights(self, part="all"):
         """Kernel-side weight layouts (k-major transposes, folded BatchNorm / project_out / tour), rebuilt only
-        when a parameter or buffer changed (tensor version counters).  ``part`` = "encoder" / "decoder" packs (and
-        caches) that half only: a REINFORCE step re-packs just the decoder half after every optimizer step."""
+        when a parameter or buffer they depend on changed (tensor version counters).  The two halves are cached
+        separately: a REINFORCE step re-packs just the decoder half after every optimizer step, and the BatchNorm buffers
+        the encoder forward of that step updates do not invalidate it (``part`` = "encoder" / "decoder" / "all")."""
         sd = self.__dict__.get("_tensor_list")
         if sd is None:                               # walking the module tree costs ~0.6 ms: done once (reset by _apply)
-            sd = list(self.parameters()) + list(self.buffers())
+            sd = (list(self.parameters()) + list(self.buffers()), self._decoder_tensors())
             self.__dict__["_tensor_list"] = sd
-        key = (tuple(t._version for t in sd), tuple(t.data_ptr() for t in sd), self.training, self.gemm_mode, self.ff_mode, self.attn_mode)
         cache = self._pack_cache
-        if cache is None or cache[0] != key:
-            cache = self._pack_cache = (key, {})
-        packed = cache[1]
+        if cache is None:
+            cache = self._pack_cache = {}
         with torch.no_grad():
-            if part in ("all", "encoder") and "enc_struct" not in packed:
-                packed.update(policy_math.pack_encoder_weights(self))
-            if part in ("all", "decoder") and "dec_struct" not in packed:
-                packed.update(policy_math.pack_decoder_weights(self))
-        return packed
+            if part in ("all", "encoder"):
+                key = (tuple(t._version for t in sd[0]), tuple(t.data_ptr() for t in sd[0]), self.training, self.gemm_mode,
+                       self.attn_mode)
+                if cache.get("enc_key") != key:
+                    cache["enc_key"], cache["enc"], cache["all"] = key, policy_math.pack_encoder_weights(self), None
+            if part in ("all", "decoder"):
+                key = (tuple(t._version for t in sd[1]), tuple(t.data_ptr() for t in sd[1]), self.ff_mode)
+                if cache.get("dec_key") != key:
+                    cache["dec_key"], cache["dec"], cache["all"] = key, policy_math.pack_decoder_weights(self), None
+        if part == "encoder":
+            return cache["enc"]
+        if part == "decoder":
+            return cache["dec"]
+        if cache.get("all") is None:
+            cache["all"] = {**cache["enc"], **cache["dec"]}
+        return cache["all"]
 
     def _prepare_inputs(self, input):
         dev = self._device()

@@ -198,6 +198,29 @@ def pack_decoder_weights(model):
         dw.ff_mode = 1
         keep["dec_struct"] = dw
         return keep
+    W1, W2, tw = model.FF_tour[0].weight, model.FF_tour[2].weight, model.tour.weight
+    if W1.is_cuda and W1.dtype == torch.float32 and tuple(W1.shape) == (512, 256) and tuple(W2.shape) == (128, 512) \
+            and tuple(tw.shape) == (128, 3) and W1.is_contiguous() and W2.is_contiguous() and tw.is_contiguous():
+        # product path: two kernels, no host read-back (csrc/evrp_train.cu::pack_decoder_kernel); same values as below
+        d = W1.device
+        bufs = dict(w1_veh=torch.empty(3, 512, device=d), w1_max=torch.empty(128, 512, device=d), w2=torch.empty(512, 128, device=d),
+                    w1max_hi=torch.empty(512, 128, device=d, dtype=torch.float16), w1max_lo=torch.empty(512, 128, device=d, dtype=torch.float16),
+                    w2_hi=torch.empty(128, 512, device=d, dtype=torch.float16), w2_lo=torch.empty(128, 512, device=d, dtype=torch.float16),
+                    inv_scales=torch.empty(2, device=d), pack_scratch=torch.empty(2, device=d))
+        keep.update(bufs)
+        _lib.check(_lib.lib().evrp_pack_decoder(
+            _lib.ptr(tw.detach()), _lib.ptr(W1.detach()), _lib.ptr(W2.detach()), _lib.ptr(bufs["w1_veh"]), _lib.ptr(bufs["w1_max"]),
+            _lib.ptr(bufs["w2"]), _lib.ptr(bufs["w1max_hi"]), _lib.ptr(bufs["w1max_lo"]), _lib.ptr(bufs["w2_hi"]), _lib.ptr(bufs["w2_lo"]),
+            _lib.ptr(bufs["inv_scales"]), _lib.ptr(bufs["pack_scratch"]), _lib.stream_ptr()), "evrp_pack_decoder")
+        dw.w1_veh, dw.w1_max, dw.w2 = _lib.ptr(bufs["w1_veh"]), _lib.ptr(bufs["w1_max"]), _lib.ptr(bufs["w2"])
+        dw.b1, dw.b2 = dev("b1", model.FF_tour[0].bias), dev("b2", model.FF_tour[2].bias)
+        dw.w1max_hi, dw.w1max_lo = _lib.ptr(bufs["w1max_hi"]), _lib.ptr(bufs["w1max_lo"])
+        dw.w2_hi, dw.w2_lo = _lib.ptr(bufs["w2_hi"]), _lib.ptr(bufs["w2_lo"])
+        dw.w1_inv_scale = dw.w2_inv_scale = 1.0
+        dw.inv_scales = _lib.ptr(bufs["inv_scales"])
+        dw.ff_mode = int(getattr(model, "ff_mode", 0))
+        keep["dec_struct"] = dw
+        return keep
     dw.w1_veh = dev("w1_veh", folded_tour_weight(model).t())
     dw.w1_max = dev("w1_max", model.FF_tour[0].weight[:, 128:].t())
     dw.b1 = dev("b1", model.FF_tour[0].bias)

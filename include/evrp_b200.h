@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 19
+#define EVRP_ABI_VERSION 20
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -203,7 +203,19 @@ typedef struct {
                             emb[now] (the fields above).  1: nets/AM.py:336-337  fixed_ctx + project_step_context(
                             [emb[now], load]) = fixed_ctx + step_tab[now] + load * am_w_load: no FF_tour, and the `emb`
                             argument of evrp_rollout is the encoder's step_tab                                   */
+  const float *inv_scales; /* optional DEVICE [2] = {w1_inv_scale, w2_inv_scale}: when set the kernel reads the scales here
+                              (evrp_pack_decoder derives them on the device, so packing needs no host read-back)       */
 } evrp_decoder_weights;
+
+/* Decoder half of the weight packing in two kernels and without a host read-back (a REINFORCE step re-packs it after every
+ * optimizer step): from tour.weight [128,3], FF_tour.0.weight [512,256] / bias, FF_tour.2.weight [128,512] (nn.Linear
+ * layouts, nets/DRLModel.py:89-92) to w1_veh [3,512] = (W1[:, :128] tour.weight)^T folded in fp64, w1_max [128,512] and
+ * w2 [512,128] k-major, the fp16 (hi, lo) planes of W1[:, 128:] and W2 scaled by a power of two chosen from the
+ * largest magnitude (max |s w| ~ 2^12, as evrp_b200/policy_math.py::split_f16), and inv_scales [2] = 1 / s.
+ * `scratch` is 2 device floats (zeroed by the call). */
+int evrp_pack_decoder(const float* tour_w, const float* w1, const float* w2, float* w1_veh, float* w1_max, float* w2_t,
+                      void* w1max_hi, void* w1max_lo, void* w2_hi, void* w2_lo, float* inv_scales, float* scratch,
+                      void* stream);
 
 #define EVRP_DECODE_GREEDY 0
 #define EVRP_DECODE_SAMPLE 1

@@ -961,6 +961,23 @@ def test_route_context_kernels_match_torch(evrp, B, T, S):
     assert float((gf - fixed.grad).abs().max()) < 1e-4 * float(fixed.grad.abs().max())
 
 
+def test_native_decoder_packing_matches_host_packing(evrp, weights):
+    """evrp_pack_decoder (two kernels, scales derived on the device, no host read-back) against the host-side statement of the
+    same packing (policy_math.split_f16 / folded_tour_weight): fp16 planes and scales bit-equal, fold within one ulp"""
+    from evrp_b200 import policy_math as PM
+    m, _ = make_model(evrp, 20, weights)
+    with torch.no_grad():
+        m.FF_tour[2].weight.mul_(37.0)                    # different magnitudes -> different power-of-two scales
+    pk = m.packed_weights("decoder")
+    hi, lo, inv = PM.split_f16(m.FF_tour[0].weight[:, 128:])
+    assert torch.equal(pk["w1max_hi"], hi) and torch.equal(pk["w1max_lo"], lo) and float(pk["inv_scales"][0]) == inv
+    hi, lo, inv = PM.split_f16(m.FF_tour[2].weight)
+    assert torch.equal(pk["w2_hi"], hi) and torch.equal(pk["w2_lo"], lo) and float(pk["inv_scales"][1]) == inv
+    assert torch.equal(pk["w1_max"], m.FF_tour[0].weight[:, 128:].t()) and torch.equal(pk["w2"], m.FF_tour[2].weight.t())
+    fold = PM.folded_tour_weight(m).t()
+    assert float((pk["w1_veh"] - fold).abs().max()) <= 2e-7 * float(fold.abs().max())
+
+
 def test_init_embed_kernels_match_torch(evrp, weights):
     """training-path init embedding (evrp_init_embed_forward / _backward, nets/DRLModel.py:192-200) against the plain PyTorch
     statement: values and the six parameter gradients"""
