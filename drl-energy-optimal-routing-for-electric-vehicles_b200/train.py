@@ -68,7 +68,9 @@ def allreduce_min_int(v):
 
 def global_mean(x):
     """mean over the GLOBAL batch of a per-rank 1-D tensor (loss / baseline means are global, trainer.py:121)"""
-    s = torch.stack([x.sum().double(), torch.tensor(float(x.numel()), dtype=torch.float64, device=x.device)])
+    if world()[1] == 1:
+        return x.mean()                              # one kernel; what the reference computes (reinforce_baselines.py:160)
+    s = torch.stack([x.sum().double(), torch.full((), float(x.numel()), dtype=torch.float64, device=x.device)])
     allreduce_sum_(s)
     return (s[0] / s[1]).to(x.dtype)
 
@@ -314,7 +316,7 @@ def reinforce_step(actor, baseline, optimizer, batch, max_grad_norm=2.0, forced_
         bl_val, bl_loss = bl_val.to(reward.device), 0
     n_global = float(reward.numel())
     if w > 1:                                    # ranks may hold different batch sizes: the mean is over the GLOBAL batch
-        n_t = torch.tensor(n_global, device=reward.device)
+        n_t = torch.full((), n_global, device=reward.device)
         allreduce_sum_(n_t)
         n_global = float(n_t)
     # fused kernel: reward / advantage / loss and d loss / d ll; each rank holds its share of the GLOBAL mean
