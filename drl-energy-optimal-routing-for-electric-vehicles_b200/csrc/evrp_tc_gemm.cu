@@ -34,7 +34,8 @@ constexpr int MAX_STAGES = 4;
 #endif
 constexpr int PLANE = BM * BKB * 4;                  // 16 KB: one [128 x 32] fp32 plane
 constexpr int NTHREADS = 320;
-constexpr int EPI_BIAS = 1, EPI_RELU = 2, EPI_RESID = 4, EPI_AFFINE = 8, EPI_AUX = 16;   // AUX: + aux[m][0..2] . auxw[0..2][n] before the ReLU
+constexpr int EPI_BIAS = 1, EPI_RELU = 2, EPI_RESID = 4, EPI_AFFINE = 8, EPI_AUX = 16, EPI_GATE = 32;
+// AUX: + aux[m][0..2] . auxw[0..2][n] before the ReLU; GATE: the result is kept where resid[m][n] > 0, else 0 (ReLU backward)
 
 constexpr uint32_t IDESC = make_idesc_tf32(128, 128);
 
@@ -312,6 +313,10 @@ gemm3xtf32_kernel(const __grid_constant__ CUtensorMap mapWh, const __grid_consta
                 const float2 rr = __ldg(reinterpret_cast<const float2*>(ep.resid + (size_t)m * ep.ldr + n));
                 v0 += rr.x; v1 += rr.y;
               }
+              if (EPI & EPI_GATE) {                             // gradient through a ReLU whose output is `resid`
+                const float2 rr = __ldg(reinterpret_cast<const float2*>(ep.resid + (size_t)m * ep.ldr + n));
+                v0 = rr.x > 0.f ? v0 : 0.f; v1 = rr.y > 0.f ? v1 : 0.f;
+              }
               if (EPI & EPI_AFFINE) { v0 = fmaf(v0, sc.x, sh.x); v1 = fmaf(v1, sc.y, sh.y); }
               *reinterpret_cast<float2*>(C + (size_t)m * ldc + n) = make_float2(v0, v1);
             }
@@ -428,6 +433,7 @@ int tc_gemm(int epi, const float* A, int lda, const float* Wh, const float* Wl, 
       case EPI_BIAS | EPI_RELU: return launch<true, EPI_BIAS | EPI_RELU>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
       case EPI_RESID | EPI_AFFINE: return launch<true, EPI_RESID | EPI_AFFINE>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
       case EPI_BIAS | EPI_RELU | EPI_AUX: return launch<true, EPI_BIAS | EPI_RELU | EPI_AUX>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
+      case EPI_GATE: return launch<true, EPI_GATE>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
     }
   } else if (epi == (EPI_BIAS | EPI_RESID | EPI_AFFINE)) {
     return launch<false, EPI_BIAS | EPI_RESID | EPI_AFFINE>(mh, ml, ma, A, lda, C, ldc, M, N, K, ep, sm_count, st);
@@ -446,7 +452,7 @@ extern "C" int evrp_gemm_3xtf32(int epilogue, const float* A, int lda, const flo
                                 const float* scale, const float* shift, const float* aux, const float* aux_w, void* stream) {
   using namespace evrp::tc;
   if (!A || !W_hi || !W_lo || !C || M < 0 || N < 1 || K < 1 || lda < K || ldc < N) return -EVRP_E_BADARG;
-  if (((epilogue & EPI_BIAS) && !bias) || ((epilogue & EPI_RESID) && !resid) || ((epilogue & EPI_AFFINE) && (!scale || !shift)) ||
+  if (((epilogue & EPI_BIAS) && !bias) || ((epilogue & (EPI_RESID | EPI_GATE)) && !resid) || ((epilogue & EPI_AFFINE) && (!scale || !shift)) ||
       ((epilogue & EPI_AUX) && (!aux || !aux_w)))
     return -EVRP_E_BADARG;
   if (M == 0) return 0;

@@ -383,8 +383,7 @@ def encode_torch(model, static, dynamic):
             heads_flat = SelfAttention.apply(qkv.view(B, S, 3 * d)).reshape(B * S, d)
             x1 = TCLinear.apply(heads_flat, att.W_out.reshape(-1, d).t(), None, flat, False)        # h + heads @ W_out
             h1 = _batch_norm(bn1, x1, model.training)
-            f = TCLinear.apply(h1, ff[0].weight, ff[0].bias, None, True)
-            x2 = TCLinear.apply(f, ff[2].weight, ff[2].bias, h1, False)                             # h1 + FF(h1)
+            x2 = FeedForwardTC.apply(h1, ff[0].weight, ff[0].bias, ff[2].weight, ff[2].bias, h1)     # h1 + FF(h1)
             h = _batch_norm(bn2, x2, model.training).view(B, S, d)
             continue
         # CPU tensors (tests): the plain PyTorch statement of the same layer
@@ -427,7 +426,7 @@ def split_tf32_planes(W):
     return hi, lo
 
 
-def tc_gemm(x, W, bias=None, resid=None, relu=False, aux=None, aux_w=None):
+def tc_gemm(x, W, bias=None, resid=None, relu=False, aux=None, aux_w=None, gate=None):
     """((x @ W^T + bias + aux @ aux_w^T) [relu] + resid) on the tcgen05 3xTF32 GEMM of csrc/evrp_tc_gemm.cu
     (evrp_gemm_3xtf32).  x [M,K], W [N,K] (nn.Linear layout, any strides), aux [M,3], aux_w [N,3], fp32 CUDA.
     Epilogues the kernel does not instantiate are finished in torch."""
@@ -439,7 +438,10 @@ def tc_gemm(x, W, bias=None, resid=None, relu=False, aux=None, aux_w=None):
     y = torch.empty(M, N, device=x.device, dtype=torch.float32)
     one, zero = _affine_identity(x.device, N)
     epi, post_bias, post_relu, post_resid = 0, None, False, None
-    if aux is not None:
+    if gate is not None:                                   # y * (gate > 0): input gradient through a ReLU (gate = its output)
+        assert bias is None and resid is None and not relu and aux is None and K == 128 and gate.shape == (M, N)
+        epi, resid = 32, gate
+    elif aux is not None:
         assert bias is not None and relu and resid is None and K == 128 and aux.shape == (M, 3) and aux_w.shape == (N, 3)
         epi = 1 | 2 | 16
     elif bias is not None and relu and resid is None and K == 128:
@@ -451,7 +453,7 @@ def tc_gemm(x, W, bias=None, resid=None, relu=False, aux=None, aux_w=None):
     else:
         post_bias, post_relu, post_resid = bias, relu, resid
     b = bias.detach().contiguous() if (epi & 1) else None
-    r = resid.detach().contiguous() if (epi & 4) else None
+    r = resid.detach().contiguous() if (epi & (4 | 32)) else None
     a = aux.detach().contiguous() if (epi & 16) else None
     aw = aux_w.detach().t().contiguous() if (epi & 16) else None          # [3][N]
     _lib.check(_lib.lib().evrp_gemm_3xtf32(epi, _lib.ptr(x), K, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(y), N, M, N, K,
@@ -531,6 +533,31 @@ class TCLinear(torch.autograd.Function):
                 gb = g.sum(0) if want_b else None
                 gaw = g.t() @ aux if want_aw else None
         return gx, gW, gb, (gy if has_resid else None), None, None, gaw
+
+
+class FeedForwardTC(torch.autograd.Function):
+    """y = relu(x W1^T + b1 [+ aux aux_w^T]) W2^T + b2 + resid  (nets/GraphEncoder.py:172-176 with its skip connection;
+    FF_tour of nets/DRLModel.py:233-237 with the vehicle term) as ONE autograd node on the tcgen05 kernels: two forward
+    GEMMs with fused epilogues; backward = input-gradient GEMM through W2 with the ReLU gate in its epilogue, the
+    input-gradient GEMM through W1 and two split-K weight-gradient launches (bias and vehicle-weight rows included)."""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2, resid, aux=None, aux_w=None):
+        f = tc_gemm(x.detach(), W1, b1, None, True, aux, aux_w)
+        y = tc_gemm(f, W2, b2, resid.detach(), False)
+        ctx.save_for_backward(x, W1, W2, f, aux)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W1, W2, f, aux = ctx.saved_tensors
+        gy = gy.contiguous()
+        gf = tc_gemm(gy, W2.t(), gate=f)                                   # d hidden, gated by the ReLU
+        gW2, ga2 = tc_wgrad(gy, f, True)
+        gx = tc_gemm(gf, W1.t()) if ctx.needs_input_grad[0] else None
+        want_aw = aux is not None and ctx.needs_input_grad[7]
+        gW1, ga1 = tc_wgrad(gf, x, True, aux if want_aw else None)
+        return gx, gW1, ga1[0], gW2, ga2[0], gy, None, (ga1[1:].t() if want_aw else None)
 
 
 class BatchNormTrain(torch.autograd.Function):
@@ -707,9 +734,9 @@ def teacher_forced_ll(model, emb, kvl, fixed, pi, mask_bits, veh, steps):
         # GEMM with the vehicle term, bias and ReLU in its epilogue
         run_max, base = RouteContext.apply(emb, fixed, pi, True)
         W1 = model.FF_tour[0]
-        h1 = TCLinear.apply(run_max.view(B * T, d), W1.weight[:, 128:], W1.bias, None, True,
-                            veh.reshape(B * T, 3), folded_tour_weight(model))
-        q = TCLinear.apply(h1, model.FF_tour[2].weight, model.FF_tour[2].bias, base.view(B * T, d), False).view(B, T, d)
+        q = FeedForwardTC.apply(run_max.view(B * T, d), W1.weight[:, 128:], W1.bias, model.FF_tour[2].weight,
+                                model.FF_tour[2].bias, base.view(B * T, d), veh.reshape(B * T, 3),
+                                folded_tour_weight(model)).view(B, T, d)
     else:
         now = torch.cat([torch.zeros_like(pi[:, :1]), pi[:, :-1]], 1)
         emb_now = emb.gather(1, now[..., None].expand(B, T, d))

@@ -296,8 +296,9 @@ int evrp_self_attention_backward(const float* qkv, const float* heads, const flo
 /* ------------------------------------------------------------------------------------------------
  * (7) the encoder's tcgen05 GEMM on its own (training path):  C[M,N] = epilogue( A[M,K] @ W[N,K]^T ), fp32-faithful
  *     3xTF32 (W given as TF32 hi / lo planes in nn.Linear layout [out][in]).  N % 128 == 0.  epilogue bits: 1 bias,
- *     2 ReLU, 4 residual, 8 per-column affine, 16 auxiliary rank-3 term; supported: 0 (any K % 32 == 0), 1|2, 4|8 and
- *     1|2|16 (K == 128), 1|4|8 (K == 512):  C = ((A W^T + bias + aux aux_w) [relu] + resid) * scale + shift with
+ *     2 ReLU, 4 residual, 8 per-column affine, 16 auxiliary rank-3 term, 32 gate (result kept where resid > 0: the
+ *     gradient through a ReLU whose output is `resid`); supported: 0 (any K % 32 == 0), 1|2, 4|8, 1|2|16 and 32
+ *     (K == 128), 1|4|8 (K == 512):  C = ((A W^T + bias + aux aux_w) [relu] + resid) * scale + shift with
  *     aux [M,3] row-major and aux_w [3][N] (the vehicle-scalar term of FF_tour.0, nets/DRLModel.py:215-235).
  *     evrp_split_tf32 builds the planes from a weight with arbitrary strides (a transposed view for the input-gradient
  *     product): hi = rna_tf32(w), lo = rna_tf32(w - hi), dense [rows][cols].

@@ -961,6 +961,38 @@ def test_route_context_kernels_match_torch(evrp, B, T, S):
     assert float((gf - fixed.grad).abs().max()) < 1e-4 * float(fixed.grad.abs().max())
 
 
+@pytest.mark.parametrize("with_aux", [False, True])
+def test_feed_forward_node_matches_fp64(evrp, with_aux):
+    """policy_math.FeedForwardTC (FF1 + ReLU + FF2 + skip as one autograd node: gated input-gradient GEMM, weight-gradient
+    kernel) against the fp64 statement, with and without the rank-3 vehicle term of FF_tour"""
+    from evrp_b200 import policy_math as PM
+    gen = torch.Generator(device="cpu").manual_seed(21)
+    M = 2777
+    x = torch.randn(M, 128, generator=gen).cuda().requires_grad_(True)
+    W1 = (torch.randn(512, 128, generator=gen) / 11).cuda().requires_grad_(True)
+    b1 = torch.randn(512, generator=gen).cuda().requires_grad_(True)
+    W2 = (torch.randn(128, 512, generator=gen) / 23).cuda().requires_grad_(True)
+    b2 = torch.randn(128, generator=gen).cuda().requires_grad_(True)
+    r = torch.randn(M, 128, generator=gen).cuda().requires_grad_(True)
+    aux = torch.rand(M, 3, generator=gen).cuda() if with_aux else None
+    aw = torch.randn(512, 3, generator=gen).cuda().requires_grad_(True) if with_aux else None
+    w = torch.randn(M, 128, generator=gen).cuda()
+    ps = [t for t in (x, W1, b1, W2, b2, r, aw) if t is not None]
+    y = PM.FeedForwardTC.apply(x, W1, b1, W2, b2, r, aux, aw)
+    (y * w).sum().backward()
+    got = [t.grad.clone() for t in ps]
+    for t in ps:
+        t.grad = None
+    pre = x.double() @ W1.double().t() + b1.double()
+    if with_aux:
+        pre = pre + aux.double() @ aw.double().t()
+    ref = torch.relu(pre) @ W2.double().t() + b2.double() + r.double()
+    (ref * w.double()).sum().backward()
+    assert float((y.double() - ref).abs().max()) < 6e-6 * max(1.0, float(ref.abs().max()))
+    for g, t in zip(got, ps):
+        assert float((g.double() - t.grad.double()).norm() / t.grad.double().norm()) < 1e-5
+
+
 def test_native_decoder_packing_matches_host_packing(evrp, weights):
     """evrp_pack_decoder (two kernels, scales derived on the device, no host read-back) against the host-side statement of the
     same packing (policy_math.split_f16 / folded_tour_weight): fp16 planes and scales bit-equal, fold within one ulp"""
