@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EVRP_B200_LIB") or os.path.join(_HERE, "libevrp_b200.so")   # override: instrumented debug builds (tools/)
 
 EVRP_MAX_S = 128
-ABI_VERSION = 20
+ABI_VERSION = 21
 EVRP_MAX_LAYERS = 8
 ST_NAN_LOGIT, ST_INFEASIBLE_PICK, ST_STEP_CAP, ST_NONUNIFORM_DYNAMIC, ST_NO_FEASIBLE, ST_STUCK_AT_DEPOT = 1, 2, 4, 8, 16, 32
 DECODE_GREEDY, DECODE_SAMPLE = 0, 1
@@ -46,7 +46,7 @@ class DecoderWeights(C.Structure):
     _fields_ = [(n, _FP) for n in ("w1_veh", "w1_max", "b1", "w2", "b2", "w1max_hi", "w1max_lo", "w2_hi", "w2_lo",
                                    "am_w_load")] + \
         [("w1_inv_scale", C.c_float), ("w2_inv_scale", C.c_float), ("ff_mode", C.c_int32), ("policy", C.c_int32),
-         ("inv_scales", _FP)]
+         ("inv_scales", _FP), ("ff_stream", _FP)]
 
 
 class RolloutCfg(C.Structure):
@@ -95,7 +95,7 @@ SIGNATURES = {
     "evrp_route_context_forward": (C.c_int, [_FP, _FP, _FP, C.c_int, C.c_int, C.c_int, _FP, _FP, _FP]),
     "evrp_route_context_backward": (C.c_int, [_FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, _FP, _FP, _FP]),
     "evrp_relu_mask": (C.c_int, [_FP, _FP, _FP, C.c_longlong, _FP]),
-    "evrp_pack_decoder": (C.c_int, [_FP] * 13),
+    "evrp_pack_decoder": (C.c_int, [_FP] * 14),
     "evrp_init_embed_forward": (C.c_int, [_FP, _FP, C.c_int, C.c_int, C.c_int, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP]),
     "evrp_init_embed_backward_workspace_bytes": (C.c_size_t, []),
     "evrp_init_embed_backward": (C.c_int, [_FP, _FP, _FP, C.c_int, C.c_int, C.c_int, _FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_size_t,

@@ -134,6 +134,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // the two warps of a row team (TEAM == 2) meet here; orders their shared-memory traffic
 __device__ __forceinline__ void team_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
@@ -288,7 +293,11 @@ rollout_tc_kernel(const __grid_constant__ Maps maps, evrp_phys phys, evrp_decode
           mbar_wait(&sm.empty[s], ((it / WSTAGES) & 1) ^ 1);
           unsigned char* st = ring + s * WSTAGE;
           mbar_expect_tx(&sm.full[s], WSTAGE);
-          if (i < 8) {
+          if (w.ff_stream) {
+            // pre-swizzled stream: the stage is ONE contiguous 32 KB bulk copy (as 2 x 128 strided 128-byte rows the
+            // tensor copy took ~0.65 us per stage and set the length of the whole FF phase)
+            bulk_load(st, reinterpret_cast<const unsigned char*>(w.ff_stream) + (size_t)i * WSTAGE, WSTAGE, &sm.full[s]);
+          } else if (i < 8) {
             tma_load_2d(st, &maps.w1h, &sm.full[s], (i & 1) * 64, (i >> 1) * 128);
             tma_load_2d(st + WPLANE, &maps.w1l, &sm.full[s], (i & 1) * 64, (i >> 1) * 128);
           } else {

@@ -262,7 +262,8 @@ __device__ __forceinline__ float pow2_scale(float amax, float& inv) {
 __global__ void pack_decoder_kernel(const float* __restrict__ tour_w, const float* __restrict__ w1, const float* __restrict__ w2,
                                     const float* __restrict__ scratch, float* __restrict__ w1_veh, float* __restrict__ w1_max,
                                     float* __restrict__ w2_t, __half* __restrict__ w1h, __half* __restrict__ w1l,
-                                    __half* __restrict__ w2h, __half* __restrict__ w2l, float* __restrict__ inv_scales) {
+                                    __half* __restrict__ w2h, __half* __restrict__ w2l, float* __restrict__ inv_scales,
+                                    __half* __restrict__ ffs) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;                 // one thread per element of a 512 x 128 matrix
   if (i >= 512 * 128) return;
   float inv1, inv2;
@@ -274,7 +275,13 @@ __global__ void pack_decoder_kernel(const float* __restrict__ tour_w, const floa
     w1_max[k * 512 + f] = v;                                           // k-major copy (FFMA kernel)
     const float ws = v * s1;                                           // exact (power of two)
     const __half hi = __float2half_rn(ws);
-    w1h[i] = hi; w1l[i] = __float2half_rn(ws - __half2float(hi));
+    const __half lo = __float2half_rn(ws - __half2float(hi));
+    w1h[i] = hi; w1l[i] = lo;
+    if (ffs) {                                                         // stage (f / 128, k / 64): [hi 8192 | lo 8192] halfs
+      const int r = f & 127, kk = k & 63;
+      const int off = ((f >> 7) * 2 + (k >> 6)) * 16384 + r * 64 + ((((kk >> 3) ^ (r & 7)) << 3) | (kk & 7));
+      ffs[off] = hi; ffs[off + 8192] = lo;
+    }
   }
   {                                                                    // W2  [128 out][512 in]
     const int o = i >> 9, k = i & 511;
@@ -282,7 +289,13 @@ __global__ void pack_decoder_kernel(const float* __restrict__ tour_w, const floa
     w2_t[k * 128 + o] = v;
     const float ws = v * s2;
     const __half hi = __float2half_rn(ws);
-    w2h[i] = hi; w2l[i] = __float2half_rn(ws - __half2float(hi));
+    const __half lo = __float2half_rn(ws - __half2float(hi));
+    w2h[i] = hi; w2l[i] = lo;
+    if (ffs) {                                                         // stage 8 + k / 64
+      const int kk = k & 63;
+      const int off = (8 + (k >> 6)) * 16384 + o * 64 + ((((kk >> 3) ^ (o & 7)) << 3) | (kk & 7));
+      ffs[off] = hi; ffs[off + 8192] = lo;
+    }
   }
   if (i < 512 * 3) {                                                   // fold: (W1[:, :128] @ tour.weight)[f][c], fp64 like the host fold
     const int f = i / 3, c = i % 3;
@@ -385,7 +398,7 @@ extern "C" int evrp_route_context_backward(const float* emb, const int64_t* pi, 
 
 extern "C" int evrp_pack_decoder(const float* tour_w, const float* w1, const float* w2, float* w1_veh, float* w1_max, float* w2_t,
                                  void* w1max_hi, void* w1max_lo, void* w2_hi, void* w2_lo, float* inv_scales, float* scratch,
-                                 void* stream) {
+                                 void* ff_stream, void* stream) {
   if (!tour_w || !w1 || !w2 || !w1_veh || !w1_max || !w2_t || !w1max_hi || !w1max_lo || !w2_hi || !w2_lo || !inv_scales || !scratch)
     return -EVRP_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
@@ -393,7 +406,7 @@ extern "C" int evrp_pack_decoder(const float* tour_w, const float* w1, const flo
   trn::pack_decoder_amax_kernel<<<256, 256, 0, st>>>(w1, w2, reinterpret_cast<unsigned int*>(scratch));
   EVRP_LAUNCH_OK();
   trn::pack_decoder_kernel<<<256, 256, 0, st>>>(tour_w, w1, w2, scratch, w1_veh, w1_max, w2_t, (__half*)w1max_hi, (__half*)w1max_lo,
-                                              (__half*)w2_hi, (__half*)w2_lo, inv_scales);
+                                              (__half*)w2_hi, (__half*)w2_lo, inv_scales, (__half*)ff_stream);
   EVRP_LAUNCH_OK();
   return 0;
 }

@@ -65,6 +65,21 @@ def split_f16(w):
     return hi.contiguous(), lo.contiguous(), 2.0 ** (-e)
 
 
+def pack_ff_stream(w1_hi, w1_lo, w2_hi, w2_lo):
+    """The four fp16 planes of FF_tour (W1[:, 128:] [512,128], W2 [128,512]) as the ONE 512 KB stream the rollout kernel
+    consumes (include/evrp_b200.h ``ff_stream``): 16 stages x (hi | lo) of [128 rows][64 halfs] tiles with the 128-byte
+    shared-memory swizzle applied (16-byte chunk c of row r stored at c ^ (r & 7))."""
+    def tiles(p, n_row_tiles, n_kb):          # [rows, K] -> [row tile, K block, 128, 8 chunks, 8]
+        t = p.reshape(n_row_tiles, 128, n_kb, 8, 8).permute(0, 2, 1, 3, 4)
+        r = torch.arange(128, device=p.device)[:, None]
+        c = torch.arange(8, device=p.device)[None, :]
+        src = (c ^ (r & 7))[None, None, :, :, None].expand_as(t)          # dest chunk c holds source chunk c ^ (r & 7)
+        return torch.gather(t, 3, src)
+    a = torch.stack([tiles(w1_hi, 4, 2), tiles(w1_lo, 4, 2)], 2)           # [4, 2, plane, 128, 8, 8]
+    b = torch.stack([tiles(w2_hi, 1, 8), tiles(w2_lo, 1, 8)], 2)           # [1, 8, plane, 128, 8, 8]
+    return torch.cat([a.reshape(-1), b.reshape(-1)]).contiguous()
+
+
 FUSED_LP = 1280          # floats of fused_params per layer (csrc/evrp_encoder_fused.cu)
 
 
@@ -206,12 +221,15 @@ def pack_decoder_weights(model):
         bufs = dict(w1_veh=torch.empty(3, 512, device=d), w1_max=torch.empty(128, 512, device=d), w2=torch.empty(512, 128, device=d),
                     w1max_hi=torch.empty(512, 128, device=d, dtype=torch.float16), w1max_lo=torch.empty(512, 128, device=d, dtype=torch.float16),
                     w2_hi=torch.empty(128, 512, device=d, dtype=torch.float16), w2_lo=torch.empty(128, 512, device=d, dtype=torch.float16),
-                    inv_scales=torch.empty(2, device=d), pack_scratch=torch.empty(2, device=d))
+                    inv_scales=torch.empty(2, device=d), pack_scratch=torch.empty(2, device=d),
+                    ff_stream=torch.empty(16 * 16384, device=d, dtype=torch.float16))
         keep.update(bufs)
         _lib.check(_lib.lib().evrp_pack_decoder(
             _lib.ptr(tw.detach()), _lib.ptr(W1.detach()), _lib.ptr(W2.detach()), _lib.ptr(bufs["w1_veh"]), _lib.ptr(bufs["w1_max"]),
             _lib.ptr(bufs["w2"]), _lib.ptr(bufs["w1max_hi"]), _lib.ptr(bufs["w1max_lo"]), _lib.ptr(bufs["w2_hi"]), _lib.ptr(bufs["w2_lo"]),
-            _lib.ptr(bufs["inv_scales"]), _lib.ptr(bufs["pack_scratch"]), _lib.stream_ptr()), "evrp_pack_decoder")
+            _lib.ptr(bufs["inv_scales"]), _lib.ptr(bufs["pack_scratch"]), _lib.ptr(bufs["ff_stream"]), _lib.stream_ptr()),
+            "evrp_pack_decoder")
+        dw.ff_stream = _lib.ptr(bufs["ff_stream"])
         dw.w1_veh, dw.w1_max, dw.w2 = _lib.ptr(bufs["w1_veh"]), _lib.ptr(bufs["w1_max"]), _lib.ptr(bufs["w2"])
         dw.b1, dw.b2 = dev("b1", model.FF_tour[0].bias), dev("b2", model.FF_tour[2].bias)
         dw.w1max_hi, dw.w1max_lo = _lib.ptr(bufs["w1max_hi"]), _lib.ptr(bufs["w1max_lo"])
@@ -232,8 +250,10 @@ def pack_decoder_weights(model):
         return _lib.ptr(t) if t.is_cuda else None
     hi, lo, inv = split_f16(model.FF_tour[0].weight[:, 128:])
     dw.w1max_hi, dw.w1max_lo, dw.w1_inv_scale = dev_raw("w1max_hi", hi), dev_raw("w1max_lo", lo), inv
-    hi, lo, inv = split_f16(model.FF_tour[2].weight)
-    dw.w2_hi, dw.w2_lo, dw.w2_inv_scale = dev_raw("w2_hi", hi), dev_raw("w2_lo", lo), inv
+    hi2, lo2, inv = split_f16(model.FF_tour[2].weight)
+    dw.w2_hi, dw.w2_lo, dw.w2_inv_scale = dev_raw("w2_hi", hi2), dev_raw("w2_lo", lo2), inv
+    if tuple(hi.shape) == (512, 128) and tuple(hi2.shape) == (128, 512):
+        dw.ff_stream = dev_raw("ff_stream", pack_ff_stream(hi, lo, hi2, lo2))
     dw.ff_mode = int(getattr(model, "ff_mode", 0))
     keep["dec_struct"] = dw
     return keep

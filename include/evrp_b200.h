@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 20
+#define EVRP_ABI_VERSION 21
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -205,17 +205,23 @@ typedef struct {
                             argument of evrp_rollout is the encoder's step_tab                                   */
   const float *inv_scales; /* optional DEVICE [2] = {w1_inv_scale, w2_inv_scale}: when set the kernel reads the scales here
                               (evrp_pack_decoder derives them on the device, so packing needs no host read-back)       */
+  const void *ff_stream;   /* optional: the same four fp16 planes as ONE 512 KB stream in the order the rollout kernel consumes
+                              them: 16 stages x (hi 16 KB | lo 16 KB), stage i < 8 = rows 128(i/2).. of W1[:, 128:], K block
+                              i%2 (64 inputs); stage 8 + k = W2, K block k; every 16 KB plane is a [128 rows][128 B] tile with
+                              the 128-byte shared-memory swizzle already applied (16-byte chunk c of row r sits at c ^ (r & 7)).
+                              When set, a stage is ONE contiguous 32 KB bulk copy instead of 256 strided 128-byte rows        */
 } evrp_decoder_weights;
 
 /* Decoder half of the weight packing in two kernels and without a host read-back (a REINFORCE step re-packs it after every
  * optimizer step): from tour.weight [128,3], FF_tour.0.weight [512,256] / bias, FF_tour.2.weight [128,512] (nn.Linear
  * layouts, nets/DRLModel.py:89-92) to w1_veh [3,512] = (W1[:, :128] tour.weight)^T folded in fp64, w1_max [128,512] and
  * w2 [512,128] k-major, the fp16 (hi, lo) planes of W1[:, 128:] and W2 scaled by a power of two chosen from the
- * largest magnitude (max |s w| ~ 2^12, as evrp_b200/policy_math.py::split_f16), and inv_scales [2] = 1 / s.
+ * largest magnitude (max |s w| ~ 2^12, as evrp_b200/policy_math.py::split_f16), inv_scales [2] = 1 / s, and the stream form
+ * of the planes (ff_stream).
  * `scratch` is 2 device floats (zeroed by the call). */
 int evrp_pack_decoder(const float* tour_w, const float* w1, const float* w2, float* w1_veh, float* w1_max, float* w2_t,
                       void* w1max_hi, void* w1max_lo, void* w2_hi, void* w2_lo, float* inv_scales, float* scratch,
-                      void* stream);
+                      void* ff_stream /* 512 KB, nullable: evrp_decoder_weights.ff_stream */, void* stream);
 
 #define EVRP_DECODE_GREEDY 0
 #define EVRP_DECODE_SAMPLE 1

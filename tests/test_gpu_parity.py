@@ -1003,8 +1003,10 @@ def test_native_decoder_packing_matches_host_packing(evrp, weights):
     pk = m.packed_weights("decoder")
     hi, lo, inv = PM.split_f16(m.FF_tour[0].weight[:, 128:])
     assert torch.equal(pk["w1max_hi"], hi) and torch.equal(pk["w1max_lo"], lo) and float(pk["inv_scales"][0]) == inv
-    hi, lo, inv = PM.split_f16(m.FF_tour[2].weight)
-    assert torch.equal(pk["w2_hi"], hi) and torch.equal(pk["w2_lo"], lo) and float(pk["inv_scales"][1]) == inv
+    hi2, lo2, inv = PM.split_f16(m.FF_tour[2].weight)
+    assert torch.equal(pk["w2_hi"], hi2) and torch.equal(pk["w2_lo"], lo2) and float(pk["inv_scales"][1]) == inv
+    # the stream form the rollout kernel consumes (contiguous pre-swizzled 32 KB stages)
+    assert torch.equal(pk["ff_stream"], PM.pack_ff_stream(hi, lo, hi2, lo2))
     assert torch.equal(pk["w1_max"], m.FF_tour[0].weight[:, 128:].t()) and torch.equal(pk["w2"], m.FF_tour[2].weight.t())
     fold = PM.folded_tour_weight(m).t()
     assert float((pk["w1_veh"] - fold).abs().max()) <= 2e-7 * float(fold.abs().max())

@@ -1,7 +1,9 @@
 // Micro-benchmark (B200): tensor-memory read bandwidth (tcgen05.ld) and tcgen05.mma issue rates, alone and together.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/_build/tmem_bench tools/tmem_bench.cu -lcuda
 // mode bits: 1 = 16 reader warps, 2 = 4 reader warps (one per SM sub-partition), 4 = MMA warp (A from TMEM, N=128),
-//            8 = MMA with A from shared memory, 16 = MMA N=16 (A from TMEM), 32 = MMA N=256 (A from TMEM)
+//            8 = MMA with A from shared memory, 16 = MMA N=16 (A from TMEM), 32 = MMA N=256 (A from TMEM),
+//            64 = MMA N=64, A from shared memory, ONE accumulator (the FF_tour shape of the rollout kernel),
+//            128 = the same with the 4 MMAs of a round going to 4 different accumulators
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -68,10 +70,10 @@ __global__ void __launch_bounds__(576, 1) bench(int mode, int iters, long long* 
       if (acc == 0x12345678u) sink[threadIdx.x] = acc;
       if (threadIdx.x == 0) out[0] = clock64() - t0;
     }
-  } else if (warp == 16 && (mode & (4 | 8 | 16 | 32))) {
+  } else if (warp == 16 && (mode & (4 | 8 | 16 | 32 | 64 | 128))) {
     uint32_t pred;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    const int n = (mode & 16) ? 16 : (mode & 32) ? 256 : 128;
+    const int n = (mode & 16) ? 16 : (mode & 32) ? 256 : (mode & (64 | 128)) ? 64 : 128;
     const uint32_t idesc = idesc_f16(128, n);
     const uint64_t db = umma_desc(smem_u32(smem)), da = umma_desc(smem_u32(smem) + 32768);
     const uint32_t d = tb + 256, a = tb;           // D columns 256.. (up to 256 wide), A planes at columns 0..
@@ -79,7 +81,9 @@ __global__ void __launch_bounds__(576, 1) bench(int mode, int iters, long long* 
       for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          if (mode & 8) mma_ss(d, da + 2 * k, db + 2 * k, 1u, idesc);
+          if (mode & 64) mma_ss(d, da + 2 * k, db + 2 * k, 1u, idesc);
+          else if (mode & 128) mma_ss(d + 64 * k, da + 2 * k, db + 2 * k, 1u, idesc);
+          else if (mode & 8) mma_ss(d, da + 2 * k, db + 2 * k, 1u, idesc);
           else mma_ts(d, a + 8 * k, db + 2 * k, 1u, idesc);
         }
       }
@@ -99,7 +103,7 @@ int main() {
   cudaMalloc(&out, 16); cudaMalloc(&sink, 4096);
   cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int iters = 2000;
-  const int modes[] = {1, 2, 4, 8, 16, 32, 1 | 4, 2 | 4, 1 | 8, 1 | 16, 1 | 32};
+  const int modes[] = {1, 2, 4, 8, 16, 32, 64, 128, 1 | 4, 2 | 4, 1 | 8, 1 | 16, 1 | 32};
   for (int mode : modes) {
     long long h[2] = {0, 0};
     cudaMemset(out, 0, 16);
