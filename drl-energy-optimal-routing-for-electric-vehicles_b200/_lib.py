@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EVRP_B200_LIB") or os.path.join(_HERE, "libevrp_b200.so")   # override: instrumented debug builds (tools/)
 
 EVRP_MAX_S = 128
-ABI_VERSION = 21
+ABI_VERSION = 22
 EVRP_MAX_LAYERS = 8
 ST_NAN_LOGIT, ST_INFEASIBLE_PICK, ST_STEP_CAP, ST_NONUNIFORM_DYNAMIC, ST_NO_FEASIBLE, ST_STUCK_AT_DEPOT = 1, 2, 4, 8, 16, 32
 DECODE_GREEDY, DECODE_SAMPLE = 0, 1
@@ -100,7 +100,7 @@ SIGNATURES = {
     "evrp_init_embed_backward_workspace_bytes": (C.c_size_t, []),
     "evrp_init_embed_backward": (C.c_int, [_FP, _FP, _FP, C.c_int, C.c_int, C.c_int, _FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_size_t,
                                            _FP]),
-    "evrp_reinforce_loss": (C.c_int, [_FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_float, _FP, _FP, _FP, _FP, _FP, _FP]),
+    "evrp_reinforce_loss": (C.c_int, [_FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_float, _FP, _FP, _FP, _FP, _FP, _FP, _FP]),
 }
 
 _lib = None

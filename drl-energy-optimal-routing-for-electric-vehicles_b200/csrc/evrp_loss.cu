@@ -11,8 +11,10 @@ namespace evrp {
 
 __global__ void __launch_bounds__(256)
 reinforce_rows_kernel(const float* __restrict__ ll, const float* __restrict__ R, const float* __restrict__ baseline,
-                      int baseline_is_scalar, int B, int T, float inv_global_batch, float* __restrict__ reward,
-                      float* __restrict__ advantage, float* __restrict__ grad_ll, float* __restrict__ term) {
+                      int baseline_is_scalar, int B, int T, float inv_global_batch, const float* __restrict__ n_global_dev,
+                      float* __restrict__ reward, float* __restrict__ advantage, float* __restrict__ grad_ll,
+                      float* __restrict__ term) {
+  if (n_global_dev) inv_global_batch = __fdiv_rn(1.f, *n_global_dev);     // the global batch size stays on the device (multi-rank)
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -29,7 +31,9 @@ reinforce_rows_kernel(const float* __restrict__ ll, const float* __restrict__ R,
 }
 
 __global__ void __launch_bounds__(1024)
-reinforce_reduce_kernel(const float* __restrict__ term, int B, float inv_global_batch, float* __restrict__ loss) {
+reinforce_reduce_kernel(const float* __restrict__ term, int B, float inv_global_batch, const float* __restrict__ n_global_dev,
+                        float* __restrict__ loss) {
+  if (n_global_dev) inv_global_batch = __fdiv_rn(1.f, *n_global_dev);
   __shared__ double part[32];
   double s = 0.0;
   for (int i = threadIdx.x; i < B; i += 1024) s += (double)term[i];
@@ -48,15 +52,15 @@ reinforce_reduce_kernel(const float* __restrict__ term, int B, float inv_global_
 }  // namespace evrp
 
 extern "C" int evrp_reinforce_loss(const float* ll, const float* R, const float* baseline, int baseline_is_scalar, int B,
-                                   int T, float inv_global_batch, float* reward, float* advantage, float* grad_ll,
-                                   float* loss, float* scratch, void* stream) {
+                                   int T, float inv_global_batch, const float* global_batch_dev, float* reward, float* advantage,
+                                   float* grad_ll, float* loss, float* scratch, void* stream) {
   if (!ll || !R || !baseline || !reward || !advantage || !grad_ll || !loss || !scratch || B < 1 || T < 1)
     return -EVRP_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
   evrp::reinforce_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(ll, R, baseline, baseline_is_scalar, B, T, inv_global_batch,
-                                                          reward, advantage, grad_ll, scratch);
+                                                          global_batch_dev, reward, advantage, grad_ll, scratch);
   EVRP_LAUNCH_OK();
-  evrp::reinforce_reduce_kernel<<<1, 1024, 0, st>>>(scratch, B, inv_global_batch, loss);
+  evrp::reinforce_reduce_kernel<<<1, 1024, 0, st>>>(scratch, B, inv_global_batch, global_batch_dev, loss);
   EVRP_LAUNCH_OK();
   return 0;
 }

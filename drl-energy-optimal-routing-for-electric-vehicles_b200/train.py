@@ -277,8 +277,14 @@ class ReinforceLoss(torch.autograd.Function):
         reward, adv, scratch = (torch.empty(B, device=dev) for _ in range(3))
         grad_ll = torch.empty(B, T, device=dev)
         loss = torch.empty(1, device=dev)
+        # ``inv_global_batch``: a Python float (1 / global batch size), or a CUDA scalar tensor holding the global batch SIZE
+        # (multi-rank: the all-reduced count stays on the device, the kernel takes its reciprocal -- no host read-back)
+        n_dev = None
+        if torch.is_tensor(inv_global_batch):
+            n_dev = inv_global_batch.detach().to(dev, torch.float32).reshape(1).contiguous()
+            inv_global_batch = 0.0
         rc = L.evrp_reinforce_loss(_lib.ptr(ll_c), _lib.ptr(R_c), _lib.ptr(bl), int(bl.numel() == 1), B, T,
-                                   float(inv_global_batch), _lib.ptr(reward), _lib.ptr(adv), _lib.ptr(grad_ll),
+                                   float(inv_global_batch), _lib.ptr(n_dev), _lib.ptr(reward), _lib.ptr(adv), _lib.ptr(grad_ll),
                                    _lib.ptr(loss), _lib.ptr(scratch), _lib.stream_ptr())
         _lib.check(rc, "evrp_reinforce_loss")
         ctx.save_for_backward(grad_ll)
@@ -314,13 +320,12 @@ def reinforce_step(actor, baseline, optimizer, batch, max_grad_norm=2.0, forced_
         bl_val, bl_loss = baseline.eval(x, reward)
     else:
         bl_val, bl_loss = bl_val.to(reward.device), 0
-    n_global = float(reward.numel())
-    if w > 1:                                    # ranks may hold different batch sizes: the mean is over the GLOBAL batch
-        n_t = torch.full((), n_global, device=reward.device)
-        allreduce_sum_(n_t)
-        n_global = float(n_t)
+    n_global = 1.0 / float(reward.numel())
+    if w > 1:                                    # ranks may hold different batch sizes: the mean is over the GLOBAL batch;
+        n_global = torch.full((), float(reward.numel()), device=reward.device)     # the count stays on the device
+        allreduce_sum_(n_global)
     # fused kernel: reward / advantage / loss and d loss / d ll; each rank holds its share of the GLOBAL mean
-    loss, reward, advantage = ReinforceLoss.apply(ll, R, bl_val, 1.0 / n_global)
+    loss, reward, advantage = ReinforceLoss.apply(ll, R, bl_val, n_global)
     loss = loss + bl_loss
     optimizer.zero_grad()
     loss.backward()

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define EVRP_ABI_VERSION 21
+#define EVRP_ABI_VERSION 22
 #define EVRP_MAX_S 128          /* mask bits live in 4 x uint32 per instance                         */
 #define EVRP_D 128              /* embedding_dim (trainer.py:261 / run.py --embedding_dim default)   */
 #define EVRP_H 8                /* n_heads (nets/DRLModel.py:52)                                     */
@@ -266,9 +266,11 @@ int evrp_sample_min(const float* reward /*[B*R,Tcap]*/, const int64_t* pi, int B
  *     `baseline` is [B] (rollout baseline) or one scalar (exponential baseline); `scratch` is [B] floats.
  * ---------------------------------------------------------------------------------------------- */
 int evrp_reinforce_loss(const float* ll /*[B,T]*/, const float* R /*[B,T]*/, const float* baseline,
-                        int baseline_is_scalar, int B, int T, float inv_global_batch, float* reward /*[B]*/,
-                        float* advantage /*[B]*/, float* grad_ll /*[B,T]*/, float* loss /*[1]*/, float* scratch /*[B]*/,
-                        void* stream);
+                        int baseline_is_scalar, int B, int T, float inv_global_batch,
+                        const float* global_batch_dev /* nullable: device scalar = global batch size (e.g. all-reduced over
+                                                         ranks); when set, 1 / it replaces inv_global_batch (no host read) */,
+                        float* reward /*[B]*/, float* advantage /*[B]*/, float* grad_ll /*[B,T]*/, float* loss /*[1]*/,
+                        float* scratch /*[B]*/, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (5) teacher-forced decoder log-probabilities and their backward (the differentiable half of

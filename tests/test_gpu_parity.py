@@ -1081,6 +1081,11 @@ def test_fused_reinforce_loss_kernel(evrp):
         assert torch.allclose(reward, R.sum(1), rtol=1e-6) and torch.allclose(adv, R.sum(1) - bl, rtol=1e-5, atol=1e-3)
         assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
         assert torch.allclose(ll.grad, ll2.grad, rtol=1e-5, atol=1e-6)
+        # the global batch size as a device scalar (multi-rank path: no host read-back) gives the same numbers
+        ll3 = ll.detach().clone().requires_grad_(True)
+        loss3, _, _ = T.ReinforceLoss.apply(ll3, R, bl, torch.tensor(74.0, device="cuda"))
+        loss3.backward()
+        assert abs(loss3.item() - loss.item()) <= 1e-6 * abs(loss.item()) and torch.allclose(ll3.grad, ll.grad, rtol=1e-6, atol=0)
 
 
 def test_reinforce_step_runs_and_learns_signal(evrp, weights):
