@@ -179,6 +179,35 @@ def test_weight_packing_and_folds():
     assert m.packed_weights() is not pk                       # version counter invalidates the cache
 
 
+def test_ff_stream_layout_is_the_swizzled_stage_order():
+    """policy_math.pack_ff_stream (host statement of include/evrp_b200.h ``ff_stream``): stage order, (hi | lo) halves and the
+    128-byte swizzle, checked element by element against the definition and against a decoded copy"""
+    g = torch.Generator().manual_seed(3)
+    w1h, w1l = torch.randn(512, 128, generator=g).half(), torch.randn(512, 128, generator=g).half()
+    w2h, w2l = torch.randn(128, 512, generator=g).half(), torch.randn(128, 512, generator=g).half()
+    st = PM.pack_ff_stream(w1h, w1l, w2h, w2l)
+    assert st.dtype == torch.float16 and st.numel() == 16 * 16384                      # 16 stages x 32 KB
+    def at(stage, plane, r, k):                    # k in [0, 64): element of the [128 rows][64 halfs] tile
+        c = (k >> 3) ^ (r & 7)                     # 16-byte chunk position after the swizzle
+        return float(st[stage * 16384 + plane * 8192 + r * 64 + c * 8 + (k & 7)])
+    rs = np.random.RandomState(0)
+    for _ in range(400):
+        f, k = int(rs.randint(512)), int(rs.randint(128))
+        stage = (f >> 7) * 2 + (k >> 6)
+        assert at(stage, 0, f & 127, k & 63) == float(w1h[f, k]) and at(stage, 1, f & 127, k & 63) == float(w1l[f, k])
+        o, k2 = int(rs.randint(128)), int(rs.randint(512))
+        assert at(8 + (k2 >> 6), 0, o, k2 & 63) == float(w2h[o, k2]) and at(8 + (k2 >> 6), 1, o, k2 & 63) == float(w2l[o, k2])
+
+
+def test_bench_arms_print_the_same_config():
+    """bench.py: the repo arm and --impl reference emit the same static `config` object (nothing measured inside it)"""
+    import bench
+    a = bench.static_config(100, 5, 8192, 1)
+    assert a == bench.static_config(100, 5, 8192, 1) and set(a) == {"workload", "per_gpu_batch", "global_batch", "nodes", "stations",
+                                                                     "l2", "parallelism"}
+    assert bench.static_config(100, 5, 8192, 8)["global_batch"] == 65536
+
+
 def test_tf32_split_is_exact_to_fp32_rounding():
     w = torch.randn(512, 128) * 3
     hi, lo = PM.split_tf32(w)
