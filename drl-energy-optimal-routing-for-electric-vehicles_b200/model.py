@@ -329,14 +329,22 @@ class AttentionModel(nn.Module):
                                   float(self.temp), float(self.tanh_clipping), tcap,
                                   (self._sampler_seed() + 0x9E3779B1 * self._calls) & 0xFFFFFFFFFFFFFFFF, n_replicas,
                                   _lib.ptr(static_xy), _lib.ptr(elev))
-            pi = torch.zeros(rows, tcap, dtype=torch.int64, device=dev)
-            ll = torch.zeros(rows, tcap, device=dev)
-            R = torch.zeros(rows, tcap, device=dev)
-            E = torch.zeros(rows, tcap, device=dev)
-            smask = torch.zeros(rows, tcap, 4, dtype=torch.int32, device=dev) if save_trace else None
-            sveh = torch.zeros(rows, tcap, 3, device=dev) if save_trace else None
-            steps = torch.zeros(rows, dtype=torch.int32, device=dev)
-            meta = torch.zeros(2, dtype=torch.int32, device=dev)          # [t_max, status]
+            # every output of the launch out of ONE zero-filled buffer (one allocation, one fill kernel per rollout)
+            n = rows * tcap
+            parts = [("pi", 8 * n), ("ll", 4 * n), ("R", 4 * n), ("E", 4 * n), ("smask", 16 * n if save_trace else 0),
+                     ("sveh", 12 * n if save_trace else 0), ("steps", 4 * rows), ("meta", 8)]
+            offs, total = {}, 0
+            for name, nb in parts:
+                offs[name] = (total, nb)
+                total += (nb + 255) & ~255
+            buf = torch.zeros(total, dtype=torch.uint8, device=dev)
+            piece = lambda name, dtype, shape: buf[offs[name][0]:offs[name][0] + offs[name][1]].view(dtype).view(shape)
+            pi = piece("pi", torch.int64, (rows, tcap))
+            ll, R, E = (piece(k, torch.float32, (rows, tcap)) for k in ("ll", "R", "E"))
+            smask = piece("smask", torch.int32, (rows, tcap, 4)) if save_trace else None
+            sveh = piece("sveh", torch.float32, (rows, tcap, 3)) if save_trace else None
+            steps = piece("steps", torch.int32, (rows,))
+            meta = piece("meta", torch.int32, (2,))                          # [t_max, status]
             ev = None
             if self.profile_events is not None:                   # bench.py: CUDA events around the kernel launch only
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
