@@ -58,14 +58,15 @@ init_embed_kernel(const float* __restrict__ xy, const float* __restrict__ dyn, i
 // g [B*S,128] weighted by (x, y, 1 | x, y, 1 | x, y, demand, 1) per node class.  One CTA = 128 channels x a stride of
 // rows, partial sums per CTA, second kernel sums the CTAs in a fixed order (deterministic).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 init_embed_bwd_kernel(const float* __restrict__ xy, const float* __restrict__ dyn, const float* __restrict__ g, int B, int S,
                       int F, float* __restrict__ partial /*[grid][10][128]*/) {
-  const int c = threadIdx.x;
+  __shared__ float red[3][10][D];
+  const int c = threadIdx.x & 127, rl = threadIdx.x >> 7;              // channel, row lane (4 rows in flight per CTA)
   float a[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const size_t rows = (size_t)B * S;
 #pragma unroll 4
-  for (size_t row = blockIdx.x; row < rows; row += gridDim.x) {
+  for (size_t row = (size_t)blockIdx.x * 4 + rl; row < rows; row += (size_t)gridDim.x * 4) {
     const int j = (int)(row % S);
     const size_t b = row / S;
     const float gv = __ldg(g + row * D + c);
@@ -77,8 +78,15 @@ init_embed_bwd_kernel(const float* __restrict__ xy, const float* __restrict__ dy
       a[6] = fmaf(gv, x, a[6]); a[7] = fmaf(gv, y, a[7]); a[8] = fmaf(gv, dem, a[8]); a[9] += gv;
     }
   }
+  if (rl > 0) {
 #pragma unroll
-  for (int k = 0; k < 10; ++k) partial[((size_t)blockIdx.x * 10 + k) * D + c] = a[k];
+    for (int k = 0; k < 10; ++k) red[rl - 1][k][c] = a[k];
+  }
+  __syncthreads();
+  if (rl == 0) {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) partial[((size_t)blockIdx.x * 10 + k) * D + c] = ((a[k] + red[0][k][c]) + red[1][k][c]) + red[2][k][c];
+  }
 }
 
 __global__ void init_embed_bwd_reduce_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ gw0, float* __restrict__ gb0,
@@ -461,10 +469,10 @@ int evrp_init_embed_backward(const float* static_xy, const float* dynamic, const
       !workspace || B < 1 || S < 2 || F < 1 || F >= S)
     return -EVRP_E_BADARG;
   const long long rows = (long long)B * S;
-  const int grid = (int)(rows < 592 ? rows : 592);
+  const int grid = (int)((rows + 3) / 4 < 592 ? (rows + 3) / 4 : 592);
   if (workspace_bytes < (size_t)grid * 10 * 128 * sizeof(float)) return -EVRP_E_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
-  init_embed_bwd_kernel<<<grid, 128, 0, st>>>(static_xy, dynamic, grad_h, B, S, F, (float*)workspace);
+  init_embed_bwd_kernel<<<grid, 512, 0, st>>>(static_xy, dynamic, grad_h, B, S, F, (float*)workspace);
   EVRP_LAUNCH_OK();
   init_embed_bwd_reduce_kernel<<<10, 128, 0, st>>>((const float*)workspace, grid, g_depot_w, g_depot_b, g_station_w, g_station_b,
                                                    g_cust_w, g_cust_b);
